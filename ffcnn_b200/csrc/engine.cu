@@ -1,0 +1,909 @@
+/*
+ * engine.cu -- device half of the ffcnn.h boundary: the layer loop of net_forward (ffcnn.c:476-520)
+ * re-designed for a B200.
+ *
+ *   reference                                    here
+ *   -------------------------------------------  ------------------------------------------------------
+ *   one image, planar CHW, malloc/free per       batch of frames, NHWC fp32 in one HBM arena planned once
+ *   layer with refcounts (ffcnn.c:481-517)        from the same dependency information (liveness reuse)
+ *   switch(type) -> static C loops                one hand-written sm_100a kernel (or alias) per layer,
+ *                                                 the whole sequence captured in a CUDA graph per batch size
+ *   groupconv() picks a CPU kernel by shape       conv_pick() picks a GPU kernel by the same predicates
+ *   (conv-v6.c:481-502)
+ *   dropout moves a pointer (ffcnn.c:412-416)     dropout / single-input route are aliases: no launch
+ *   yolo decode + nms on the CPU                  GPU candidate filter, exact decode + NMS on the host
+ *
+ * There is deliberately no CPU execution path in this file: without a CUDA device attach fails.
+ */
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "ffb_internal.h"
+#include "../../include/conv.h"
+#include "kernels.cuh"
+#include "pw_ffma.cuh"
+#include "pw_tc.h"
+
+using namespace ffb;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ffb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return -1;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+static int g_num_sms = 148;
+
+static inline int grid_for(long total, int block, int waves = 8)
+{
+    long g = (total + block - 1) / block;
+    long cap = (long)g_num_sms * waves;
+    return (int)std::max<long>(1, std::min(g, cap));
+}
+
+/* =================================================================================== conv operator */
+
+enum ConvKind { CK_GENERIC = 0, CK_PW_FFMA, CK_PW_TC, CK_DW_S1_3, CK_DW_S1_5, CK_DW3_S2, CK_STEM };
+
+struct ffb_conv {
+    int ic, groups, pad, stride, fs, fn, act, row, taps;
+    int dw5_exact, pw_mode;
+    ConvKind kind;
+    const float *d_packed;      /* packed reference rows on device */
+    float *d_owned_packed;      /* set when this op owns d_packed (standalone ops) */
+    float *d_prep;              /* [taps][fn_pad] + scale[fn_pad] + bias[fn_pad] */
+    int fn_pad;
+    /* pointwise FFMA tiling */
+    int TM, TN, NT, TY; size_t smem;
+    PwTcPlan *tc;               /* tcgen05 plan (pw_tc.cu), NULL if not used */
+    char name[48];
+};
+
+static int conv_out_dim(int in, int fs, int pad, int stride) { return (in - fs + 2 * pad) / stride + 1; }
+
+static void conv_pick(ffb_conv *op)
+{
+    const int cpg = op->ic / op->groups;
+    op->kind = CK_GENERIC;
+    if (op->pad == 0 && op->fs == 1 && op->stride == 1 && op->groups == 1 && op->ic % 4 == 0) op->kind = CK_PW_FFMA;
+    else if (cpg == 1 && op->fn == op->ic && op->ic % 4 == 0 && op->stride == 1 && op->fs == 3 && op->pad == 1) op->kind = CK_DW_S1_3;
+    else if (cpg == 1 && op->fn == op->ic && op->ic % 4 == 0 && op->stride == 1 && op->fs == 5 && op->pad == 2) op->kind = CK_DW_S1_5;
+    else if (cpg == 1 && op->fn == op->ic && op->ic % 4 == 0 && op->stride == 2 && op->fs == 3 && op->pad == 1) op->kind = CK_DW3_S2;
+    else if (op->groups == 1 && op->ic == 3 && op->fn == 8 && op->fs == 3 && op->stride == 2 && op->pad == 1) op->kind = CK_STEM;
+}
+
+/* shared-memory footprint of the FFMA pointwise kernel for a given tiling */
+static size_t pw_smem(int K, int BN, int TM, int TY) { return ((size_t)K * BN + 2 * BN + 2 * (size_t)TM * TY * (K + 4)) * sizeof(float); }
+
+static void pw_plan(ffb_conv *op)
+{
+    const int K = op->ic, N = op->fn;
+    op->TN = N > 64 ? 8 : 4;
+    op->NT = (N + op->TN - 1) / op->TN;
+    op->TY = 256 / op->NT;
+    op->fn_pad = op->NT * op->TN;
+    const int tms[4] = { 8, 4, 2, 1 };
+    op->TM = 1;
+    for (int pass = 0; pass < 2; pass++) {
+        const size_t limit = pass == 0 ? 100 * 1024 : 220 * 1024;
+        bool found = false;
+        for (int t = 0; t < 4; t++) {
+            if (tms[t] * op->TN > 64) continue;
+            if (pw_smem(K, op->fn_pad, tms[t], op->TY) <= limit) { op->TM = tms[t]; found = true; break; }
+        }
+        if (found) break;
+    }
+    op->smem = pw_smem(K, op->fn_pad, op->TM, op->TY);
+}
+
+template <int TM, int TN>
+static cudaError_t pw_launch(const PwArgs &a, int grid, size_t smem, cudaStream_t st)
+{
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_pw_ffma<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_pw_ffma<TM, TN><<<grid, 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+static int conv_prepare(ffb_conv *op, cudaStream_t st)
+{
+    conv_pick(op);
+    op->taps = op->fs * op->fs * (op->ic / op->groups);
+    op->row  = FFB_ALIGN(op->taps, 4) + 4;
+    op->fn_pad = FFB_ALIGN(op->fn, 4);
+    op->tc = NULL;
+    if (op->kind == CK_PW_FFMA) {
+        pw_plan(op);
+        if (op->pw_mode != 1) {
+            op->tc = pw_tc_plan_create(op->ic, op->fn, op->act, op->pw_mode);
+            if (op->tc) op->kind = CK_PW_TC;
+        }
+    }
+    const char *names[] = { "conv_generic", "pw_ffma", "pw_tcgen05", "dw3x3_s1", "dw5x5_s1", "dw3x3_s2", "stem3x3_s2" };
+    snprintf(op->name, sizeof op->name, "%s", names[op->kind]);
+    if (op->kind == CK_PW_TC) snprintf(op->name, sizeof op->name, "pw_tcgen05_%s", pw_tc_mode_name(op->tc));
+    if (op->kind == CK_GENERIC) return 0;
+    const size_t nfl = (size_t)op->taps * op->fn_pad + 2 * op->fn_pad;
+    if (!op->d_prep) CK(cudaMalloc(&op->d_prep, nfl * sizeof(float)));
+    float *wt = op->d_prep, *sc = wt + (size_t)op->taps * op->fn_pad, *bi = sc + op->fn_pad;
+    k_prep_weights<<<grid_for((long)nfl, 256), 256, 0, st>>>(op->d_packed, op->row, op->fn, op->taps, op->fn_pad, wt, sc, bi);
+    CK(cudaGetLastError());
+    if (op->tc && pw_tc_prepare(op->tc, op->d_packed, op->row, st) != 0) return -1;
+    return 0;
+}
+
+static void conv_release(ffb_conv *op)
+{
+    if (!op) return;
+    if (op->tc) pw_tc_plan_destroy(op->tc);
+    cudaFree(op->d_prep);
+    cudaFree(op->d_owned_packed);
+    delete op;
+}
+
+/* in: [n][ih][iw][ldi], out: [n][oh][ow][ldo] written at channel offset coff */
+static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo, int coff,
+                    int n, int ih, int iw, cudaStream_t st)
+{
+    const int oh = conv_out_dim(ih, op->fs, op->pad, op->stride), ow = conv_out_dim(iw, op->fs, op->pad, op->stride);
+    const float *wt = op->d_prep, *sc = wt ? wt + (size_t)op->taps * op->fn_pad : NULL, *bi = sc ? sc + op->fn_pad : NULL;
+    /* conv-v6.c:499 geometry -> its 5x5 path drops kernel row 0 on output row oh-2 (422-441) */
+    const bool v6_dw5 = op->pad == 2 && op->fs == 5 && op->stride == 1 && op->ic / op->groups == 1 && oh >= 4 && ow >= 5;
+    const int skip = (v6_dw5 && !op->dw5_exact) ? oh - 2 : -1;
+    ConvKind kind = op->kind;
+    if ((kind == CK_DW_S1_3 || kind == CK_DW_S1_5 || kind == CK_DW3_S2) && (ldi != op->ic || ldo != op->fn || coff != 0)) kind = CK_GENERIC;
+    if (kind == CK_STEM && (ldi != 4 || ldo != 8 || coff != 0)) kind = CK_GENERIC;
+    switch (kind) {
+    case CK_PW_TC:
+        return pw_tc_run(op->tc, in, ldi, out, ldo, coff, (long)n * ih * iw, st);
+    case CK_PW_FFMA: {
+        PwArgs a; a.in = in; a.out = out; a.wt = wt; a.scale = sc; a.bias = bi; a.M = (long)n * ih * iw; a.K = op->ic; a.N = op->fn;
+        a.ldi = ldi; a.ldo = ldo; a.coff = coff; a.BN = op->fn_pad; a.NT = op->NT; a.TY = op->TY; a.act = op->act;
+        const long tiles = (a.M + (long)op->TM * op->TY - 1) / ((long)op->TM * op->TY);
+        const int per_sm = op->smem <= 100 * 1024 ? 2 : 1;
+        const int grid = (int)std::max<long>(1, std::min<long>(tiles, (long)g_num_sms * per_sm));
+        cudaError_t e = cudaSuccess;
+        if      (op->TM == 8 && op->TN == 8) e = pw_launch<8, 8>(a, grid, op->smem, st);
+        else if (op->TM == 4 && op->TN == 8) e = pw_launch<4, 8>(a, grid, op->smem, st);
+        else if (op->TM == 2 && op->TN == 8) e = pw_launch<2, 8>(a, grid, op->smem, st);
+        else if (op->TM == 1 && op->TN == 8) e = pw_launch<1, 8>(a, grid, op->smem, st);
+        else if (op->TM == 8 && op->TN == 4) e = pw_launch<8, 4>(a, grid, op->smem, st);
+        else if (op->TM == 4 && op->TN == 4) e = pw_launch<4, 4>(a, grid, op->smem, st);
+        else if (op->TM == 2 && op->TN == 4) e = pw_launch<2, 4>(a, grid, op->smem, st);
+        else                                 e = pw_launch<1, 4>(a, grid, op->smem, st);
+        CK(e);
+        return 0; }
+    case CK_DW_S1_3: case CK_DW_S1_5: {
+        const int R = ih >= 64 ? 16 : ih >= 32 ? 10 : ih;
+        dim3 grid((iw * op->ic / 4 + 127) / 128, (ih + R - 1) / R, n);
+        if (kind == CK_DW_S1_3) k_dw_s1<3><<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, R, op->act, -1);
+        else                    k_dw_s1<5><<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, R, op->act, skip);
+        CK(cudaGetLastError());
+        return 0; }
+    case CK_DW3_S2: {
+        const int R = oh >= 40 ? 10 : oh;
+        dim3 grid((ow * op->ic / 4 + 127) / 128, (oh + R - 1) / R, n);
+        k_dw3_s2<<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, oh, ow, R, op->act);
+        CK(cudaGetLastError());
+        return 0; }
+    case CK_STEM: {
+        dim3 grid((ow + 31) / 32, (oh + 7) / 8, n), block(32, 8);
+        k_stem3x3s2<32, 8><<<grid, block, 0, st>>>(in, out, wt, sc, bi, ih, iw, oh, ow, op->act);
+        CK(cudaGetLastError());
+        return 0; }
+    default: {
+        const long total = (long)n * oh * ow * op->fn;
+        k_conv_generic<<<grid_for(total, 256, 16), 256, 0, st>>>(in, out + coff, op->d_packed, n, ih, iw, op->ic, ldi, oh, ow, op->fn, ldo,
+                                                                 op->groups, op->pad, op->stride, op->fs, op->row, op->act, skip);
+        CK(cudaGetLastError());
+        return 0; }
+    }
+}
+
+/* =================================================================================== engine */
+
+struct Tens { int buf = -1; float *p = nullptr; int h = 0, w = 0, c = 0, ld = 0; size_t frame_floats() const { return (size_t)h * w * ld; } };
+
+struct Buf { size_t floats = 0, offset = 0; int first = 0, last = 0; };
+
+struct ffb_engine {
+    ffb_net *net = nullptr;
+    int device = 0, max_batch = 0, batch = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    float *d_packed = nullptr;
+    std::vector<ffb_conv *> convs;          /* per layer, NULL for non-conv */
+    std::vector<Tens> outs;                 /* per layer output (aliases share buf) */
+    Tens input;
+    std::vector<Buf> bufs;
+    float *d_arena = nullptr; size_t arena_floats = 0;
+    int dw5_exact = 0, pw_mode = 0, use_graph = 1, keep_all = 0;
+    bool plan_dirty = true;
+    cudaGraphExec_t gexec = nullptr; int graph_batch = -1;
+    int launches = 0;
+    /* input staging */
+    unsigned char *d_frames = nullptr; size_t d_frames_cap = 0;
+    float *h_stage = nullptr; size_t h_stage_cap = 0;
+    /* detection */
+    Candidate *d_cand = nullptr, *h_cand = nullptr; int *d_count = nullptr, *h_count = nullptr; int cand_cap = 0;
+    std::vector<std::vector<BBOX>> boxes, raw;
+    int s1 = 1, s2 = 1;
+    /* L2 flush scratch for ffb_layer_times */
+    float *d_flush = nullptr; size_t flush_floats = 0;
+};
+
+static ffb_engine *engine_of(NET *net)
+{
+    if (!net) { ffb_set_error("NULL net"); return nullptr; }
+    ffb_net *fn = ffb_from_pub(net);
+    if (fn->magic != FFB_MAGIC) { ffb_set_error("NET was not created by this library"); return nullptr; }
+    if (!fn->engine) { ffb_set_error("net has no GPU engine (ffb_net_attach not called or failed)"); return nullptr; }
+    return fn->engine;
+}
+
+int ffb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static void engine_free_plan(ffb_engine *e)
+{
+    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+    e->graph_batch = -1;
+    cudaFree(e->d_arena); e->d_arena = nullptr; e->arena_floats = 0;
+    e->bufs.clear();
+}
+
+void ffb_engine_destroy(ffb_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    engine_free_plan(e);
+    for (ffb_conv *c : e->convs) conv_release(c);
+    cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_cand); cudaFree(e->d_count); cudaFree(e->d_flush);
+    cudaFreeHost(e->h_stage); cudaFreeHost(e->h_cand); cudaFreeHost(e->h_count);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+/* ---- activation arena: one buffer per produced tensor, reused once its last reader has run ---- */
+static int engine_plan(ffb_engine *e)
+{
+    NET *net = &e->net->pub; const int L = net->layer_num;
+    engine_free_plan(e);
+    e->outs.assign(L, Tens());
+    std::vector<Buf> &bufs = e->bufs;
+    auto new_buf = [&](size_t frame_floats, int first) {
+        Buf b; b.floats = FFB_ALIGN(frame_floats * (size_t)e->max_batch, 64); b.first = first; b.last = first;
+        bufs.push_back(b); return (int)bufs.size() - 1;
+    };
+    const LAYER *l0 = net->layer_list;
+    e->input.h = l0->h; e->input.w = l0->w; e->input.c = l0->c; e->input.ld = FFB_ALIGN(l0->c, 4);
+    e->input.buf = new_buf(e->input.frame_floats(), -1);
+    auto in_of = [&](int i) -> Tens & { return i == 0 ? e->input : e->outs[i - 1]; };
+    auto touch = [&](const Tens &t, int at) { if (t.buf >= 0) bufs[t.buf].last = std::max(bufs[t.buf].last, at); };
+    for (int i = 0; i < L; i++) {
+        const LAYER *il = net->layer_list + i, *ol = il + 1;
+        Tens &o = e->outs[i];
+        o.h = ol->h; o.w = ol->w; o.c = ol->c; o.ld = FFB_ALIGN(ol->c, 4);
+        switch (il->type) {
+        case LAYER_TYPE_DROPOUT: o = in_of(i); break;                               /* alias */
+        case LAYER_TYPE_ROUTE:
+            if (il->depend_num == 1) { o = e->outs[il->depend_list[0]]; break; }   /* alias */
+            o.buf = new_buf(o.frame_floats(), i);
+            for (int d = 0; d < il->depend_num; d++) touch(e->outs[il->depend_list[d]], i);
+            break;
+        case LAYER_TYPE_YOLO: o = Tens(); touch(in_of(i), 1 << 30); break;          /* heads stay alive for ffb_detect */
+        case LAYER_TYPE_SHORTCUT:
+            o.buf = new_buf(o.frame_floats(), i); touch(in_of(i), i); touch(e->outs[il->depend_list[0]], i); break;
+        default:
+            o.buf = new_buf(o.frame_floats(), i); touch(in_of(i), i); break;
+        }
+        if (o.buf >= 0) touch(o, i);
+    }
+    if (e->keep_all) for (Buf &b : bufs) b.last = 1 << 30;
+    /* greedy best-fit over a free list, in creation order */
+    struct Free { size_t off, len; };
+    std::vector<Free> fl; size_t top = 0;
+    std::vector<int> order(bufs.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::vector<int> live;
+    for (int bi : order) {
+        Buf &b = bufs[bi];
+        /* release buffers whose last reader ran strictly before this buffer is first written */
+        for (size_t k = 0; k < live.size();) {
+            Buf &lb = bufs[live[k]];
+            if (lb.last < b.first) {
+                fl.push_back({ lb.offset, lb.floats });
+                live.erase(live.begin() + k);
+            } else k++;
+        }
+        std::sort(fl.begin(), fl.end(), [](const Free &x, const Free &y) { return x.off < y.off; });
+        for (size_t k = 0; k + 1 < fl.size();) {
+            if (fl[k].off + fl[k].len == fl[k + 1].off) { fl[k].len += fl[k + 1].len; fl.erase(fl.begin() + k + 1); } else k++;
+        }
+        int best = -1;
+        for (size_t k = 0; k < fl.size(); k++) if (fl[k].len >= b.floats && (best < 0 || fl[k].len < fl[best].len)) best = (int)k;
+        if (best >= 0) { b.offset = fl[best].off; fl[best].off += b.floats; fl[best].len -= b.floats; if (!fl[best].len) fl.erase(fl.begin() + best); }
+        else { b.offset = top; top += b.floats; }
+        live.push_back(bi);
+    }
+    e->arena_floats = top;
+    CK(cudaMalloc(&e->d_arena, top * sizeof(float)));
+    CK(cudaMemsetAsync(e->d_arena, 0, top * sizeof(float), e->stream));
+    e->input.p = e->d_arena + bufs[e->input.buf].offset;
+    for (Tens &t : e->outs) if (t.buf >= 0) t.p = e->d_arena + bufs[t.buf].offset;
+    e->plan_dirty = false;
+    return 0;
+}
+
+static int engine_prepare_weights(ffb_engine *e)
+{
+    NET *net = &e->net->pub;
+    for (int i = 0; i < net->layer_num; i++) {
+        const LAYER *l = net->layer_list + i;
+        if (l->type != LAYER_TYPE_CONV) continue;
+        ffb_conv *op = e->convs[i];
+        if (!op) {
+            op = new ffb_conv(); memset(op, 0, sizeof *op);
+            e->convs[i] = op;
+        }
+        op->ic = l->c; op->groups = l->groups; op->pad = l->pad; op->stride = l->stride; op->fs = l->fs; op->fn = l->fn;
+        op->act = l->activation; op->dw5_exact = e->dw5_exact; op->pw_mode = e->pw_mode;
+        op->d_packed = e->d_packed + (l->filter - net->weight_buf);
+        if (op->tc) { pw_tc_plan_destroy(op->tc); op->tc = NULL; }
+        if (conv_prepare(op, e->stream) != 0) return -1;
+    }
+    return 0;
+}
+
+int ffb_net_attach(NET *net, int device, int max_batch)
+{
+    if (!net) { ffb_set_error("NULL net"); return -1; }
+    ffb_net *fn = ffb_from_pub(net);
+    if (fn->magic != FFB_MAGIC) { ffb_set_error("NET was not created by this library"); return -1; }
+    if (max_batch < 1) max_batch = 1;
+    int ndev = ffb_device_count();
+    if (ndev <= 0) { ffb_set_error("no CUDA device available: libffcnn_b200 has no CPU fallback"); return -1; }
+    if (device < 0 || device >= ndev) { ffb_set_error("device %d out of range (%d devices)", device, ndev); return -1; }
+    ffb_engine *e = fn->engine;
+    if (e && e->device == device) {
+        if (max_batch > e->max_batch) { e->max_batch = max_batch; e->plan_dirty = true; }
+        return 0;
+    }
+    if (e) { ffb_engine_destroy(e); fn->engine = nullptr; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { ffb_set_error("device %d is sm_%d%d; this build only carries sm_100a code", device, prop.major, prop.minor); return -1; }
+    g_num_sms = prop.multiProcessorCount;
+    e = new ffb_engine(); e->net = fn; e->device = device; e->max_batch = max_batch;
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; ffb_set_error("cudaStreamCreate failed"); return -1; }
+    e->stream = e->own_stream;
+    fn->engine = e;
+    e->convs.assign(net->layer_num, nullptr);
+    const char *env;
+    if ((env = getenv("FFCNN_DW5_EXACT"))) e->dw5_exact = atoi(env);
+    if ((env = getenv("FFCNN_PW_MODE")))   e->pw_mode = atoi(env);
+    if ((env = getenv("FFCNN_GRAPH")))     e->use_graph = atoi(env);
+    CK(cudaMalloc(&e->d_packed, std::max(1, net->weight_size) * sizeof(float)));
+    CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    if (engine_prepare_weights(e) != 0) return -1;
+    CK(cudaMalloc(&e->d_count, sizeof(int)));
+    CK(cudaMallocHost(&e->h_count, sizeof(int)));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+NET *net_load(char *cfgfile, char *weightsfile, int inputw, int inputh)
+{
+    NET *net = ffb_net_parse(cfgfile, weightsfile, inputw, inputh);
+    const char *dev = getenv("FFCNN_DEVICE");
+    if (!net) { fprintf(stderr, "ffcnn_b200: net_load: %s\n", ffb_last_error()); return NULL; }
+    if (ffb_net_attach(net, dev ? atoi(dev) : 0, 1) != 0) {
+        fprintf(stderr, "ffcnn_b200: net_load: %s\n", ffb_last_error());
+        net_free(net);
+        return NULL;
+    }
+    return net;
+}
+
+void *ffb_packed_weights_device(NET *net, size_t *nfloats)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return NULL;
+    if (nfloats) *nfloats = (size_t)net->weight_size;
+    return e->d_packed;
+}
+
+int ffb_commit_weights(NET *net)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    CK(cudaSetDevice(e->device));
+    /* keep the host copy coherent with what was broadcast into the device buffer */
+    CK(cudaMemcpyAsync(net->weight_buf, e->d_packed, (size_t)net->weight_size * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (engine_prepare_weights(e) != 0) return -1;
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; e->graph_batch = -1; }
+    return 0;
+}
+
+int ffb_set_option(NET *net, const char *name, int value)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e || !name) return -1;
+    bool reweight = false;
+    if      (!strcmp(name, "dw5_exact")) { reweight = e->dw5_exact != value; e->dw5_exact = value; }
+    else if (!strcmp(name, "pw_mode"))   { reweight = e->pw_mode != value; e->pw_mode = value; }
+    else if (!strcmp(name, "graph"))     { e->use_graph = value; }
+    else if (!strcmp(name, "keep_all"))  { if (e->keep_all != value) e->plan_dirty = true; e->keep_all = value; }
+    else { ffb_set_error("unknown option '%s'", name); return -1; }
+    if (reweight) {
+        CK(cudaSetDevice(e->device));
+        if (engine_prepare_weights(e) != 0) return -1;
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; e->graph_batch = -1; }
+    return 0;
+}
+
+int ffb_get_option(NET *net, const char *name)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e || !name) return -1;
+    if (!strcmp(name, "dw5_exact")) return e->dw5_exact;
+    if (!strcmp(name, "pw_mode")) return e->pw_mode;
+    if (!strcmp(name, "graph")) return e->use_graph;
+    if (!strcmp(name, "keep_all")) return e->keep_all;
+    if (!strcmp(name, "max_batch")) return e->max_batch;
+    if (!strcmp(name, "batch")) return e->batch;
+    if (!strcmp(name, "device")) return e->device;
+    if (!strcmp(name, "arena_mb")) return (int)(e->arena_floats * sizeof(float) >> 20);
+    return -1;
+}
+
+int ffb_set_stream(NET *net, void *s)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    cudaStreamSynchronize(e->stream);
+    e->stream = s ? (cudaStream_t)s : e->own_stream;
+    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; e->graph_batch = -1; }
+    return 0;
+}
+void *ffb_get_stream(NET *net) { ffb_engine *e = engine_of(net); return e ? (void *)e->stream : NULL; }
+
+int ffb_sync(NET *net)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int engine_ready(ffb_engine *e, int n)
+{
+    CK(cudaSetDevice(e->device));
+    if (n > e->max_batch) { e->max_batch = n; e->plan_dirty = true; }
+    if (e->plan_dirty || !e->d_arena) { CK(cudaStreamSynchronize(e->stream)); if (engine_plan(e) != 0) return -1; }
+    return 0;
+}
+
+/* ---- input ---- */
+int ffb_input_u8(NET *net, const unsigned char *frames, int n, int w, int h, int pitch,
+                 const float *mean, const float *norm, int on_device)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    if (!frames || n < 1 || w < 1 || h < 1 || pitch < 3 * w) { ffb_set_error("ffb_input_u8: bad arguments"); return -1; }
+    if (net->layer_list[0].c != 3) { ffb_set_error("ffb_input_u8 needs a 3-channel network input"); return -1; }
+    if (engine_ready(e, n) != 0) return -1;
+    static const float zero3[3] = { 0, 0, 0 }, unit3[3] = { 1 / 255.f, 1 / 255.f, 1 / 255.f };
+    if (!mean) mean = zero3;
+    if (!norm) norm = unit3;
+    const unsigned char *src = frames;
+    const size_t bytes = (size_t)n * h * pitch;
+    if (!on_device) {
+        if (bytes > e->d_frames_cap) {
+            CK(cudaStreamSynchronize(e->stream));
+            cudaFree(e->d_frames); e->d_frames = nullptr; e->d_frames_cap = 0;
+            CK(cudaMalloc(&e->d_frames, bytes)); e->d_frames_cap = bytes;
+        }
+        CK(cudaMemcpyAsync(e->d_frames, frames, bytes, cudaMemcpyHostToDevice, e->stream));
+        src = e->d_frames;
+    }
+    int sw, sh, s1, s2;
+    ffb_fit_geometry(w, h, e->input.w, e->input.h, &sw, &sh, &s1, &s2);
+    e->s1 = s1; e->s2 = s2; e->batch = n;
+    net->s1 = s1; net->s2 = s2;
+    const long total = (long)n * e->input.h * e->input.w;
+    k_input_u8<<<grid_for(total, 256, 16), 256, 0, e->stream>>>(src, e->input.p, n, w, h, pitch, e->input.w, e->input.h, sw, sh, s1, s2,
+                                                                mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ffb_input_chw(NET *net, const float *chw, int n, int s1, int s2)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    if (!chw || n < 1) { ffb_set_error("ffb_input_chw: bad arguments"); return -1; }
+    if (engine_ready(e, n) != 0) return -1;
+    const Tens &t = e->input;
+    const size_t fl = (size_t)n * t.frame_floats();
+    CK(cudaStreamSynchronize(e->stream));                 /* staging buffer may still be in flight */
+    if (fl > e->h_stage_cap) { cudaFreeHost(e->h_stage); e->h_stage = nullptr; CK(cudaMallocHost(&e->h_stage, fl * sizeof(float))); e->h_stage_cap = fl; }
+    const size_t plane = (size_t)t.h * t.w;
+    for (int f = 0; f < n; f++)
+        for (size_t p = 0; p < plane; p++)
+            for (int c = 0; c < t.ld; c++)
+                e->h_stage[((size_t)f * plane + p) * t.ld + c] = c < t.c ? chw[((size_t)f * t.c + c) * plane + p] : 0.f;
+    CK(cudaMemcpyAsync(t.p, e->h_stage, fl * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    e->batch = n; e->s1 = s1; e->s2 = s2; net->s1 = s1; net->s2 = s2;
+    return 0;
+}
+
+/* ---- the layer loop ---- */
+static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
+{
+    NET *net = &e->net->pub; const LAYER *il = net->layer_list + i;
+    const Tens &in = i == 0 ? e->input : e->outs[i - 1]; const Tens &o = e->outs[i];
+    const int n = e->batch;
+    switch (il->type) {
+    case LAYER_TYPE_CONV:
+        if (conv_run(e->convs[i], in.p, in.ld, o.p, o.ld, 0, n, in.h, in.w, st) != 0) return -1;
+        (*launches)++;
+        break;
+    case LAYER_TYPE_MAXPOOL: case LAYER_TYPE_AVGPOOL:
+        if (in.c % 4) { ffb_set_error("pool layer %d: channels %d not a multiple of 4", i, in.c); return -1; }
+        k_pool<<<grid_for((long)n * o.h * o.w * (o.c / 4), 128), 128, 0, st>>>(in.p, o.p, n, in.h, in.w, in.c, in.ld, o.h, o.w, o.ld, 0,
+                                                                              il->fs, il->stride, il->type == LAYER_TYPE_MAXPOOL);
+        (*launches)++;
+        break;
+    case LAYER_TYPE_UPSAMPLE:
+        if (in.c % 4) { ffb_set_error("upsample layer %d: channels %d not a multiple of 4", i, in.c); return -1; }
+        k_upsample<<<grid_for((long)n * o.h * o.w * (o.c / 4), 128), 128, 0, st>>>(in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride);
+        (*launches)++;
+        break;
+    case LAYER_TYPE_SHORTCUT: {
+        const Tens &s = e->outs[il->depend_list[0]];
+        if (s.h != in.h || s.w != in.w || s.c != in.c) { ffb_set_error("shortcut layer %d: shape mismatch", i); return -1; }
+        const long n4 = (long)n * o.frame_floats() / 4;       /* ld is a multiple of 4 and identical for all three */
+        k_shortcut<<<grid_for(n4, 256), 256, 0, st>>>(in.p, s.p, o.p, n4, il->activation);
+        (*launches)++;
+        break; }
+    case LAYER_TYPE_ROUTE:
+        if (il->depend_num > 1) {
+            int coff = 0;
+            for (int d = 0; d < il->depend_num; d++) {
+                const Tens &s = e->outs[il->depend_list[d]];
+                const long px = (long)n * s.h * s.w;
+                if (s.c % 4 == 0 && coff % 4 == 0) k_concat<<<grid_for(px * (s.c / 4), 256), 256, 0, st>>>(s.p, o.p, px, s.c, s.ld, o.ld, coff);
+                else k_copy_strided<<<grid_for(px * s.c, 256), 256, 0, st>>>(s.p, o.p, px, s.c, s.ld, o.ld, coff);
+                coff += s.c; (*launches)++;
+            }
+        }
+        break;
+    default: break;                                            /* dropout, yolo: nothing to launch */
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { ffb_set_error("layer %d launch failed: %s", i, cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+static int run_all(ffb_engine *e, cudaStream_t st)
+{
+    int launches = 0;
+    for (int i = 0; i < e->net->pub.layer_num; i++) if (run_layer(e, i, st, &launches) != 0) return -1;
+    e->launches = launches;
+    return 0;
+}
+
+int ffb_forward(NET *net)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    if (e->batch < 1 || !e->d_arena || e->plan_dirty) { ffb_set_error("ffb_forward: no input set for the current plan"); return -1; }
+    CK(cudaSetDevice(e->device));
+    if (!e->use_graph) return run_all(e, e->stream);
+    if (!e->gexec || e->graph_batch != e->batch) {
+        if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+        /* one eager pass first: lazily-set function attributes must not happen inside capture */
+        if (run_all(e, e->stream) != 0) return -1;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_all(e, e->stream);
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        if (rc != 0 || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); if (ce != cudaSuccess) ffb_set_error("graph capture failed: %s", cudaGetErrorString(ce)); return -1; }
+        ce = cudaGraphInstantiate(&e->gexec, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) { ffb_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); e->gexec = nullptr; return -1; }
+        e->graph_batch = e->batch;
+        return 0;                                               /* the eager pass above already produced this batch's outputs */
+    }
+    CK(cudaGraphLaunch(e->gexec, e->stream));
+    return 0;
+}
+
+int ffb_launches_per_forward(NET *net) { ffb_engine *e = engine_of(net); return e ? e->launches : -1; }
+
+/* ---- detection ---- */
+int ffb_detect(NET *net)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    CK(cudaSetDevice(e->device));
+    const int n = e->batch, L = net->layer_num;
+    if (n < 1) { ffb_set_error("ffb_detect: no batch"); return -1; }
+    struct Head { int layer, cells, gw, gh, key_base; };
+    std::vector<Head> heads; int key = 0;
+    for (int i = 1; i < L; i++) if (net->layer_list[i].type == LAYER_TYPE_YOLO) {
+        const Tens &t = e->outs[i - 1];
+        heads.push_back({ i, t.h * t.w, t.w, t.h, key }); key += t.h * t.w * 3;
+    }
+    const int cap = std::max(4096, std::min(key, 2048) * n);
+    if (cap > e->cand_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_cand); cudaFreeHost(e->h_cand); e->d_cand = nullptr; e->h_cand = nullptr;
+        CK(cudaMalloc(&e->d_cand, (size_t)cap * sizeof(Candidate)));
+        CK(cudaMallocHost(&e->h_cand, (size_t)cap * sizeof(Candidate)));
+        e->cand_cap = cap;
+    }
+    CK(cudaMemsetAsync(e->d_count, 0, sizeof(int), e->stream));
+    for (const Head &h : heads) {
+        const LAYER *yl = net->layer_list + h.layer; const Tens &t = e->outs[h.layer - 1];
+        if (t.c != 3 * (5 + yl->class_num)) { ffb_set_error("yolo layer %d: %d channels, expected %d", h.layer, t.c, 3 * (5 + yl->class_num)); return -1; }
+        const long warps = (long)n * h.cells;
+        k_yolo_filter<<<(int)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(t.p, n, h.cells, t.ld, yl->class_num, 0, h.key_base,
+                                                                              yl->ignore_thres, e->d_cand, e->d_count, e->cand_cap);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(e->h_count, e->d_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    int cnt = std::min(*e->h_count, e->cand_cap);
+    if (cnt > 0) {
+        CK(cudaMemcpyAsync(e->h_cand, e->d_cand, (size_t)cnt * sizeof(Candidate), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    std::sort(e->h_cand, e->h_cand + cnt, [](const Candidate &a, const Candidate &b) { return a.frame != b.frame ? a.frame < b.frame : a.key < b.key; });
+    e->boxes.assign(n, std::vector<BBOX>()); e->raw.assign(n, std::vector<BBOX>());
+    const int netw = net->layer_list[0].w, neth = net->layer_list[0].h;
+    for (int k = 0; k < cnt; k++) {
+        const Candidate &c = e->h_cand[k];
+        if (c.frame < 0 || c.frame >= n) continue;
+        const Head *hd = nullptr;
+        for (const Head &h : heads) if (c.key >= h.key_base && c.key < h.key_base + h.cells * 3) hd = &h;
+        if (!hd) continue;
+        ffb_candidate hc; hc.frame = c.frame; hc.key = c.key; hc.cls = c.cls; hc.bs = c.bs; hc.cs = c.cs; hc.tx = c.tx; hc.ty = c.ty; hc.tw = c.tw; hc.th = c.th;
+        BBOX b; const int rel = c.key - hd->key_base;
+        if ((int)e->raw[c.frame].size() < net->bbox_max &&
+            ffb_decode_candidate(net->layer_list + hd->layer, netw, neth, hd->gw, hd->gh, rel / 3, rel % 3, &hc, &b)) e->raw[c.frame].push_back(b);
+    }
+    for (int f = 0; f < n; f++) {
+        e->boxes[f] = e->raw[f];
+        const int m = ffb_nms(e->boxes[f].data(), (int)e->boxes[f].size(), 0.5f, 1, e->s1, e->s2);
+        e->boxes[f].resize(m);
+    }
+    return 0;
+}
+
+int ffb_boxes(NET *net, int frame, BBOX **boxes)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e || frame < 0 || frame >= (int)e->boxes.size()) { if (e) ffb_set_error("ffb_boxes: frame %d out of range", frame); return -1; }
+    if (boxes) *boxes = e->boxes[frame].data();
+    return (int)e->boxes[frame].size();
+}
+
+int ffb_raw_boxes(NET *net, int frame, BBOX **boxes)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e || frame < 0 || frame >= (int)e->raw.size()) { if (e) ffb_set_error("ffb_raw_boxes: frame %d out of range", frame); return -1; }
+    if (boxes) *boxes = e->raw[frame].data();
+    return (int)e->raw[frame].size();
+}
+
+int ffb_detect_batch_u8(NET *net, const unsigned char *frames_host, int n, int w, int h, int pitch,
+                        const float *mean, const float *norm)
+{
+    if (ffb_input_u8(net, frames_host, n, w, h, pitch, mean, norm, 0) != 0) return -1;
+    if (ffb_forward(net) != 0) return -1;
+    return ffb_detect(net);
+}
+
+/* net_forward(): host CHW input tensor -> boxes, one frame (the reference's own entry point) */
+int ffb_engine_forward_single(ffb_net *fn)
+{
+    NET *net = &fn->pub;
+    const int s1 = net->s1 ? net->s1 : 1, s2 = net->s2 ? net->s2 : 1;
+    if (ffb_input_chw(net, net->layer_list[0].data, 1, s1, s2) != 0) return -1;
+    if (ffb_forward(net) != 0) return -1;
+    if (ffb_detect(net) != 0) return -1;
+    BBOX *b = nullptr; int m = ffb_boxes(net, 0, &b);
+    if (m < 0) return -1;
+    if (m > net->bbox_max) m = net->bbox_max;
+    memset(net->bbox_list, 0, sizeof(BBOX) * (size_t)net->bbox_max);
+    if (m) memcpy(net->bbox_list, b, sizeof(BBOX) * (size_t)m);
+    net->bbox_num = m;
+    return 0;
+}
+
+/* ---- inspection ---- */
+long ffb_layer_output(NET *net, int layer, int frame, float *chw, long capacity)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    if (layer < -1 || layer >= net->layer_num || frame < 0 || frame >= e->batch) { ffb_set_error("ffb_layer_output: bad layer/frame"); return -1; }
+    if (!e->keep_all) { ffb_set_error("ffb_layer_output needs option keep_all=1 before ffb_forward"); return -1; }
+    const Tens &t = layer < 0 ? e->input : e->outs[layer];
+    if (!t.p) return 0;
+    const long count = (long)t.c * t.h * t.w;
+    if (!chw) return count;
+    if (capacity < count) { ffb_set_error("ffb_layer_output: buffer too small"); return -1; }
+    CK(cudaSetDevice(e->device));
+    std::vector<float> tmp(t.frame_floats());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(tmp.data(), t.p + (size_t)frame * t.frame_floats(), tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    const size_t plane = (size_t)t.h * t.w;
+    for (int c = 0; c < t.c; c++) for (size_t p = 0; p < plane; p++) chw[c * plane + p] = tmp[p * t.ld + c];
+    return count;
+}
+
+int ffb_layer_cost(NET *net, int i, double *bytes, double *flops, char *kname, int cap)
+{
+    if (!net || i < 0 || i >= net->layer_num) { ffb_set_error("ffb_layer_cost: bad layer"); return -1; }
+    const LAYER *a = net->layer_list + i, *b = a + 1;
+    const double in = (double)a->w * a->h * a->c, out = (double)b->w * b->h * b->c;
+    double by = 0, fl = 0; const char *nm = "alias";
+    switch (a->type) {
+    case LAYER_TYPE_CONV: {
+        const double taps = (double)a->fs * a->fs * (a->c / a->groups);
+        by = 4 * (in + out + a->fn * (taps + 2)); fl = 2 * taps * out; nm = "conv"; break; }
+    case LAYER_TYPE_MAXPOOL: case LAYER_TYPE_AVGPOOL: by = 4 * (in + out); fl = out * a->fs * a->fs; nm = "pool"; break;
+    case LAYER_TYPE_UPSAMPLE: by = 4 * (in + out); nm = "upsample"; break;
+    case LAYER_TYPE_SHORTCUT: by = 4 * 3 * out; fl = out; nm = "shortcut"; break;
+    case LAYER_TYPE_ROUTE: by = 4 * 2 * out; nm = a->depend_num > 1 ? "concat" : "alias"; break;
+    case LAYER_TYPE_YOLO: by = 4 * in; nm = "yolo_filter"; break;
+    default: break;
+    }
+    ffb_net *fn = ffb_from_pub(net);
+    if (a->type == LAYER_TYPE_CONV && fn->engine && fn->engine->convs[i]) nm = fn->engine->convs[i]->name;
+    if (bytes) *bytes = by;
+    if (flops) *flops = fl;
+    if (kname && cap > 0) snprintf(kname, (size_t)cap, "%s", nm);
+    return 0;
+}
+
+int ffb_layer_times(NET *net, float *ms, int nlayers, int reps, int flush_l2)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    if (e->batch < 1 || !e->d_arena || e->plan_dirty) { ffb_set_error("ffb_layer_times: run ffb_forward first"); return -1; }
+    CK(cudaSetDevice(e->device));
+    if (reps < 1) reps = 1;
+    if (flush_l2 && !e->d_flush) { e->flush_floats = (size_t)64 << 20; CK(cudaMalloc(&e->d_flush, e->flush_floats * sizeof(float))); }
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int L = std::min(nlayers, net->layer_num);
+    for (int i = 0; i < L; i++) {
+        float total = 0; int launches = 0;
+        for (int r = 0; r < reps + 1; r++) {                    /* first rep is an untimed warm-up */
+            if (flush_l2) k_fill<<<g_num_sms * 8, 256, 0, e->stream>>>(e->d_flush, (long)e->flush_floats, 0.f);
+            CK(cudaEventRecord(a, e->stream));
+            launches = 0;
+            if (run_layer(e, i, e->stream, &launches) != 0) return -1;
+            CK(cudaEventRecord(b, e->stream));
+            CK(cudaEventSynchronize(b));
+            float t = 0; CK(cudaEventElapsedTime(&t, a, b));
+            if (r > 0) total += t;
+        }
+        ms[i] = launches ? total / reps : 0.f;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return 0;
+}
+
+/* =================================================================================== standalone op API */
+
+static int ensure_device()
+{
+    if (ffb_device_count() <= 0) { ffb_set_error("no CUDA device available: libffcnn_b200 has no CPU fallback"); return -1; }
+    cudaDeviceProp prop; int dev = 0;
+    CK(cudaGetDevice(&dev)); CK(cudaGetDeviceProperties(&prop, dev));
+    g_num_sms = prop.multiProcessorCount;
+    return 0;
+}
+
+ffb_conv *ffb_conv_create(const float *packed, int ic, int groups, int pad, int stride, int fs, int fn, int act, int flags)
+{
+    if (!packed || ic < 1 || groups < 1 || fs < 1 || fn < 1 || stride < 1 || ic % groups || fn % groups) { ffb_set_error("ffb_conv_create: bad arguments"); return NULL; }
+    if (ensure_device() != 0) return NULL;
+    ffb_conv *op = new ffb_conv(); memset(op, 0, sizeof *op);
+    op->ic = ic; op->groups = groups; op->pad = pad; op->stride = stride; op->fs = fs; op->fn = fn; op->act = act;
+    op->dw5_exact = flags & 1; op->pw_mode = (flags >> 8) & 0xff;
+    const int row = FFB_ALIGN(fs * fs * (ic / groups), 4) + 4;
+    const size_t bytes = (size_t)fn * row * sizeof(float);
+    if (cudaMalloc(&op->d_owned_packed, bytes) != cudaSuccess || cudaMemcpy(op->d_owned_packed, packed, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        ffb_set_error("ffb_conv_create: device allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError())); conv_release(op); return NULL;
+    }
+    op->d_packed = op->d_owned_packed;
+    if (conv_prepare(op, 0) != 0 || cudaDeviceSynchronize() != cudaSuccess) { conv_release(op); return NULL; }
+    return op;
+}
+
+void ffb_conv_destroy(ffb_conv *op) { conv_release(op); }
+const char *ffb_conv_kernel_name(ffb_conv *op) { return op ? op->name : ""; }
+
+int ffb_conv_run(ffb_conv *op, const float *in, float *out, int n, int ih, int iw, void *stream)
+{
+    if (!op || !in || !out) { ffb_set_error("ffb_conv_run: bad arguments"); return -1; }
+    return conv_run(op, in, FFB_ALIGN(op->ic, 4), out, FFB_ALIGN(op->fn, 4), 0, n, ih, iw, (cudaStream_t)stream);
+}
+
+void *ffb_dev_alloc(size_t bytes) { void *p = NULL; if (cudaMalloc(&p, bytes) != cudaSuccess) { ffb_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError())); return NULL; } return p; }
+void  ffb_dev_free(void *p) { cudaFree(p); }
+int   ffb_copy_h2d(void *d, const void *s, size_t b) { CK(cudaMemcpy(d, s, b, cudaMemcpyHostToDevice)); return 0; }
+int   ffb_copy_d2h(void *d, const void *s, size_t b) { CK(cudaMemcpy(d, s, b, cudaMemcpyDeviceToHost)); return 0; }
+void *ffb_host_alloc_pinned(size_t bytes) { void *p = NULL; if (cudaMallocHost(&p, bytes) != cudaSuccess) { ffb_set_error("cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError())); return NULL; } return p; }
+void  ffb_host_free_pinned(void *p) { cudaFreeHost(p); }
+
+int ffb_chw_to_nhwc(const float *src, float *dst, int n, int c, int h, int w, void *stream)
+{
+    const int ld = FFB_ALIGN(c, 4);
+    k_chw_to_nhwc<<<grid_for((long)n * h * w * ld, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, dst, n, c, h, w, ld);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ffb_nhwc_to_chw(const float *src, float *dst, int n, int c, int h, int w, void *stream)
+{
+    const int ld = FFB_ALIGN(c, 4);
+    k_nhwc_to_chw<<<grid_for((long)n * c * h * w, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, dst, n, c, h, w, ld);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+/* =================================================================================== operator seam */
+
+/* conv.h:4-7 backed by the GPU: host CHW in -> device NHWC -> kernel -> host CHW out. */
+extern "C" void groupconv(float *datai, float *dataf, float *datao, int iw, int ih, int ic, int ig, int ipad, int istride,
+                          int fs, int fn, int ow, int oh, int oc, int activation, float **gc_buffer, int *gc_bufsize)
+{
+    (void)gc_buffer; (void)gc_bufsize; (void)oc;
+    const char *ex = getenv("FFCNN_DW5_EXACT"), *pm = getenv("FFCNN_PW_MODE");
+    const int flags = (ex && atoi(ex) ? 1 : 0) | ((pm ? atoi(pm) : 0) << 8);
+    ffb_conv *op = ffb_conv_create(dataf, ic, ig, ipad, istride, fs, fn, activation, flags);
+    if (!op) { fprintf(stderr, "ffcnn_b200: groupconv: %s\n", ffb_last_error()); return; }
+    const int ldi = FFB_ALIGN(ic, 4), ldo = FFB_ALIGN(fn, 4);
+    const size_t in_chw = (size_t)ic * ih * iw, out_chw = (size_t)fn * oh * ow;
+    const size_t in_n = (size_t)ih * iw * ldi, out_n = (size_t)oh * ow * ldo;
+    float *d = NULL;
+    if (cudaMalloc(&d, (in_chw + out_chw + in_n + out_n) * sizeof(float)) != cudaSuccess) {
+        fprintf(stderr, "ffcnn_b200: groupconv: device allocation failed\n"); cudaGetLastError(); conv_release(op); return;
+    }
+    float *d_in_chw = d, *d_out_chw = d + in_chw, *d_in = d_out_chw + out_chw, *d_out = d_in + in_n;
+    bool ok = cudaMemcpy(d_in_chw, datai, in_chw * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess
+           && cudaMemset(d_out, 0, out_n * sizeof(float)) == cudaSuccess
+           && ffb_chw_to_nhwc(d_in_chw, d_in, 1, ic, ih, iw, 0) == 0
+           && conv_run(op, d_in, ldi, d_out, ldo, 0, 1, ih, iw, 0) == 0
+           && ffb_nhwc_to_chw(d_out, d_out_chw, 1, fn, oh, ow, 0) == 0
+           && cudaMemcpy(datao, d_out_chw, out_chw * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (!ok) fprintf(stderr, "ffcnn_b200: groupconv failed: %s / %s\n", ffb_last_error(), cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    conv_release(op);
+}

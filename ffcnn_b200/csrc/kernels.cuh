@@ -1,0 +1,436 @@
+/*
+ * kernels.cuh -- hand-written sm_100a kernels for the HBM-bound half of ffcnn's hot path.
+ *
+ * Data layout: batched NHWC fp32, `ld` floats between consecutive pixels (ld = ALIGN(c,4); the
+ * 255-channel yolo heads therefore sit at ld = 256 so every pixel row stays 16-byte aligned).
+ * One image row is a flat run of W*C floats, so the depthwise stencils below treat an image as
+ * [H][W*C] and each thread owns one float4 (4 channels of one pixel) of that run: consecutive
+ * lanes touch consecutive 16 B -> fully coalesced 128-bit accesses; a tap to the left/right is an
+ * offset of -/+C floats, to the row above/below -/+W*C.
+ *
+ * Every conv kernel ends in the reference's fused epilogue  act(sum * scale + bias)
+ * (conv-v0.c:27 / conv-v6.c:38,72-75; activate(): utils.h:15-23); BN is pre-folded into
+ * (scale, bias) at load (ffcnn.c:222-233).  sum*scale+bias is one FMA here, as in the
+ * reference's shipped -Ofast build.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ffb {
+
+__device__ __forceinline__ float act_apply(float v, int act)
+{
+    return act == 2 ? (v > 0.f ? v : 0.1f * v) : act == 1 ? fmaxf(v, 0.f) : v;
+}
+
+__device__ __forceinline__ float4 epilogue4(float4 a, float4 s, float4 b, int act)
+{
+    float4 r;
+    r.x = act_apply(fmaf(a.x, s.x, b.x), act); r.y = act_apply(fmaf(a.y, s.y, b.y), act);
+    r.z = act_apply(fmaf(a.z, s.z, b.z), act); r.w = act_apply(fmaf(a.w, s.w, b.w), act);
+    return r;
+}
+
+__device__ __forceinline__ void fma4(float4 &acc, const float4 v, const float4 w)
+{
+    acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y);
+    acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
+}
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+/* ------------------------------------------------------------------------------------------------
+ * net_input, batched (ffcnn.c:259-289): BGR u8 frames -> NHWC fp32 [n][H][W][ld=4] (channel 3 = 0),
+ * nearest-neighbour fit to the top-left sw x sh corner, (px - mean) * norm, zero elsewhere.
+ * One thread per output pixel; the float4 store is coalesced, the 3 byte loads hit L1/L2 sectors
+ * shared with the neighbouring lanes.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void k_input_u8(const uint8_t *__restrict__ frames, float *__restrict__ out,
+                           int n, int w, int h, int pitch, int W, int H, int sw, int sh, int s1, int s2,
+                           float m0, float m1, float m2, float n0, float n1, float n2)
+{
+    const long total = (long)n * H * W;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H); const long f = i / ((long)W * H);
+        float4 v = zero4();
+        if (x < sw && y < sh) {
+            const uint8_t *px = frames + f * (long)h * pitch + (long)(y * s1 / s2) * pitch + (x * s1 / s2) * 3;
+            v.x = ((float)px[2] - m0) * n0;          /* R */
+            v.y = ((float)px[1] - m1) * n1;          /* G */
+            v.z = ((float)px[0] - m2) * n2;          /* B */
+        }
+        reinterpret_cast<float4 *>(out)[i] = v;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Stem: dense 3x3 stride-2 pad-1 conv, CI (3, stored at ld 4) -> CO=8 -- the only layer that takes the
+ * reference's generic im2row path (conv-v6.c:9-42).  Each CTA stages the (2*TY+1) x (2*TX+1) input
+ * halo tile in shared memory with coalesced float4 loads, then every thread produces one output
+ * pixel x 8 channels (two float4 stores).  Weights [27][8] + scale/bias sit in shared memory and are
+ * read as broadcasts.  Accumulation order channel -> ky -> kx as conv-v0.c:16-25.
+ * ---------------------------------------------------------------------------------------------- */
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY)
+k_stem3x3s2(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wt /* [27][8] */,
+            const float *__restrict__ scale, const float *__restrict__ bias,
+            int H, int W, int OH, int OW, int act)
+{
+    constexpr int IW = 2 * TX + 1, IH = 2 * TY + 1;
+    __shared__ float4 tile[IH][IW];
+    __shared__ float  sw[27 * 8 + 16];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int ox0 = blockIdx.x * TX, oy0 = blockIdx.y * TY;
+    const long f = blockIdx.z;
+    const float *img = in + f * (long)H * W * 4;
+    for (int i = tid; i < 27 * 8 + 16; i += TX * TY) sw[i] = i < 216 ? wt[i] : i < 224 ? scale[i - 216] : bias[i - 224];
+    const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+    for (int i = tid; i < IW * IH; i += TX * TY) {
+        const int tx = i % IW, ty = i / IW, ix = ix0 + tx, iy = iy0 + ty;
+        tile[ty][tx] = (ix >= 0 && ix < W && iy >= 0 && iy < H) ? ldg4(img + ((long)iy * W + ix) * 4) : zero4();
+    }
+    __syncthreads();
+    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+    if (ox >= OW || oy >= OH) return;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; o++) acc[o] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float4 p = tile[2 * threadIdx.y + j][2 * threadIdx.x + k];
+                const float v = c == 0 ? p.x : c == 1 ? p.y : p.z;
+                const float *w8 = sw + ((c * 3 + j) * 3 + k) * 8;
+#pragma unroll
+                for (int o = 0; o < 8; o++) acc[o] = fmaf(v, w8[o], acc[o]);
+            }
+    float4 r0, r1;
+    r0.x = act_apply(fmaf(acc[0], sw[216], sw[224]), act); r0.y = act_apply(fmaf(acc[1], sw[217], sw[225]), act);
+    r0.z = act_apply(fmaf(acc[2], sw[218], sw[226]), act); r0.w = act_apply(fmaf(acc[3], sw[219], sw[227]), act);
+    r1.x = act_apply(fmaf(acc[4], sw[220], sw[228]), act); r1.y = act_apply(fmaf(acc[5], sw[221], sw[229]), act);
+    r1.z = act_apply(fmaf(acc[6], sw[222], sw[230]), act); r1.w = act_apply(fmaf(acc[7], sw[223], sw[231]), act);
+    float4 *o = reinterpret_cast<float4 *>(out + (f * (long)OH * OW + (long)oy * OW + ox) * 8);
+    o[0] = r0; o[1] = r1;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise FSxFS, stride 1, pad FS/2 (conv-v6.c:96-229 for 3x3, 291-465 for 5x5).
+ * Thread = one float4 of the flattened row (pixel x, channels c..c+3); it walks R output rows downwards
+ * keeping the last FS input rows in registers (slot = row mod FS, resolved at compile time by unrolling
+ * the row loop FS-fold), so each input row is loaded once per thread: FS float4 loads per output float4.
+ * wt is [FS*FS][C] (tap-major) so the 4 channel weights of a tap are one float4.
+ * skip_row0_at: output row index whose kernel row 0 is ignored (-1 = never): conv-v6.c:422-441 forgets
+ * kernel row 0 on output row oh-2 of its 5x5 path; default builds reproduce that (the named oracle).
+ * ---------------------------------------------------------------------------------------------- */
+template <int FS>
+__global__ void __launch_bounds__(128)
+k_dw_s1(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wt,
+        const float *__restrict__ scale, const float *__restrict__ bias,
+        int H, int W, int C, int R, int act, int skip_row0_at)
+{
+    constexpr int P = FS / 2;
+    const int rowlen = W * C;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) * 4;           /* float offset inside a row */
+    if (q >= rowlen) return;
+    const int c = q % C, x = q / C;
+    const long f = blockIdx.z;
+    const float *img = in + f * (long)H * rowlen;
+    float *dst = out + f * (long)H * rowlen;
+    const int y0 = blockIdx.y * R, y1 = min(H, y0 + R);
+
+    float4 wv[FS * FS];
+#pragma unroll
+    for (int t = 0; t < FS * FS; t++) wv[t] = ldg4(wt + t * C + c);
+    const float4 sc = ldg4(scale + c), bi = ldg4(bias + c);
+    bool okx[FS];
+#pragma unroll
+    for (int k = 0; k < FS; k++) okx[k] = (unsigned)(x + k - P) < (unsigned)W;
+
+    float4 win[FS][FS];                                                   /* [slot][kx] */
+    auto load_row = [&](int slot, int iy) {
+        const bool oky = (unsigned)iy < (unsigned)H;
+        const float *rp = img + (long)iy * rowlen + q;
+#pragma unroll
+        for (int k = 0; k < FS; k++) win[slot][k] = (oky && okx[k]) ? ldg4(rp + (k - P) * C) : zero4();
+    };
+    /* slot(row) = (row - (y0 - P)) mod FS */
+#pragma unroll
+    for (int j = 0; j < FS - 1; j++) load_row(j, y0 - P + j);
+
+    for (int yb = y0; yb < y1; yb += FS) {
+#pragma unroll
+        for (int u = 0; u < FS; u++) {
+            const int y = yb + u;
+            if (y < y1) {
+                load_row((u + FS - 1) % FS, y + P);
+                float4 acc = zero4();
+                const bool skip0 = (y == skip_row0_at);
+#pragma unroll
+                for (int j = 0; j < FS; j++) {
+                    if (j == 0 && skip0) continue;
+#pragma unroll
+                    for (int k = 0; k < FS; k++) fma4(acc, win[(u + j) % FS][k], wv[j * FS + k]);
+                }
+                *reinterpret_cast<float4 *>(dst + (long)y * rowlen + q) = epilogue4(acc, sc, bi, act);
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise 3x3, stride 2, pad 1 (conv-v6.c:233-287).  Thread = one output float4 (ox, c..c+3), walking
+ * R output rows; input row 2*oy+1 of one step is row 2*(oy+1)-1 of the next, so it is carried in
+ * registers: 6 float4 loads per output float4 for 9 taps.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128)
+k_dw3_s2(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wt,
+         const float *__restrict__ scale, const float *__restrict__ bias,
+         int H, int W, int C, int OH, int OW, int R, int act)
+{
+    const int orow = OW * C, irow = W * C;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q >= orow) return;
+    const int c = q % C, ox = q / C;
+    const long f = blockIdx.z;
+    const float *img = in + f * (long)H * irow;
+    float *dst = out + f * (long)OH * orow;
+    const int y0 = blockIdx.y * R, y1 = min(OH, y0 + R);
+    float4 wv[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) wv[t] = ldg4(wt + t * C + c);
+    const float4 sc = ldg4(scale + c), bi = ldg4(bias + c);
+    const int ix = 2 * ox - 1;
+    const bool okl = ix >= 0, okr = ix + 2 < W;
+    auto load_row = [&](float4 (&r)[3], int iy) {
+        const bool oky = (unsigned)iy < (unsigned)H;
+        const float *rp = img + (long)iy * irow + (long)ix * C + c;
+        r[0] = (oky && okl) ? ldg4(rp) : zero4();
+        r[1] = oky ? ldg4(rp + C) : zero4();
+        r[2] = (oky && okr) ? ldg4(rp + 2 * C) : zero4();
+    };
+    float4 top[3], mid[3], bot[3];
+    load_row(top, 2 * y0 - 1);
+    for (int oy = y0; oy < y1; oy++) {
+        load_row(mid, 2 * oy);
+        load_row(bot, 2 * oy + 1);
+        float4 acc = zero4();
+#pragma unroll
+        for (int k = 0; k < 3; k++) fma4(acc, top[k], wv[k]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) fma4(acc, mid[k], wv[3 + k]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) fma4(acc, bot[k], wv[6 + k]);
+        *reinterpret_cast<float4 *>(dst + (long)oy * orow + q) = epilogue4(acc, sc, bi, act);
+#pragma unroll
+        for (int k = 0; k < 3; k++) top[k] = bot[k];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Generic grouped convolution, any geometry (conv-v0.c:7-31 semantics): one thread per output element.
+ * The slow-but-always-right path behind the groupconv seam for shapes the specialised kernels do not
+ * cover.  flt = packed reference rows (row floats each, scale/bias at row-4/row-3).
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void k_conv_generic(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ flt,
+                               int n, int H, int W, int C, int ldi, int OH, int OW, int OC, int ldo,
+                               int groups, int pad, int stride, int fs, int row, int act, int skip_row0_at)
+{
+    const int cpg = C / groups, opg = OC / groups;
+    const long total = (long)n * OH * OW * OC;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int o = (int)(i % OC); long p = i / OC;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH); const long f = p / OH;
+        const int g = o / opg;
+        const float *w = flt + (long)o * row;
+        const float *img = in + f * (long)H * W * ldi + g * cpg;
+        float sum = 0.f;
+        for (int c = 0; c < cpg; c++)
+            for (int j = (oy == skip_row0_at ? 1 : 0); j < fs; j++) {
+                const int iy = oy * stride - pad + j;
+                if ((unsigned)iy >= (unsigned)H) continue;
+                for (int k = 0; k < fs; k++) {
+                    const int ix = ox * stride - pad + k;
+                    if ((unsigned)ix >= (unsigned)W) continue;
+                    sum = fmaf(__ldg(img + ((long)iy * W + ix) * ldi + c), __ldg(w + (c * fs + j) * fs + k), sum);
+                }
+            }
+        out[(f * (long)OH * OW + (long)oy * OW + ox) * ldo + o] = act_apply(fmaf(sum, w[row - 4], w[row - 3]), act);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Pool with the reference's clamped window (ffcnn.c:337-372,381-394): window [x-(fs-1)/2, +fs) cut to
+ * the image; max, or sum / fs^2.  One thread per output float4.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void k_pool(const float *__restrict__ in, float *__restrict__ out, int n, int H, int W, int C, int ldi,
+                       int OH, int OW, int ldo, int coff, int fs, int stride, int is_max)
+{
+    const int c4n = C / 4;
+    const long total = (long)n * OH * OW * c4n;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4; long p = i / c4n;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH); const long f = p / OH;
+        const int xa = max(ox * stride - (fs - 1) / 2, 0), xb = min(ox * stride - (fs - 1) / 2 + fs, W);
+        const int ya = max(oy * stride - (fs - 1) / 2, 0), yb = min(oy * stride - (fs - 1) / 2 + fs, H);
+        const float *img = in + f * (long)H * W * ldi + c;
+        float4 m = is_max ? ldg4(img + ((long)ya * W + xa) * ldi) : zero4();
+        for (int y = ya; y < yb; y++)
+            for (int x = xa; x < xb; x++) {
+                const float4 v = ldg4(img + ((long)y * W + x) * ldi);
+                if (is_max) { m.x = m.x < v.x ? v.x : m.x; m.y = m.y < v.y ? v.y : m.y; m.z = m.z < v.z ? v.z : m.z; m.w = m.w < v.w ? v.w : m.w; }
+                else        { m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w; }
+            }
+        if (!is_max) { const float d = (float)(fs * fs); m.x /= d; m.y /= d; m.z /= d; m.w /= d; }
+        *reinterpret_cast<float4 *>(out + (f * (long)OH * OW + (long)oy * OW + ox) * ldo + coff + c) = m;
+    }
+}
+
+/* nearest upsample (ffcnn.c:396-410): out[y][x] = in[y/s][x/s] */
+__global__ void k_upsample(const float *__restrict__ in, float *__restrict__ out, int n, int H, int W, int C, int ldi,
+                           int ldo, int coff, int s)
+{
+    const int c4n = C / 4, OH = H * s, OW = W * s;
+    const long total = (long)n * OH * OW * c4n;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4; long p = i / c4n;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH); const long f = p / OH;
+        *reinterpret_cast<float4 *>(out + (f * (long)OH * OW + (long)oy * OW + ox) * ldo + coff + c) =
+            ldg4(in + (f * (long)H * W + (long)(oy / s) * W + ox / s) * ldi + c);
+    }
+}
+
+/* shortcut (ffcnn.c:418-423): out = act(a + b), both operands dense (ld == c), flat float4 stream */
+__global__ void k_shortcut(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long n4, int act)
+{
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 x = ldg4(a + 4 * i), y = ldg4(b + 4 * i);
+        float4 r;
+        r.x = act_apply(x.x + y.x, act); r.y = act_apply(x.y + y.y, act);
+        r.z = act_apply(x.z + y.z, act); r.w = act_apply(x.w + y.w, act);
+        reinterpret_cast<float4 *>(out)[i] = r;
+    }
+}
+
+/* route (ffcnn.c:425-434): copy one source into channel range [coff, coff+C) of the concat tensor */
+__global__ void k_concat(const float *__restrict__ in, float *__restrict__ out, long pixels, int C, int ldi, int ldo, int coff)
+{
+    const int c4n = C / 4;
+    const long total = pixels * c4n;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4; const long p = i / c4n;
+        *reinterpret_cast<float4 *>(out + p * ldo + coff + c) = ldg4(in + p * ldi + c);
+    }
+}
+
+/* scalar variants for channel counts that are not a multiple of 4 (only reachable through odd cfgs) */
+__global__ void k_copy_strided(const float *__restrict__ in, float *__restrict__ out, long pixels, int C, int ldi, int ldo, int coff)
+{
+    const long total = pixels * C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); const long p = i / C;
+        out[p * ldo + coff + c] = in[p * ldi + c];
+    }
+}
+
+/* layout converters for the CHW boundary (groupconv seam, ffb_input_chw): [n][c][h][w] <-> [n][h][w][ld] */
+__global__ void k_chw_to_nhwc(const float *__restrict__ src, float *__restrict__ dst, int n, int C, int H, int W, int ld)
+{
+    const long total = (long)n * H * W * ld;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ld); long p = i / ld;
+        const int x = (int)(p % W); p /= W;
+        const int y = (int)(p % H); const long f = p / H;
+        dst[i] = c < C ? src[((f * C + c) * H + y) * (long)W + x] : 0.f;
+    }
+}
+
+__global__ void k_nhwc_to_chw(const float *__restrict__ src, float *__restrict__ dst, int n, int C, int H, int W, int ld)
+{
+    const long total = (long)n * C * H * W;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W); long p = i / W;
+        const int y = (int)(p % H); p /= H;
+        const int c = (int)(p % C); const long f = p / C;
+        dst[i] = src[((f * H + y) * (long)W + x) * ld + c];
+    }
+}
+
+/* weights: packed reference rows -> tap-major [taps][fn_pad] (+ scale[fn_pad], bias[fn_pad], zero padded) */
+__global__ void k_prep_weights(const float *__restrict__ flt, int row, int fn, int taps, int fn_pad,
+                               float *__restrict__ wt, float *__restrict__ scale, float *__restrict__ bias)
+{
+    const int total = taps * fn_pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + fn_pad; i += gridDim.x * blockDim.x) {
+        if (i < total) {
+            const int t = i / fn_pad, o = i % fn_pad;
+            wt[i] = o < fn ? flt[(long)o * row + t] : 0.f;
+        } else {
+            const int o = i - total;
+            scale[o] = o < fn ? flt[(long)o * row + row - 4] : 0.f;
+            bias[o]  = o < fn ? flt[(long)o * row + row - 3] : 0.f;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * yolo candidate filter (first half of ffcnn.c:438-452 on the GPU).  One warp per grid cell: the 255
+ * head values of the cell are read coalesced, each anchor's first arg-max over the class logits is
+ * found with a shuffle reduction (ties -> lowest class index, like the sequential `cs < val` scan), and
+ * lane 0 tests a float estimate of the reference confidence against thresh - margin.  Survivors are
+ * appended (atomic counter) as raw logits; the host re-does the exact double-precision decode.
+ * ---------------------------------------------------------------------------------------------- */
+struct Candidate { int frame, key, cls; float bs, cs, tx, ty, tw, th; };
+
+__global__ void k_yolo_filter(const float *__restrict__ head, int n, int cells, int ld, int classes, int head_index,
+                              int key_base, float thresh, Candidate *__restrict__ list, int *__restrict__ counter, int cap)
+{
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (long)n * cells) return;
+    const int cell = (int)(warp % cells); const int f = (int)(warp / cells);
+    const float *v = head + warp * ld;
+    const int per = 5 + classes;
+    for (int a = 0; a < 3; a++) {
+        const float *pv = v + a * per;
+        float best = -INFINITY; int bi = 0x7fffffff;
+        for (int l = lane; l < classes; l += 32) {
+            const float s = __ldg(pv + 5 + l);
+            if (s > best) { best = s; bi = l; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int   oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+            const float bs = __ldg(pv + 4);
+            const float conf = 1.0f / (1.0f + expf(-bs) * (1.0f + expf(-best)));
+            if (conf >= thresh - 1e-3f || !(conf == conf)) {
+                const int slot = atomicAdd(counter, 1);
+                if (slot < cap) {
+                    Candidate c;
+                    c.frame = f; c.key = key_base + cell * 3 + a; c.cls = bi == 0x7fffffff ? 0 : bi;
+                    c.bs = bs; c.cs = best; c.tx = __ldg(pv); c.ty = __ldg(pv + 1); c.tw = __ldg(pv + 2); c.th = __ldg(pv + 3);
+                    list[slot] = c;
+                }
+            }
+        }
+    }
+    (void)head_index;
+}
+
+__global__ void k_fill(float *p, long n, float v)
+{
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+} // namespace ffb

@@ -1,0 +1,119 @@
+/*
+ * pw_ffma.cuh -- pointwise (1x1, stride 1, groups 1) convolution as an fp32 FFMA GEMM.
+ *
+ * Reference path: convolution_pad0_fs1_stride1_all, conv-v6.c:46-91 -- out[oc][px] = act(s*(W[oc][:] . in[:][px]) + b).
+ * In NHWC the activation matrix is row-major [M = n*h*w pixels][K = ic] and the output [M][N = oc], both plain
+ * contiguous runs per M-tile.  This kernel is the exact-fp32 path (strict parity mode, the tiny-K layers that are
+ * far below the FFMA ridge, and any shape the tcgen05 kernel does not take).
+ *
+ * Persistent CTAs (grid = a multiple of the SM count) loop over M-tiles of BM = TM*TY pixels:
+ *   - the layer's weights, transposed to [K][BN] at load time, are staged once per CTA in shared memory;
+ *   - activation tiles are double-buffered with cp.async (16 B per request, zero-fill past M);
+ *   - thread (tx, ty) owns TM rows {ty + i*TY} x TN columns {tx*4 + h*NT*4 + 0..3}: A is read as
+ *     LDS.128 along K (rows padded to K+4 floats -> adjacent rows land in different bank groups,
+ *     lanes sharing a row get a broadcast), W as LDS.128 contiguous across lanes;
+ *   - epilogue act(fma(sum, scale, bias)) and float4 stores, contiguous across the lanes of a row.
+ */
+#pragma once
+#include "kernels.cuh"
+
+namespace ffb {
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+struct PwArgs {
+    const float *in; float *out; const float *wt, *scale, *bias;
+    long M; int K, N, ldi, ldo, coff, BN, NT, TY, act;
+};
+
+template <int TM, int TN>
+__global__ void __launch_bounds__(256) k_pw_ffma(const PwArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int K = a.K, BN = a.BN, NT = a.NT, TY = a.TY, KP = K + 4, BM = TM * TY;
+    float *Ws = smem;                       /* [K][BN]  */
+    float *Ss = Ws + (size_t)K * BN;        /* [BN] scale, [BN] bias */
+    float *As = Ss + 2 * BN;                /* [2][BM][KP] */
+    const int tid = threadIdx.x;
+    const long ntiles = (a.M + BM - 1) / BM;
+
+    for (int i = tid; i < K * BN / 4; i += 256) reinterpret_cast<float4 *>(Ws)[i] = ldg4(a.wt + 4 * i);
+    for (int i = tid; i < BN; i += 256) { Ss[i] = a.scale[i]; Ss[BN + i] = a.bias[i]; }
+
+    const int kc = K / 4;
+    auto prefetch = [&](long tile, int buf) {
+        const long m0 = tile * BM;
+        float *dst = As + (size_t)buf * BM * KP;
+        for (int i = tid; i < BM * kc; i += 256) {
+            const int r = i / kc, c4 = i - r * kc;
+            const long m = m0 + r;
+            const bool ok = m < a.M;
+            cp_async16(dst + r * KP + c4 * 4, a.in + (ok ? m : 0) * a.ldi + c4 * 4, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+
+    const bool worker = tid < NT * TY;
+    const int tx = tid % NT, ty = tid / NT;
+    int buf = 0;
+    if ((long)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const long next = tile + gridDim.x;
+        if (next < ntiles) { prefetch(next, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        if (worker) {
+            const float *At = As + (size_t)buf * BM * KP;
+            float acc[TM][TN];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+            for (int k4 = 0; k4 < kc; k4++) {
+                float4 av[TM];
+#pragma unroll
+                for (int i = 0; i < TM; i++) av[i] = *reinterpret_cast<const float4 *>(At + (ty + i * TY) * KP + k4 * 4);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const float *wr = Ws + (size_t)(k4 * 4 + kk) * BN + tx * 4;
+                    float w[TN];
+#pragma unroll
+                    for (int h = 0; h < TN / 4; h++) {
+                        const float4 t = *reinterpret_cast<const float4 *>(wr + h * NT * 4);
+                        w[h * 4 + 0] = t.x; w[h * 4 + 1] = t.y; w[h * 4 + 2] = t.z; w[h * 4 + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < TM; i++) {
+                        const float x = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
+#pragma unroll
+                        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(x, w[j], acc[i][j]);
+                    }
+                }
+            }
+            const long m0 = tile * BM;
+#pragma unroll
+            for (int h = 0; h < TN / 4; h++) {
+                const int n0 = tx * 4 + h * NT * 4;
+                if (n0 < a.N) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(Ss + n0), bi = *reinterpret_cast<const float4 *>(Ss + BN + n0);
+#pragma unroll
+                    for (int i = 0; i < TM; i++) {
+                        const long m = m0 + ty + i * TY;
+                        if (m < a.M) {
+                            const float4 v = make_float4(acc[i][h * 4], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+                            *reinterpret_cast<float4 *>(a.out + m * a.ldo + a.coff + n0) = epilogue4(v, sc, bi, a.act);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+} // namespace ffb

@@ -1,0 +1,14 @@
+/*
+ * pw_tc.h -- interface of the tcgen05 (5th-gen tensor core) pointwise-conv kernel, pw_tc.cu.
+ * mode: 0 auto (3xTF32 where the layer is above the FFMA ridge), 2 force 3xTF32, 3 force 1xTF32.
+ * pw_tc_plan_create returns NULL when the shape is not eligible (caller falls back to the FFMA kernel).
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+struct PwTcPlan;
+PwTcPlan   *pw_tc_plan_create(int K, int N, int act, int mode);
+void        pw_tc_plan_destroy(PwTcPlan *p);
+int         pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStream_t st);
+int         pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int coff, long M, cudaStream_t st);
+const char *pw_tc_mode_name(const PwTcPlan *p);

@@ -1,0 +1,127 @@
+/*
+ * ffcnn_b200.h -- additive C-ABI of libffcnn_b200.so (plain pointers and sizes only).
+ *
+ * The reference has no batch dimension, no device and no multi-GPU notion; its whole public
+ * surface is ffcnn.h:48-52 + conv.h:4-7 (kept, see include/ffcnn.h and include/conv.h).
+ * The entry points below are what a reference-side binding adds to drive the same hot path
+ * (net_input -> net_forward -> bbox_list, ffcnn.c:259-289,476-520) over BATCHES of frames on
+ * a B200.  Each one names the reference code it stands in for.
+ *
+ * Conventions: int return = 0 on success, negative on failure with text in ffb_last_error().
+ * All device work is enqueued on the net's stream (ffb_set_stream); calls that hand results
+ * to the host synchronise that stream themselves.  Nothing here falls back to the CPU.
+ */
+#ifndef FFCNN_B200_EXT_H
+#define FFCNN_B200_EXT_H
+
+#include <stddef.h>
+#include "ffcnn.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *ffb_last_error(void);
+int         ffb_device_count(void);                      /* 0 without a usable CUDA device */
+
+/* ---- load, split in two so the host half is testable without a GPU ---------------------- */
+
+/* Host half of net_load (ffcnn.c:114-239): cfg parse, weights read, filter packing, BN fold.
+ * weightsfile may be NULL / missing -> zero weights, as the reference (ffcnn.c:213-220). */
+NET *ffb_net_parse(const char *cfgfile, const char *weightsfile, int inputw, int inputh);
+
+/* Device half: pick `device`, upload NET.weight_buf, derive per-kernel weight layouts, plan the
+ * activation arena for up to max_batch frames.  net_load() = ffb_net_parse + ffb_net_attach(net,
+ * $FFCNN_DEVICE or 0, 1).  Re-attaching with a larger max_batch re-plans. */
+int  ffb_net_attach(NET *net, int device, int max_batch);
+
+/* Device copy of NET.weight_buf (packed rows, ffcnn.c:218-234), weight_size floats.  Exposed so
+ * a multi-GPU frontend can broadcast rank 0's weights into it (NCCL) and then call
+ * ffb_commit_weights() to rebuild the kernel-side layouts from it. */
+void *ffb_packed_weights_device(NET *net, size_t *nfloats);
+int   ffb_commit_weights(NET *net);
+
+/* Options (name, value): "dw5_exact" 0 = reproduce conv-v6's dropped kernel row on output row
+ * oh-2 of the 5x5 depthwise path (conv-v6.c:422-441; default, the named oracle), 1 = exact math
+ * (conv-v0); "pw_mode" 0 = auto, 1 = fp32 FFMA everywhere, 2 = tcgen05 3xTF32 where eligible,
+ * 3 = tcgen05 1xTF32; "graph" 1 = replay a captured CUDA graph (default), 0 = plain launches;
+ * "keep_all" 1 = every layer output gets its own buffer (needed by ffb_layer_output). */
+int  ffb_set_option(NET *net, const char *name, int value);
+int  ffb_get_option(NET *net, const char *name);
+
+int   ffb_set_stream(NET *net, void *cuda_stream);       /* cudaStream_t; NULL = engine's own */
+void *ffb_get_stream(NET *net);
+int   ffb_sync(NET *net);
+
+/* ---- batched hot path -------------------------------------------------------------------- */
+
+/* Batched net_input (ffcnn.c:259-289): n frames of w x h BGR u8, rows top-down, `pitch` bytes
+ * per row, frame stride h*pitch.  Nearest-neighbour fit to the top-left of the net input,
+ * (px - mean[c]) * norm[c], rest zero.  frames_on_device != 0: `frames` is a device pointer
+ * (resident input); otherwise it is host memory (pinned for async copies) and the H2D copy is
+ * enqueued here. */
+int  ffb_input_u8(NET *net, const unsigned char *frames, int n, int w, int h, int pitch,
+                  const float *mean, const float *norm, int frames_on_device);
+
+/* n host CHW fp32 tensors [n][c][H][W] as the network input (what layer_list[0].data holds). */
+int  ffb_input_chw(NET *net, const float *chw, int n, int s1, int s2);
+
+/* The layer loop of net_forward (ffcnn.c:488-518) for the current batch, asynchronous. */
+int  ffb_forward(NET *net);
+
+/* yolo decode + NMS (ffcnn.c:438-474,298-335) for every frame of the batch: the GPU filters
+ * candidates, the host finishes with the reference's exact libm arithmetic.  Synchronises. */
+int  ffb_detect(NET *net);
+
+/* Boxes of frame `frame` after ffb_detect; pointer valid until the next ffb_detect. */
+int  ffb_boxes(NET *net, int frame, BBOX **boxes);
+int  ffb_raw_boxes(NET *net, int frame, BBOX **boxes);   /* pre-NMS candidates in reference scan order */
+
+/* ffb_input_u8 + ffb_forward + ffb_detect: the end-to-end call (host frames in, boxes out). */
+int  ffb_detect_batch_u8(NET *net, const unsigned char *frames_host, int n, int w, int h, int pitch,
+                         const float *mean, const float *norm);
+
+/* ---- inspection / measurement ------------------------------------------------------------ */
+
+/* Copy the output of layer `layer` for frame `frame` to host as CHW fp32 (the reference layout).
+ * Needs option keep_all=1 set before ffb_forward.  Returns the number of floats. */
+long ffb_layer_output(NET *net, int layer, int frame, float *chw_host, long capacity);
+
+/* Time every layer of the current batch with CUDA events: ms[i] = mean over `reps` launches of
+ * layer i's kernel(s) (0 for aliases: dropout, single-input route).  flush_l2 != 0 evicts L2
+ * between launches. */
+int  ffb_layer_times(NET *net, float *ms, int nlayers, int reps, int flush_l2);
+
+/* Algorithmic bytes / flops per frame of layer i as defined in SURVEY 8: fp32 input + output
+ * activations + that layer's weights, each touched once. */
+int  ffb_layer_cost(NET *net, int layer, double *bytes, double *flops, char *kernel_name, int name_cap);
+
+int  ffb_launches_per_forward(NET *net);                 /* kernels enqueued by one ffb_forward */
+
+/* ---- single operator on device tensors (configs 3 and 4 of BASELINE.json; op-level parity) - */
+
+typedef struct ffb_conv ffb_conv;
+/* Same contract as groupconv (conv.h:4-7) but batched NHWC on device, weights uploaded once.
+ * packed_filter: host, fn rows of ALIGN(fs*fs*ic/groups,4)+4 floats.  flags: bit0 = dw5_exact,
+ * bits 8..15 = pw_mode. */
+ffb_conv *ffb_conv_create(const float *packed_filter, int ic, int groups, int pad, int stride,
+                          int fs, int fn, int activation, int flags);
+void      ffb_conv_destroy(ffb_conv *op);
+int       ffb_conv_run(ffb_conv *op, const float *in_nhwc_dev, float *out_nhwc_dev,
+                       int n, int ih, int iw, void *cuda_stream);
+const char *ffb_conv_kernel_name(ffb_conv *op);
+
+void *ffb_dev_alloc(size_t bytes);
+void  ffb_dev_free(void *p);
+int   ffb_copy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int   ffb_copy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+void *ffb_host_alloc_pinned(size_t bytes);
+void  ffb_host_free_pinned(void *p);
+/* layout helpers on device: [n][c][h][w] <-> [n][h][w][c] */
+int   ffb_chw_to_nhwc(const float *src_dev, float *dst_dev, int n, int c, int h, int w, void *cuda_stream);
+int   ffb_nhwc_to_chw(const float *src_dev, float *dst_dev, int n, int c, int h, int w, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
