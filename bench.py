@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of yolo-fastest-1.1 at 320x320, batch 256 per GPU (BASELINE.json's metric), on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                      times the reference's own CPU path (oracle/_ref)
+
+One "step" = one pass of the hot path over one batch of 256 synthetic frames per GPU: batched net_input kernel,
+the 112-launch layer loop (CUDA graph replay) and the yolo candidate-filter kernels.  `value` is measured with the
+u8 frames already resident in HBM (4 distinct batches rotated, 314 MB > L2); `e2e` goes through the public C-ABI
+call ffb_detect_batch_u8 with pinned HOST frames in and decoded boxes out (H2D + kernels + D2H + host decode/NMS
+inside the timed region).  Multi-GPU: frames are independent -> contiguous shards per rank, no data-path collective;
+the only traffic is one NCCL broadcast of the packed weights at load (weak scaling, 256 frames per GPU).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+BATCH = 256
+NET_W = NET_H = 320
+PITCH = 960
+ALG_BYTES_PER_FRAME = 60.11e6          # unfused fp32 activations + weights, every layer, per frame
+METRIC = "frames/sec yolo-fastest-1.1 320x320 batch256"
+WORKLOAD = "yolo-fastest-1.1.cfg 320x320 batch=%d fp32 per GPU, all layers (net_input + 131-layer forward + yolo filter)"
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def run_reference(procs: int, frames_per_proc: int):
+    """The reference's own CPU implementation of the path: oracle/_ref/ffcnn_ref_bench (unmodified ffcnn.c + conv-v6.c,
+    build.sh flags), P independent single-threaded processes.  Returns (fps, description)."""
+    import ffcnn_b200 as fb
+    cfg, wts = fb.default_model()
+    last = None
+    for exe in ("ffcnn_ref_bench", "ffcnn_ref_bench_v3"):        # -march=native build first, portable x86-64-v3 if it cannot run here
+        path = os.path.join(REPO, "oracle", "_ref", exe)
+        if not os.path.exists(path):
+            continue
+        r = subprocess.run([path, cfg, wts, str(procs), str(frames_per_proc)], capture_output=True, text=True)
+        last = r
+        if r.returncode == 0 and "fps=" in r.stdout:
+            fps = float(r.stdout.strip().split("fps=")[1])
+            return fps, f"{exe}: {procs} procs x {frames_per_proc} frames (conv-v6, build.sh flags, 320x320 synthetic u8 frames)"
+    raise RuntimeError("oracle/_ref/ffcnn_ref_bench unavailable or failed: " + (last.stderr[-300:] if last else "not built"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="also print the per-layer roofline table to stderr")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        per_proc = 12
+        for _ in range(max(1, min(W, 2))):
+            run_reference(cores, 2)
+        t0 = time.time()
+        vals = [run_reference(cores, per_proc) for _ in range(K)]
+        wall = time.time() - t0
+        fps = sum(v[0] for v in vals) / len(vals)
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * cores * per_proc / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD % args.batch, "cpu_step": "%d single-threaded processes x %d frames" % (cores, per_proc)},
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": vals[0][1]},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": wall}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ffcnn_b200 as fb
+    from ffcnn_b200 import synth, shard
+
+    if not torch.cuda.is_available() or fb.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    cfg, wts = fb.default_model()
+    net = fb.Net(cfg, wts if rank == 0 else None, 0, 0, device=local, max_batch=B)
+    stream = torch.cuda.current_stream()
+    net.set_stream(stream.cuda_stream)
+    bcast_bytes = 0
+    if world > 1:
+        bcast_bytes = shard.broadcast_weights(net, dist, device=torch.device("cuda", local))
+
+    # synthetic frames: 4 distinct resident batches per rank (seeded per global frame index), rotated across steps
+    NB = 4
+    lo, _ = shard.shard_range(B * world, rank, world)
+    host = torch.empty((NB, B, NET_H, PITCH), dtype=torch.uint8).pin_memory()
+    base = synth.frames_u8(16, NET_W, NET_H, seed0=0xFFC0 + 16 * rank)
+    hv = host.numpy()
+    for b in range(NB):
+        for f in range(B):
+            hv[b, f] = base[(b * 5 + f) % 16]
+            hv[b, f, f % NET_H, :8] = (lo + f + b) & 0xFF          # every frame distinct
+    dev = host.cuda(non_blocking=False)
+    frame_bytes = B * NET_H * PITCH
+
+    def step_resident(i):
+        net.input_u8(dev[i % NB].data_ptr(), B, NET_W, NET_H, PITCH, on_device=True)
+        net.forward()
+        net.detect_enqueue()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step_resident(i)
+    net.detect_finish()
+    launches_per_step = 1 + net.launches_per_forward() + 2
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(K):
+        step_resident(i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    net.detect_finish()
+
+    # end to end through the public call: pinned host frames -> boxes on the host
+    for i in range(2):
+        net.detect_batch_u8(host[i % NB].data_ptr(), B, NET_W, NET_H, PITCH)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    KE = max(3, K // 2)
+    d2h = 0
+    e0.record(stream)
+    for i in range(KE):
+        net.detect_batch_u8(host[i % NB].data_ptr(), B, NET_W, NET_H, PITCH)
+        d2h += net.last_d2h_bytes()
+    e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    nboxes = sum(len(net.boxes(f)) for f in range(B))
+    clocks = sampler.summary() if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        value = world * B * K / (ms * 1e-3)
+        e2e = world * B * KE / (ms_e2e * 1e-3)
+        # per-layer CUDA-event timings (same batch), grouped by kernel: the dominant kernel's roofline
+        lt = net.layer_times(reps=5)
+        groups = {}
+        for i in range(net.layer_num):
+            by, fl, name = net.layer_cost(i)
+            if lt[i] > 0:
+                g = groups.setdefault(name, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "layers": 0})
+                g["ms"] += float(lt[i]); g["bytes"] += by * B; g["flops"] += fl * B; g["layers"] += 1
+        top = max(groups, key=lambda k: groups[k]["ms"])
+        tg = groups[top]
+        achieved = tg["bytes"] / (tg["ms"] * 1e-3) / 1e9
+        total_ms = sum(g["ms"] for g in groups.values())
+        if args.layers:
+            for i in range(net.layer_num):
+                by, fl, name = net.layer_cost(i)
+                if lt[i] > 0:
+                    print("L%-3d %-16s %8.4f ms %8.1f GB/s  %5.1f%% of HBM peak" % (i, name, lt[i], by * B / (lt[i] * 1e-3) / 1e9,
+                                                                                  100 * by * B / (lt[i] * 1e-3) / 1e9 / peak), file=sys.stderr)
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD % B,
+                       "frames_per_gpu_per_step": B, "l2": "inputs rotate over %d distinct resident batches (%d MB u8) and the activation arena (%d MB) exceeds L2"
+                       % (NB, NB * frame_bytes >> 20, net.get_option("arena_mb")),
+                       "parallelism": "dp%d: contiguous frame shards, no data-path collective; weights broadcast once over NCCL (%d B)" % (world, bcast_bytes),
+                       "pw_mode": net.get_option("pw_mode"), "weights": "yolo-fastest-1.1.weights" if os.path.exists(wts) else "zero"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": d2h // KE,
+                    "ms_per_step": ms_e2e / KE, "api": "ffb_detect_batch_u8 (pinned host u8 frames in, decoded+NMS boxes out)", "boxes_last_batch": nboxes},
+            "gpu_launches": launches_per_step * K,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_share_of_step": tg["ms"] / total_ms, "layers_in_kernel": tg["layers"],
+                         "whole_graph": {"achieved": ALG_BYTES_PER_FRAME * B * K / (ms * 1e-3) / 1e9 / 1, "frac": ALG_BYTES_PER_FRAME * B * K / (ms * 1e-3) / 1e9 / peak,
+                                         "alg_bytes_per_frame": ALG_BYTES_PER_FRAME},
+                         "by_kernel": {k: {"ms": round(v["ms"], 4), "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                                           "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3), "layers": v["layers"]} for k, v in sorted(groups.items())}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                fps, desc = run_reference(cores, 40)
+                line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": desc}
+            except Exception as ex:                      # the baseline is a reported number, never a reason to lose the GPU line
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "failed: %s" % ex}
+        print(json.dumps(line))
+    net.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

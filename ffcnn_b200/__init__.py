@@ -88,6 +88,9 @@ def lib():
         "ffb_input_chw": (C.c_int, [NP, fp, C.c_int, C.c_int, C.c_int]),
         "ffb_forward": (C.c_int, [NP]),
         "ffb_detect": (C.c_int, [NP]),
+        "ffb_detect_enqueue": (C.c_int, [NP]),
+        "ffb_detect_finish": (C.c_int, [NP]),
+        "ffb_last_d2h_bytes": (C.c_long, [NP]),
         "ffb_boxes": (C.c_int, [NP, C.c_int, C.POINTER(C.POINTER(BBOX))]),
         "ffb_raw_boxes": (C.c_int, [NP, C.c_int, C.POINTER(C.POINTER(BBOX))]),
         "ffb_detect_batch_u8": (C.c_int, [NP, vp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]),
@@ -124,7 +127,8 @@ def lib():
 
 EXPORTS = ["ffb_last_error", "ffb_device_count", "ffb_net_parse", "ffb_net_attach", "ffb_packed_weights_device",
            "ffb_commit_weights", "ffb_set_option", "ffb_get_option", "ffb_set_stream", "ffb_get_stream", "ffb_sync",
-           "ffb_input_u8", "ffb_input_chw", "ffb_forward", "ffb_detect", "ffb_boxes", "ffb_raw_boxes",
+           "ffb_input_u8", "ffb_input_chw", "ffb_forward", "ffb_detect", "ffb_detect_enqueue", "ffb_detect_finish",
+           "ffb_last_d2h_bytes", "ffb_boxes", "ffb_raw_boxes",
            "ffb_detect_batch_u8", "ffb_layer_output", "ffb_layer_times", "ffb_layer_cost", "ffb_launches_per_forward",
            "ffb_conv_create", "ffb_conv_destroy", "ffb_conv_run", "ffb_conv_kernel_name", "ffb_dev_alloc", "ffb_dev_free",
            "ffb_copy_h2d", "ffb_copy_d2h", "ffb_host_alloc_pinned", "ffb_host_free_pinned", "ffb_chw_to_nhwc",
@@ -261,6 +265,15 @@ class Net:
 
     def detect(self):
         _check(self._L.ffb_detect(self.p), "ffb_detect")
+
+    def detect_enqueue(self) -> int:
+        return _check(self._L.ffb_detect_enqueue(self.p), "ffb_detect_enqueue")
+
+    def detect_finish(self):
+        _check(self._L.ffb_detect_finish(self.p), "ffb_detect_finish")
+
+    def last_d2h_bytes(self) -> int:
+        return self._L.ffb_last_d2h_bytes(self.p)
 
     def boxes(self, frame: int = 0, raw: bool = False) -> np.ndarray:
         ptr = C.POINTER(BBOX)()

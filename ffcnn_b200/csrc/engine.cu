@@ -239,7 +239,7 @@ struct ffb_engine {
     /* detection */
     Candidate *d_cand = nullptr, *h_cand = nullptr; int *d_count = nullptr, *h_count = nullptr; int cand_cap = 0;
     std::vector<std::vector<BBOX>> boxes, raw;
-    int s1 = 1, s2 = 1;
+    int s1 = 1, s2 = 1; size_t d2h_bytes = 0;
     /* L2 flush scratch for ffb_layer_times */
     float *d_flush = nullptr; size_t flush_floats = 0;
 };
@@ -644,19 +644,28 @@ int ffb_forward(NET *net)
 int ffb_launches_per_forward(NET *net) { ffb_engine *e = engine_of(net); return e ? e->launches : -1; }
 
 /* ---- detection ---- */
-int ffb_detect(NET *net)
+struct Head { int layer, cells, gw, gh, key_base; };
+
+static std::vector<Head> yolo_heads(ffb_engine *e, int *total_keys)
+{
+    NET *net = &e->net->pub; std::vector<Head> heads; int key = 0;
+    for (int i = 1; i < net->layer_num; i++) if (net->layer_list[i].type == LAYER_TYPE_YOLO) {
+        const Tens &t = e->outs[i - 1];
+        heads.push_back({ i, t.h * t.w, t.w, t.h, key }); key += t.h * t.w * 3;
+    }
+    if (total_keys) *total_keys = key;
+    return heads;
+}
+
+/* GPU half: candidate filter kernels + async copy of the candidate count. No synchronisation. */
+int ffb_detect_enqueue(NET *net)
 {
     ffb_engine *e = engine_of(net);
     if (!e) return -1;
     CK(cudaSetDevice(e->device));
-    const int n = e->batch, L = net->layer_num;
+    const int n = e->batch;
     if (n < 1) { ffb_set_error("ffb_detect: no batch"); return -1; }
-    struct Head { int layer, cells, gw, gh, key_base; };
-    std::vector<Head> heads; int key = 0;
-    for (int i = 1; i < L; i++) if (net->layer_list[i].type == LAYER_TYPE_YOLO) {
-        const Tens &t = e->outs[i - 1];
-        heads.push_back({ i, t.h * t.w, t.w, t.h, key }); key += t.h * t.w * 3;
-    }
+    int key = 0; std::vector<Head> heads = yolo_heads(e, &key);
     const int cap = std::max(4096, std::min(key, 2048) * n);
     if (cap > e->cand_cap) {
         CK(cudaStreamSynchronize(e->stream));
@@ -675,8 +684,20 @@ int ffb_detect(NET *net)
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(e->h_count, e->d_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    return (int)heads.size();
+}
+
+/* Host half: wait, fetch the candidates, exact decode (reference scan order) and per-frame NMS. */
+int ffb_detect_finish(NET *net)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    CK(cudaSetDevice(e->device));
+    const int n = e->batch;
+    std::vector<Head> heads = yolo_heads(e, nullptr);
     CK(cudaStreamSynchronize(e->stream));
     int cnt = std::min(*e->h_count, e->cand_cap);
+    e->d2h_bytes = sizeof(int) + (size_t)cnt * sizeof(Candidate);
     if (cnt > 0) {
         CK(cudaMemcpyAsync(e->h_cand, e->d_cand, (size_t)cnt * sizeof(Candidate), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
@@ -702,6 +723,14 @@ int ffb_detect(NET *net)
     }
     return 0;
 }
+
+int ffb_detect(NET *net)
+{
+    if (ffb_detect_enqueue(net) < 0) return -1;
+    return ffb_detect_finish(net);
+}
+
+long ffb_last_d2h_bytes(NET *net) { ffb_engine *e = engine_of(net); return e ? (long)e->d2h_bytes : -1; }
 
 int ffb_boxes(NET *net, int frame, BBOX **boxes)
 {

@@ -72,6 +72,11 @@ int  ffb_forward(NET *net);
 /* yolo decode + NMS (ffcnn.c:438-474,298-335) for every frame of the batch: the GPU filters
  * candidates, the host finishes with the reference's exact libm arithmetic.  Synchronises. */
 int  ffb_detect(NET *net);
+/* The two halves of ffb_detect, for callers that overlap host work with the GPU: enqueue = filter kernels
+ * + async copy of the candidate count (returns the number of yolo heads); finish = wait, fetch, decode, NMS. */
+int  ffb_detect_enqueue(NET *net);
+int  ffb_detect_finish(NET *net);
+long ffb_last_d2h_bytes(NET *net);                        /* bytes the last ffb_detect_finish copied to the host */
 
 /* Boxes of frame `frame` after ffb_detect; pointer valid until the next ffb_detect. */
 int  ffb_boxes(NET *net, int frame, BBOX **boxes);

@@ -1,0 +1,247 @@
+"""GPU (B200): the CUDA path behind the C-ABI against the oracle and the committed reference goldens.
+
+Tolerances (written here as the contract):
+  * feature maps:  max|gpu - oracle| <= 2e-5 * max|oracle layer|   (the reference differs from itself by 8.8e-6 between
+                   its -O2 and -Ofast builds; fp32 FFMA in a different summation order lands around 1e-6)
+  * boxes:         same candidate set (class, cell), coordinates within 1e-4 px * (s1/s2 rescale) of the oracle,
+                   scores within 1e-6
+  * integer/byte:  net_input's u8 -> fp32 conversion is bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import ffcnn_b200 as fb
+from ffcnn_b200 import synth
+from oracle import oracle as orc, ref
+from conftest import boxes_close
+
+pytestmark = pytest.mark.gpu
+
+FEAT_TOL = 2e-5
+PW_MODES = [int(m) for m in os.environ.get("FFCNN_TEST_PW_MODES", "0,1").split(",")]
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(float(np.abs(b).max()), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def net4(assets):
+    cfg, wts, _ = assets
+    n = fb.Net(cfg, wts, 0, 0, device=0, max_batch=4)
+    n.set_option("keep_all", 1)
+    yield n
+    n.close()
+
+
+def test_extension_is_native_and_on_gpu():
+    assert fb.device_count() >= 1
+    assert os.path.exists(fb.LIB_PATH)
+
+
+def test_groupconv_seam_against_reference_goldens(golden):
+    """conv.h:4-7 through the GPU on every committed case: v6 semantics by default, exact math with FFCNN_DW5_EXACT."""
+    g = golden["groupconv_cases"]
+    for n, (iw, ih, ic, grp, pad, st, fs, fn, act) in enumerate(g["cases"]):
+        x, f = g[f"x{n}"], g[f"f{n}"]
+        want = g[f"v6_{n}"] if f"v6_{n}" in g.files else g[f"v0_{n}"]
+        got = fb.groupconv(x, f, iw, ih, ic, grp, pad, st, fs, fn, act)
+        assert got.shape == want.shape and rel_err(got, want) < FEAT_TOL, (n, rel_err(got, want))
+    os.environ["FFCNN_DW5_EXACT"] = "1"
+    try:
+        for n in (8, 9, 10):
+            iw, ih, ic, grp, pad, st, fs, fn, act = g["cases"][n]
+            got = fb.groupconv(g[f"x{n}"], g[f"f{n}"], iw, ih, ic, grp, pad, st, fs, fn, act)
+            assert rel_err(got, g[f"v0_{n}"]) < FEAT_TOL, n
+    finally:
+        del os.environ["FFCNN_DW5_EXACT"]
+
+
+@pytest.mark.parametrize("pw_mode", PW_MODES)
+def test_every_layer_of_testbmp_against_oracle(assets, oracle_layers, net4, pw_mode):
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    net4.set_option("pw_mode", pw_mode)
+    net4.net_input(img, w, h)
+    x = net4.input_tensor().copy()
+    got = net4.net_forward()
+    outs, raw, fin = orc.forward(oracle_layers, x, net4.net.s1, net4.net.s2, v6_quirk=True)
+    worst = 0.0
+    for i, o in enumerate(outs):
+        if o is None:
+            continue
+        e = rel_err(net4.layer_output(i, 0), o)
+        worst = max(worst, e)
+        assert e < FEAT_TOL, (i, e)
+    graw = net4.boxes(0, raw=True)
+    assert len(graw) == len(raw) and [int(t) for t in graw["type"]] == [int(t) for t in raw["type"]]
+    boxes_close(got, fin, px=2e-4, score=1e-6)      # 1e-4 px at net scale x s1/s2 = 2 rescale
+    net4.set_option("pw_mode", 0)
+
+
+def test_reference_api_flow_and_goldens(assets, golden):
+    """net_load -> net_input -> net_forward -> bbox_list exactly as ffcnn.c's main() drives it, both geometries."""
+    cfg, wts, bmp = assets
+    L = fb.lib()
+    img, w, h = ref.load_bmp(bmp)
+    mean, norm = (fb.C.c_float * 3)(0, 0, 0), (fb.C.c_float * 3)(1 / 255., 1 / 255., 1 / 255.)
+    for (iw, ih, key, scale) in ((0, 0, "testbmp_320", 2.0), (w, h, "testbmp_640x448", 1.0)):
+        p = L.net_load(cfg.encode(), wts.encode(), iw, ih)
+        assert p
+        for _ in range(2):                                                    # second pass replays the CUDA graph
+            L.net_input(p, img.ctypes.data, w, h, mean, norm)
+            L.net_forward(p)
+        net = p.contents
+        got = np.frombuffer(fb.C.string_at(net.bbox_list, net.bbox_num * 24), fb.BOX_DTYPE)
+        boxes_close(got, golden[key]["v6_O2_final"], px=1e-4 * scale, score=1e-6)
+        boxes_close(got, golden[key]["v6_final"], px=2.5e-4 * scale, score=1e-6)       # the -Ofast build (own noise 9e-5 px)
+        L.net_free(p)
+
+
+def test_heads_against_committed_goldens(assets, golden, net4):
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    net4.net_input(img, w, h)
+    net4.net_forward()
+    for hid in (120, 129):
+        assert rel_err(net4.layer_output(hid, 0), golden["testbmp_320"][f"v6_O2_head{hid}"]) < FEAT_TOL
+
+
+def test_batched_u8_path_against_goldens(assets, golden, oracle_layers, net4):
+    """ffb_input_u8 (GPU net_input) + batch of 4 distinct frames: input bit-exact, every frame's layers match its golden."""
+    g = golden["synth_320"]
+    fr = synth.frames_u8(4)
+    net4.input_u8(fr, 4, 320, 320, 960)
+    net4.forward(); net4.detect()
+    for f in range(4):
+        want_in, _, _ = orc.net_input(fr[f], 320, 320, 320, 320)
+        assert np.array_equal(net4.layer_output(-1, f).view(np.uint32), want_in.view(np.uint32))     # byte work: bit-exact
+        for i in (0, 10, 57, 108, 114, 116, 124, 129):
+            o = net4.layer_output(i, f)
+            assert abs(float(np.abs(o).max()) / float(g[f"s1_f{f}_v6_O2_maxabs"][i]) - 1) < 1e-4, (f, i)
+            assert abs(float(o.astype(np.float64).sum()) - float(g[f"s1_f{f}_v6_O2_sum"][i])) <= 2e-5 * float(g[f"s1_f{f}_v6_O2_maxabs"][i]) * o.size
+        assert len(net4.boxes(f, raw=True)) == len(g[f"s1_f{f}_v6_O2_raw"])
+    for hid in (120, 129):
+        assert rel_err(net4.layer_output(hid, 0), g[f"s1_f0_v6_O2_head{hid}"]) < FEAT_TOL
+
+
+def test_picture_frames_boxes_match_reference(assets, golden):
+    """Set S2 (frames derived from test.bmp, shifted): decode + NMS are exercised; boxes equal the reference's."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    s2f = synth.shifted_frames_from(img, w, h, 20)
+    net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=20)
+    net.detect_batch_u8(s2f, 20, 320, 320, 960)
+    g = golden["synth_320"]
+    for f in (0, 3, 7, 19):
+        want_raw, want = g[f"s2_f{f}_raw"], g[f"s2_f{f}_final"]
+        raw = net.boxes(f, raw=True)
+        assert len(raw) == len(want_raw) and [int(t) for t in raw["type"]] == [int(t) for t in want_raw["type"]]
+        boxes_close(net.boxes(f), want, px=1e-4, score=1e-6)
+    net.close()
+
+
+def test_resized_input_matches_host_net_input(assets):
+    """GPU net_input with a real resize (640x424 bmp -> 320x212 corner) equals the host/reference arithmetic bit for bit."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=2)
+    net.set_option("keep_all", 1)
+    two = np.stack([img, img[::-1].copy()])
+    net.input_u8(two, 2, w, h, img.shape[1])
+    net.forward()
+    for f in range(2):
+        want, s1, s2 = orc.net_input(two[f], w, h, 320, 320)
+        assert np.array_equal(net.layer_output(-1, f).view(np.uint32), want.view(np.uint32))
+    assert (net.net.s1, net.net.s2) == (640, 320)
+    net.close()
+
+
+def test_full_batch_256_properties(assets, golden):
+    """BASELINE size (batch 256): frames are independent, so every copy of a frame must give identical bits wherever
+    it sits in the batch, and each distinct frame must still match its golden checksum; graph replay is idempotent."""
+    cfg, wts, _ = assets
+    B = 256
+    base = synth.frames_u8(4)
+    frames = np.concatenate([base] * (B // 4), axis=0)
+    net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=B)
+    net.set_option("keep_all", 1)
+    d = fb.DeviceBuffer(frames.nbytes).upload(frames)
+    net.input_u8(d.ptr, B, 320, 320, 960, on_device=True)
+    net.forward(); net.forward(); net.forward()
+    net.detect()
+    g = golden["synth_320"]
+    first = {f: net.layer_output(129, f) for f in range(4)}
+    for f in range(4):
+        assert abs(float(first[f].astype(np.float64).sum()) - float(g[f"s1_f{f}_v6_O2_sum"][129])) <= 2e-5 * float(g[f"s1_f{f}_v6_O2_maxabs"][129]) * first[f].size
+    for pos in (4, 127, 128, 252, 255):
+        assert np.array_equal(net.layer_output(129, pos).view(np.uint32), first[pos % 4].view(np.uint32)), pos
+        assert np.array_equal(net.layer_output(120, pos).view(np.uint32), net.layer_output(120, pos % 4).view(np.uint32)), pos
+    assert net.launches_per_forward() > 0
+    net.close(); d.free()
+
+
+def test_liveness_arena_gives_same_heads_as_keep_all(assets):
+    """The reused-buffer plan (ffcnn.c:511-517's free-when-unreferenced, done statically) must not change results."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    s2f = synth.shifted_frames_from(img, w, h, 8)
+    res = []
+    for keep in (1, 0):
+        net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=8)
+        net.set_option("keep_all", keep)
+        net.detect_batch_u8(s2f, 8, 320, 320, 960)
+        res.append([net.boxes(f).tobytes() for f in range(8)])
+        if keep == 0:
+            assert net.get_option("arena_mb") < 60
+        net.close()
+    assert res[0] == res[1]
+
+
+def test_dw5_exact_mode_matches_conv_v0(assets, oracle_layers):
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=1)
+    net.set_option("keep_all", 1)
+    net.set_option("dw5_exact", 1)
+    net.net_input(img, w, h)
+    x = net.input_tensor().copy()
+    net.net_forward()
+    outs, _, _ = orc.forward(oracle_layers, x, 640, 320, v6_quirk=False)
+    for i in (116, 118, 125, 127, 129):
+        assert rel_err(net.layer_output(i, 0), outs[i]) < FEAT_TOL, i
+    quirk, _, _ = orc.forward(oracle_layers, x, 640, 320, v6_quirk=True)
+    assert rel_err(net.layer_output(116, 0), quirk[116]) > 1e-3          # and it really differs from the v6 default
+    net.close()
+
+
+@pytest.mark.parametrize("pw_mode", PW_MODES)
+def test_microbench_shapes_against_oracle(pw_mode):
+    """BASELINE configs 3 and 4 at a batch the oracle finishes in seconds: dw3x3 160x160x96 and 1x1 40x40 192->192."""
+    rng = np.random.default_rng(7)
+    for (ih, iw, ic, grp, pad, st, fs, fn, act, n) in ((160, 160, 96, 96, 1, 1, 3, 96, 2, 2), (40, 40, 192, 1, 0, 1, 1, 192, 2, 3),
+                                                       (20, 20, 120, 1, 0, 1, 1, 255, 0, 2), (40, 40, 96, 96, 1, 2, 3, 96, 2, 2)):
+        k = fs * fs * (ic // grp); row = ((k + 3) & ~3) + 4
+        f = np.zeros((fn, row), np.float32)
+        f[:, :k] = rng.standard_normal((fn, k)) / np.sqrt(k)
+        f[:, row - 4] = rng.uniform(0.5, 1.5, fn); f[:, row - 3] = rng.uniform(-0.5, 0.5, fn)
+        x = rng.standard_normal((n, ic, ih, iw)).astype(np.float32)
+        op = fb.ConvOp(f, ic, grp, pad, st, fs, fn, act, pw_mode=pw_mode)
+        y = op(np.ascontiguousarray(x.transpose(0, 2, 3, 1)))
+        for b in range(n):
+            want = orc.conv_raw(x[b], f, iw, ih, ic, grp, pad, st, fs, fn, act, v6_quirk=True)
+            assert rel_err(y[b].transpose(2, 0, 1), want) < FEAT_TOL, (op.kernel, b)
+        op.close()
+
+
+def test_ragged_and_odd_shapes_through_generic_kernel():
+    """Shapes no specialised kernel takes (channels not a multiple of 4, grouped with >1 channel per group, even kernels)."""
+    rng = np.random.default_rng(11)
+    for (iw, ih, ic, grp, pad, st, fs, fn, act) in ((9, 7, 6, 2, 1, 1, 3, 4, 2), (5, 5, 3, 1, 0, 1, 1, 5, 1), (8, 6, 4, 1, 0, 2, 2, 5, 0), (1, 1, 8, 1, 0, 1, 1, 8, 2)):
+        k = fs * fs * (ic // grp); row = ((k + 3) & ~3) + 4
+        f = np.zeros((fn, row), np.float32); f[:, :k] = rng.standard_normal((fn, k)); f[:, row - 4] = 0.75; f[:, row - 3] = 0.1
+        x = rng.standard_normal((ic, ih, iw)).astype(np.float32)
+        got = fb.groupconv(x, f, iw, ih, ic, grp, pad, st, fs, fn, act)
+        assert rel_err(got, orc.conv_raw(x, f, iw, ih, ic, grp, pad, st, fs, fn, act, False)) < FEAT_TOL

@@ -1,0 +1,194 @@
+"""CPU: the host-C half of libffcnn_b200.so (cfg/weights loader, net_input, yolo decode, NMS, BMP, net_dump) against
+the oracle, and the shape of the C-ABI itself: the library loads without a GPU, exports every symbol the headers
+declare, and refuses to compute (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import ffcnn_b200 as fb
+from ffcnn_b200 import synth
+from oracle import oracle as orc, ref
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = fb.lib()
+    declared = set()
+    for hdr in ("ffcnn.h", "conv.h", "bmpfile.h", "ffcnn_b200.h"):
+        text = open(os.path.join(REPO, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b((?:ffb|net|bmp)_\w+|groupconv)\s*\(", text))
+    assert len(declared) >= 45
+    missing = sorted(s for s in declared if not hasattr(L, s))
+    assert not missing, missing
+    assert declared <= set(fb.EXPORTS) | {"ffb_conv"}, sorted(declared - set(fb.EXPORTS))
+
+
+def test_struct_layout_matches_reference_abi():
+    # LP64 layout of ffcnn.h:16-46 -- callers read NET fields directly (ffcnn.c:583-586)
+    # numbers printed by a C program compiled against /root/reference/ffcnn.h (gcc, x86-64)
+    assert (C.sizeof(fb.LAYER), C.sizeof(fb.BBOX), C.sizeof(fb.NET)) == (120, 24, 104)
+    assert (fb.NET.bbox_list.offset, fb.NET.bbox_num.offset, fb.NET.s1.offset, fb.NET.weight_buf.offset,
+            fb.NET.cnntempbuf.offset, fb.NET.timeused.offset) == (16, 24, 32, 48, 56, 68)
+    assert (fb.LAYER.data.offset, fb.LAYER.w.offset, fb.LAYER.depend_list.offset, fb.LAYER.anchor_list.offset,
+            fb.LAYER.scale_x_y.offset) == (8, 24, 64, 88, 116)
+    # and our own header compiled by gcc agrees with the ctypes mirror
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "ffcnn.h"\nint main(){printf("%zu %zu %zu %zu %zu", sizeof(LAYER), sizeof(BBOX), '
+           'sizeof(NET), offsetof(NET, weight_buf), offsetof(LAYER, anchor_list)); return 0;}')
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "a.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), os.path.join(d, "a.c"), "-o", os.path.join(d, "a")], check=True)
+        assert subprocess.run([os.path.join(d, "a")], capture_output=True, text=True).stdout == "120 24 104 48 88"
+
+
+def test_parse_matches_oracle_loader(assets, oracle_layers):
+    cfg, wts, _ = assets
+    net = fb.Net(cfg, wts, 0, 0, device=None)
+    assert net.layer_num == len(oracle_layers) == 131
+    assert net.net.weight_size == 356576 and net.net.bbox_max == 320 * 320 * 3 * 4 // 24
+    for i, L in enumerate(oracle_layers):
+        a, b = net.layer(i), net.layer(i + 1)
+        assert (a.type, a.w, a.h, a.c) == (L.type, L.w, L.h, L.c), i
+        if L.type != orc.YOLO:
+            assert (b.w, b.h, b.c) == (L.ow, L.oh, L.oc), i
+        if L.type == orc.CONV:
+            assert (a.fn, a.fs, a.stride, a.groups, a.pad, a.batchnorm, a.activation) == (L.fn, L.fs, L.stride, L.groups, L.pad, L.batchnorm, L.activation)
+        if L.type in (orc.SHORTCUT, orc.ROUTE):
+            assert list(a.depend_list)[:a.depend_num] == L.deps
+        if L.type == orc.YOLO:
+            assert a.class_num == 80 and [tuple(p) for p in a.anchor_list] == L.anchors
+            assert a.ignore_thres == np.float32(0.45) and a.scale_x_y == 1.0
+    mine = net.packed_weights()
+    want = np.concatenate([L.filt.reshape(-1) for L in oracle_layers if L.type == orc.CONV])
+    assert np.array_equal(mine.view(np.uint32), want.view(np.uint32))           # BN fold bit-exact (ffcnn.c:230-231)
+    net.close()
+
+
+def test_parse_input_override_and_errors(assets, tmp_path):
+    cfg, wts, _ = assets
+    net = fb.Net(cfg, wts, 640, 424, device=None)           # rounded up to x32 (ffcnn.c:133-134)
+    assert net.input_whc == (640, 448, 3) and (net.layer(130).w, net.layer(130).h) == (40, 28)
+    net.close()
+    with pytest.raises(fb.FfcnnError):
+        fb.Net(str(tmp_path / "missing.cfg"), wts, device=None)
+    zero = fb.Net(cfg, str(tmp_path / "missing.weights"), device=None)        # reference: zero weights, no error
+    assert zero.net.weight_size == 356576 and not zero.packed_weights().any()
+    zero.close()
+    # minimal hand-written cfg: unknown sections skipped, defaults (stride/groups 0 -> 1), pad flag semantics
+    p = tmp_path / "tiny.cfg"
+    p.write_text("[net]\nwidth=8\nheight=8\nchannels=4\n[foo]\nx=1\n[conv]\nfilters=8\nsize=3\npad=1\nactivation=relu\n"
+                 "[maxpool]\nsize=2\nstride=2\n[avgpool]\nsize=3\n[upsample]\nstride=2\n[route]\nlayers=-1,-4\n")
+    t = fb.Net(str(p), None, device=None)
+    assert t.layer_num == 5
+    l0 = t.layer(0)
+    assert (l0.fn, l0.fs, l0.pad, l0.stride, l0.groups, l0.activation) == (8, 3, 1, 1, 1, 1)
+    assert (t.layer(2).w, t.layer(2).h) == (4, 4) and t.layer(2).type == 1
+    assert (t.layer(5).c, t.layer(5).w) == (16, 8)
+    t.close()
+
+
+def test_net_input_host_matches_oracle(assets):
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    for iw, ih in ((0, 0), (640, 424), (96, 224)):
+        net = fb.Net(cfg, None, iw, ih, device=None)
+        W, H, _ = net.input_whc
+        net.net_input(img, w, h)
+        want, s1, s2 = orc.net_input(img, w, h, W, H)
+        assert (net.net.s1, net.net.s2) == (s1, s2)
+        assert np.array_equal(net.input_tensor().view(np.uint32), want.view(np.uint32))
+        net.close()
+    net = fb.Net(cfg, None, 0, 0, device=None)
+    fr = synth.frames_u8(1)[0]
+    net.net_input(fr, 320, 320, mean=(10, 20, 30), norm=(0.5, 0.25, 2.0))
+    want, _, _ = orc.net_input(fr, 320, 320, 320, 320, mean=(10, 20, 30), norm=(0.5, 0.25, 2.0))
+    assert np.array_equal(net.input_tensor(), want)
+    net.close()
+
+
+def test_host_decode_and_nms_match_reference_goldens(assets, golden):
+    """ffb_decode_head_chw + ffb_nms on the reference's own head tensors reproduce its raw and final boxes bit-exactly."""
+    cfg, wts, _ = assets
+    L = fb.lib()
+    L.ffb_decode_head_chw.argtypes = [C.POINTER(fb.LAYER), C.POINTER(C.c_float)] + [C.c_int] * 4 + [C.POINTER(fb.BBOX), C.c_int, C.c_int]
+    L.ffb_decode_head_chw.restype = C.c_int
+    L.ffb_nms.argtypes = [C.POINTER(fb.BBOX), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.ffb_nms.restype = C.c_int
+    net = fb.Net(cfg, wts, 0, 0, device=None)
+    g = golden["testbmp_320"]
+    for variant in ("v6_O2", "v0"):
+        boxes = (fb.BBOX * 4096)()
+        n = 0
+        for yolo_layer, hid in ((121, 120), (130, 129)):
+            head = np.ascontiguousarray(g[f"{variant}_head{hid}"])
+            n = L.ffb_decode_head_chw(C.byref(net.layer(yolo_layer)), head.ctypes.data_as(C.POINTER(C.c_float)), head.shape[2], head.shape[1], 320, 320, boxes, n, 4096)
+        raw = np.frombuffer(C.string_at(boxes, n * 24), fb.BOX_DTYPE)
+        assert raw.tobytes() == g[f"{variant}_raw"].tobytes()
+        m = L.ffb_nms(boxes, n, 0.5, 1, 640, 320)
+        fin = np.frombuffer(C.string_at(boxes, m * 24), fb.BOX_DTYPE)
+        assert fin.tobytes() == g[f"{variant}_final"].tobytes()
+    assert L.ffb_nms(boxes, 0, 0.5, 1, 1, 1) == 0
+    net.close()
+
+
+def test_no_cpu_fallback(assets):
+    if fb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    cfg, wts, _ = assets
+    assert not fb.lib().net_load(cfg.encode(), wts.encode(), 0, 0)             # NULL, message on stderr
+    net = fb.Net(cfg, wts, device=None)
+    with pytest.raises(fb.FfcnnError, match="no CUDA device"):
+        net.attach(0, 1)
+    with pytest.raises(fb.FfcnnError):
+        net.forward()
+    with pytest.raises(fb.FfcnnError):
+        fb.groupconv(np.zeros((4, 4, 4), np.float32), np.zeros((4, 8), np.float32), 4, 4, 4, 1, 0, 1, 1, 4, 0)
+    net.close()
+
+
+def test_bmp_roundtrip(assets, tmp_path):
+    _, _, bmp = assets
+    L = fb.lib()
+
+    class BMP(C.Structure):
+        _fields_ = [("width", C.c_int), ("height", C.c_int), ("stride", C.c_int), ("cdepth", C.c_int), ("pdata", C.c_void_p)]
+    for f in (L.bmp_load, L.bmp_save):
+        f.argtypes, f.restype = [C.POINTER(BMP), C.c_char_p], C.c_int
+    L.bmp_free.argtypes = [C.POINTER(BMP)]
+    L.bmp_rectangle.argtypes = [C.POINTER(BMP)] + [C.c_int] * 7
+    L.bmp_getpixel.argtypes = [C.POINTER(BMP), C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+    b = BMP()
+    assert L.bmp_load(C.byref(b), bmp.encode()) == 0
+    want, w, h = ref.load_bmp(bmp)
+    assert (b.width, b.height, b.stride, b.cdepth) == (w, h, want.shape[1], 24)
+    assert C.string_at(b.pdata, b.stride * b.height) == want.tobytes()
+    L.bmp_rectangle(C.byref(b), 5, 6, 50, 40, 0, 255, 0)
+    r, g_, bl = C.c_int(), C.c_int(), C.c_int()
+    L.bmp_getpixel(C.byref(b), 5, 20, C.byref(r), C.byref(g_), C.byref(bl))
+    assert (r.value, g_.value, bl.value) == (0, 255, 0)
+    out = str(tmp_path / "o.bmp")
+    assert L.bmp_save(C.byref(b), out.encode()) == 0
+    b2 = BMP()
+    assert L.bmp_load(C.byref(b2), out.encode()) == 0
+    assert C.string_at(b2.pdata, b2.stride * b2.height) == C.string_at(b.pdata, b.stride * b.height)
+    assert L.bmp_load(C.byref(b2), b"/nonexistent.bmp") == -1
+    L.bmp_free(C.byref(b)); L.bmp_free(C.byref(b2))
+
+
+@pytest.mark.skipif(not ref.available("v6_O2"), reason="oracle/_ref not built")
+def test_net_dump_prints_the_reference_table(assets):
+    cfg, wts, _ = assets
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import ffcnn_b200 as fb; from oracle import ref\n"
+            "which = sys.argv[1]\n"
+            "if which == 'mine':\n    n = fb.Net(%r, None, 0, 0, device=None); fb.lib().net_dump(n.p)\n"
+            "else:\n    r = ref.RefNet(%r, %r, 0, 0, 'v6_O2'); r.L.net_dump.argtypes=[__import__('ctypes').c_void_p]; r.L.net_dump(r.net)\n") % (REPO, cfg, cfg, wts)
+    outs = [subprocess.run([sys.executable, "-c", code, w], capture_output=True, text=True, check=True).stdout for w in ("mine", "ref")]
+    assert outs[0] == outs[1] and outs[0].count("\n") == 132
