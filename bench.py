@@ -95,7 +95,7 @@ def run_reference(procs: int, frames_per_proc: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -143,7 +143,8 @@ def main():
     B = args.batch
     cfg, wts = fb.default_model()
     net = fb.Net(cfg, wts if rank == 0 else None, 0, 0, device=local, max_batch=B)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()            # a real (non-legacy) stream shared by torch's events and the library's launches
+    torch.cuda.set_stream(stream)
     net.set_stream(stream.cuda_stream)
     bcast_bytes = 0
     if world > 1:

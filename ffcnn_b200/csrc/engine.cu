@@ -919,19 +919,20 @@ extern "C" void groupconv(float *datai, float *dataf, float *datao, int iw, int 
     ffb_conv *op = ffb_conv_create(dataf, ic, ig, ipad, istride, fs, fn, activation, flags);
     if (!op) { fprintf(stderr, "ffcnn_b200: groupconv: %s\n", ffb_last_error()); return; }
     const int ldi = FFB_ALIGN(ic, 4), ldo = FFB_ALIGN(fn, 4);
-    const size_t in_chw = (size_t)ic * ih * iw, out_chw = (size_t)fn * oh * ow;
-    const size_t in_n = (size_t)ih * iw * ldi, out_n = (size_t)oh * ow * ldo;
+    /* every sub-buffer starts 256-byte aligned (the kernels use 128-bit accesses) */
+    const size_t in_chw = FFB_ALIGN((size_t)ic * ih * iw, 64), out_chw = FFB_ALIGN((size_t)fn * oh * ow, 64);
+    const size_t in_n = FFB_ALIGN((size_t)ih * iw * ldi, 64), out_n = FFB_ALIGN((size_t)oh * ow * ldo, 64);
     float *d = NULL;
     if (cudaMalloc(&d, (in_chw + out_chw + in_n + out_n) * sizeof(float)) != cudaSuccess) {
         fprintf(stderr, "ffcnn_b200: groupconv: device allocation failed\n"); cudaGetLastError(); conv_release(op); return;
     }
     float *d_in_chw = d, *d_out_chw = d + in_chw, *d_in = d_out_chw + out_chw, *d_out = d_in + in_n;
-    bool ok = cudaMemcpy(d_in_chw, datai, in_chw * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess
+    bool ok = cudaMemcpy(d_in_chw, datai, (size_t)ic * ih * iw * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess
            && cudaMemset(d_out, 0, out_n * sizeof(float)) == cudaSuccess
            && ffb_chw_to_nhwc(d_in_chw, d_in, 1, ic, ih, iw, 0) == 0
            && conv_run(op, d_in, ldi, d_out, ldo, 0, 1, ih, iw, 0) == 0
            && ffb_nhwc_to_chw(d_out, d_out_chw, 1, fn, oh, ow, 0) == 0
-           && cudaMemcpy(datao, d_out_chw, out_chw * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+           && cudaMemcpy(datao, d_out_chw, (size_t)fn * oh * ow * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
     if (!ok) fprintf(stderr, "ffcnn_b200: groupconv failed: %s / %s\n", ffb_last_error(), cudaGetErrorString(cudaGetLastError()));
     cudaFree(d);
     conv_release(op);
