@@ -1,7 +1,379 @@
-/* pw_tc.cu -- placeholder until the tcgen05 kernel lands: no shape is eligible yet. */
+/*
+ * pw_tc.cu -- pointwise (1x1) convolution on the 5th-generation tensor cores (tcgen05, sm_100a).
+ *
+ * Reference path: convolution_pad0_fs1_stride1_all (conv-v6.c:46-91): out[px][oc] = act(s[oc] * sum_ic W[oc][ic] *
+ * in[px][ic] + b[oc]).  In batched NHWC this is one GEMM  D[M x N] = A[M x K] * W[N x K]^T  with M = n*h*w pixels,
+ * K = ic, N = oc, both operands K-major -- a genuine dense contraction, so it goes to the tensor pipe:
+ *
+ *   warp 0  TMA producer : A tiles [128 px x 32 ch] (128-byte rows, SWIZZLE_128B) through a S-stage mbarrier ring;
+ *                          the layer's weights once per CTA (resident for the whole persistent loop)
+ *   warp 1  MMA issuer   : one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=NS, K=8 per instruction),
+ *                          accumulators live in TMEM (double buffered), completion via tcgen05.commit -> mbarrier
+ *   warps 2-5            : (a) 3xTF32 split of the activation tile, (b) epilogue: tcgen05.ld -> act(fma(acc, s, b))
+ *                          -> swizzled smem staging -> TMA store (coalesced 128-byte rows, clipped at N and M)
+ *
+ * Numerics.  One TF32 pass keeps 10 mantissa bits per operand and misses the box tolerance by ~0.4 px, so
+ * the default is the 3xTF32 split: x = hi + lo with hi = x & ~0x1fff (exactly representable in tf32), lo = x - hi
+ * (exact in fp32), and D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi accumulated in fp32 -- error ~2^-21 per product.
+ * W_hi / W_lo are split once at load; A_hi overwrites the TMA-landed tile in place and A_lo goes straight to TENSOR
+ * MEMORY (tcgen05.st) and is consumed by the A-from-TMEM form of tcgen05.mma, so the split costs no extra shared memory.
+ * Mode 3 (1xTF32) skips the split (raw fp32 bits are fed to the tensor core).
+ *
+ * Everything is HBM-bound by design: per 128-pixel tile the MMA work (K*N/16 clk per pass) is far below the time
+ * the tile's bytes need at 1/148th of HBM bandwidth, so the pipeline exists to keep ~S*Kc*16 KB of loads in flight per SM.
+ */
+#include <cstdio>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
 #include "pw_tc.h"
-PwTcPlan   *pw_tc_plan_create(int, int, int, int) { return nullptr; }
-void        pw_tc_plan_destroy(PwTcPlan *) {}
-int         pw_tc_prepare(PwTcPlan *, const float *, int, cudaStream_t) { return -1; }
-int         pw_tc_run(PwTcPlan *, const float *, int, float *, int, int, long, cudaStream_t) { return -1; }
-const char *pw_tc_mode_name(const PwTcPlan *) { return "none"; }
+#include "sm100.cuh"
+
+extern "C" void ffb_set_error(const char *fmt, ...);
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128;                 /* pixels per tile = UMMA M */
+constexpr int A_SUB = BM * 128;         /* bytes of one [128 x 32 fp32] sub-tile */
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+
+struct TcArgs {
+    long M;
+    int K, Kc, ksteps_total, NS, nsl, S, OB, act, split;
+    int tiles;                          /* M tiles */
+    uint32_t tmem_cols;
+    const float *scale, *bias;          /* [nsl*NS], zero padded */
+};
+
+__device__ __forceinline__ float act_apply(float v, int act)
+{
+    return act == 2 ? (v > 0.f ? v : 0.1f * v) : act == 1 ? fmaxf(v, 0.f) : v;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+        const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmD, const TcArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int Kc = a.Kc, NS = a.NS, S = a.S;
+    const uint32_t b_sub = (uint32_t)NS * 128;                       /* bytes of one [NS x 32] weight sub-tile */
+    uint8_t *sBh = smem;
+    uint8_t *sBl = sBh + (size_t)Kc * b_sub;
+    uint8_t *sA  = sBl + (a.split ? (size_t)Kc * b_sub : 0);
+    uint8_t *sO  = sA + (size_t)S * Kc * A_SUB;
+    float   *sSc = reinterpret_cast<float *>(sO + (size_t)a.OB * A_SUB);
+    float   *sBi = sSc + NS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sBi + NS);
+    uint64_t *full = bars, *empty = bars + S, *conv = bars + 2 * S, *tfull = bars + 3 * S, *tempty = tfull + 2, *bfull = tempty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slice = blockIdx.x % a.nsl, group = blockIdx.x / a.nsl, ngroups = gridDim.x / a.nsl;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmD);
+        if (a.split) tma_prefetch_desc(&tmBl);
+        for (int s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(conv + s, EPI_THREADS); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, EPI_THREADS); }
+        mbar_init(bfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    for (int i = threadIdx.x; i < NS; i += NUM_THREADS) { sSc[i] = a.scale[slice * NS + i]; sBi[i] = a.bias[slice * NS + i]; }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_col0 = 0, alo_col0 = 2 * NS;
+
+    if (warp == 0) {
+        /* ===================== TMA producer ===================== */
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bfull, (uint32_t)((a.split ? 2 : 1) * Kc) * b_sub);
+            for (int kc = 0; kc < Kc; kc++) {
+                tma_load_2d(sBh + (size_t)kc * b_sub, &tmBh, kc * 32, slice * NS, bfull);
+                if (a.split) tma_load_2d(sBl + (size_t)kc * b_sub, &tmBl, kc * 32, slice * NS, bfull);
+            }
+            int it = 0;
+            for (int t = group; t < a.tiles; t += ngroups, it++) {
+                const int s = it % S; const uint32_t ph = (it / S) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                mbar_arrive_expect_tx(full + s, (uint32_t)Kc * A_SUB);
+                for (int kc = 0; kc < Kc; kc++) tma_load_2d(sA + ((size_t)s * Kc + kc) * A_SUB, &tmA, kc * 32, t * BM, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        /* ===================== MMA issuer ===================== */
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_tf32(BM, NS);
+            mbar_wait(bfull, 0);
+            int it = 0;
+            for (int t = group; t < a.tiles; t += ngroups, it++) {
+                const int s = it % S; const uint32_t ph = (it / S) & 1;
+                const int ab = it & 1; const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(a.split ? conv + s : full + s, ph);
+                mbar_wait(tempty + ab, aph ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d = tmem_base + acc_col0 + ab * NS;
+                const uint32_t a_base = smem_u32(sA + (size_t)s * Kc * A_SUB);
+                const uint32_t bh_base = smem_u32(sBh), bl_base = smem_u32(sBl);
+                uint32_t accum = 0;
+                if (a.split) {
+                    const uint32_t alo = tmem_base + alo_col0 + s * Kc * 32;
+                    for (int ks = 0; ks < a.ksteps_total; ks++) {           /* A_lo (TMEM) x W_hi */
+                        const int kc = ks >> 2, kk = ks & 3;
+                        mma_tf32_ts(d, alo + ks * 8, umma_desc_sw128(bh_base + kc * b_sub + kk * 32), idesc, accum); accum = 1;
+                    }
+                    for (int ks = 0; ks < a.ksteps_total; ks++) {           /* A_hi x W_lo */
+                        const int kc = ks >> 2, kk = ks & 3;
+                        mma_tf32_ss(d, umma_desc_sw128(a_base + kc * A_SUB + kk * 32), umma_desc_sw128(bl_base + kc * b_sub + kk * 32), idesc, 1);
+                    }
+                }
+                for (int ks = 0; ks < a.ksteps_total; ks++) {               /* A_hi x W_hi (or raw x raw in 1xTF32 mode) */
+                    const int kc = ks >> 2, kk = ks & 3;
+                    mma_tf32_ss(d, umma_desc_sw128(a_base + kc * A_SUB + kk * 32), umma_desc_sw128(bh_base + kc * b_sub + kk * 32), idesc, accum); accum = 1;
+                }
+                tc_commit(empty + s);            /* smem stage (and its A_lo columns) reusable once these MMAs retire */
+                tc_commit(tfull + ab);           /* accumulator ready for the epilogue */
+            }
+        }
+    } else {
+        /* ===================== split + epilogue warps (one thread per tile row) ===================== */
+        const int q = warp & 3;                              /* TMEM lane quarter this warp may access */
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 64;                     /* 0..127 */
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int nchunks = (NS + 31) / 32;
+        int ob = 0;
+
+        auto epilogue = [&](int t, int it) {
+            const int ab = it & 1; const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(tfull + ab, aph);
+            tc_fence_after_sync();
+            for (int j = 0; j < nchunks; j++) {
+                uint8_t *stage = sO + (size_t)ob * A_SUB;
+                if (et == 0) { if (a.OB == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+                named_bar_sync(1, EPI_THREADS);              /* staging buffer `ob` is free again */
+                const int halves = (NS - j * 32) >= 32 ? 2 : 1;
+                for (int hf = 0; hf < halves; hf++) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32 + hf * 16, r);
+                    tmem_ld_wait();
+                    const float *sc = sSc + j * 32 + hf * 16, *bi = sBi + j * 32 + hf * 16;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        float4 v;
+                        v.x = act_apply(fmaf(__uint_as_float(r[4 * c + 0]), sc[4 * c + 0], bi[4 * c + 0]), a.act);
+                        v.y = act_apply(fmaf(__uint_as_float(r[4 * c + 1]), sc[4 * c + 1], bi[4 * c + 1]), a.act);
+                        v.z = act_apply(fmaf(__uint_as_float(r[4 * c + 2]), sc[4 * c + 2], bi[4 * c + 2]), a.act);
+                        v.w = act_apply(fmaf(__uint_as_float(r[4 * c + 3]), sc[4 * c + 3], bi[4 * c + 3]), a.act);
+                        const int chunk = hf * 4 + c;
+                        *reinterpret_cast<float4 *>(stage + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+                    }
+                }
+                if (j == nchunks - 1) { tc_fence_before_sync(); mbar_arrive(tempty + ab); }   /* accumulator drained */
+                fence_proxy_async_smem();
+                named_bar_sync(1, EPI_THREADS);
+                if (et == 0) { tma_store_2d(&tmD, stage, slice * NS + j * 32, t * BM); tma_store_commit(); }
+                ob = (ob + 1) % a.OB;
+            }
+        };
+
+        int it = 0, prev_t = -1;
+        for (int t = group; t < a.tiles; t += ngroups, it++) {
+            if (a.split) {
+                const int s = it % S; const uint32_t ph = (it / S) & 1;
+                mbar_wait(full + s, ph);
+                uint8_t *arow = sA + (size_t)s * Kc * A_SUB + row * 128;
+                const uint32_t alo = tmem_base + lane_addr + alo_col0 + s * Kc * 32;
+                for (int kc = 0; kc < Kc; kc++) {
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; c2++) {
+                        float4 *p0 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2) ^ (row & 7)) << 4));
+                        float4 *p1 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2 + 1) ^ (row & 7)) << 4));
+                        const float4 x0 = *p0, x1 = *p1;
+                        float4 h0, h1; uint32_t lo[8];
+                        h0.x = __uint_as_float(__float_as_uint(x0.x) & 0xffffe000u); h0.y = __uint_as_float(__float_as_uint(x0.y) & 0xffffe000u);
+                        h0.z = __uint_as_float(__float_as_uint(x0.z) & 0xffffe000u); h0.w = __uint_as_float(__float_as_uint(x0.w) & 0xffffe000u);
+                        h1.x = __uint_as_float(__float_as_uint(x1.x) & 0xffffe000u); h1.y = __uint_as_float(__float_as_uint(x1.y) & 0xffffe000u);
+                        h1.z = __uint_as_float(__float_as_uint(x1.z) & 0xffffe000u); h1.w = __uint_as_float(__float_as_uint(x1.w) & 0xffffe000u);
+                        lo[0] = __float_as_uint(x0.x - h0.x); lo[1] = __float_as_uint(x0.y - h0.y); lo[2] = __float_as_uint(x0.z - h0.z); lo[3] = __float_as_uint(x0.w - h0.w);
+                        lo[4] = __float_as_uint(x1.x - h1.x); lo[5] = __float_as_uint(x1.y - h1.y); lo[6] = __float_as_uint(x1.z - h1.z); lo[7] = __float_as_uint(x1.w - h1.w);
+                        *p0 = h0; *p1 = h1;
+                        tmem_st8(alo + kc * 32 + c2 * 8, lo);
+                    }
+                }
+                fence_proxy_async_smem();                    /* in-place A_hi writes -> visible to the tensor core (async proxy) */
+                tmem_st_wait();
+                tc_fence_before_sync();
+                mbar_arrive(conv + s);
+            }
+            if (prev_t >= 0) epilogue(prev_t, it - 1);
+            prev_t = t;
+        }
+        if (prev_t >= 0) epilogue(prev_t, it - 1);
+        if (et == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, a.tmem_cols); }
+}
+
+__global__ void k_split_weights(const float *__restrict__ flt, int row, int N, int K, int Kld, float *__restrict__ hi, float *__restrict__ lo)
+{
+    const int total = N * Kld;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i / Kld, k = i - n * Kld;
+        const float w = k < K ? flt[(long)n * row + k] : 0.f;
+        const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+        hi[i] = h; lo[i] = w - h;
+    }
+}
+
+__global__ void k_scale_bias(const float *__restrict__ flt, int row, int N, int NP, float *__restrict__ sc, float *__restrict__ bi)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NP; i += gridDim.x * blockDim.x) {
+        sc[i] = i < N ? flt[(long)i * row + row - 4] : 0.f;
+        bi[i] = i < N ? flt[(long)i * row + row - 3] : 0.f;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+/* fp32 [rows][cols] with row stride `stride_floats`; box = 32 cols x box_rows, 128-byte swizzle, OOB reads give 0 */
+int make_map(CUtensorMap *m, const void *base, uint64_t cols, uint64_t rows, uint64_t stride_floats, uint32_t box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { ffb_set_error("cuTensorMapEncodeTiled unavailable"); return -1; }
+    cuuint64_t gdim[2] = { cols, rows }, gstr[1] = { stride_floats * 4 };
+    cuuint32_t box[2] = { 32, box_rows }, estr[2] = { 1, 1 };
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ffb_set_error("cuTensorMapEncodeTiled failed (%d): cols=%llu rows=%llu stride=%llu box_rows=%u base=%p", (int)r,
+                                           (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)stride_floats, box_rows, base); return -1; }
+    return 0;
+}
+
+} // namespace
+
+struct PwTcPlan {
+    int K, N, act, mode, split;
+    int Kc, ksteps_total, NS, nsl, S, OB, NP, Kld;
+    uint32_t tmem_cols; size_t smem;
+    float *d_bhi, *d_blo, *d_scb;
+    CUtensorMap tmBh, tmBl;
+    int num_sms;
+};
+
+static bool plan_tiling(PwTcPlan *p)
+{
+    const int N16 = (p->N + 15) & ~15;
+    const size_t limit = 227 * 1024 - 2048;          /* dynamic smem ceiling minus alignment slack */
+    for (int minS = 2; minS >= 1; minS--)
+        for (int nsl = 1; nsl <= 8; nsl++) {
+            int NS = (N16 + nsl - 1) / nsl;
+            NS = nsl > 1 ? (NS + 31) & ~31 : (NS + 15) & ~15;
+            if (NS > 256) continue;
+            const size_t B = (size_t)(p->split ? 2 : 1) * p->Kc * NS * 128;
+            for (int S = (minS == 2 ? 4 : 1); S >= minS; S--)
+                for (int OB = 2; OB >= 1; OB--) {
+                    const size_t smem = B + (size_t)S * p->Kc * A_SUB + (size_t)OB * A_SUB + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
+                    const int tmem = 2 * NS + (p->split ? S * p->Kc * 32 : 0);
+                    if (smem <= limit && tmem <= 512) {
+                        p->NS = NS; p->nsl = nsl; p->S = S; p->OB = OB; p->NP = nsl * NS;
+                        p->smem = smem + 1024;
+                        if (p->smem < 120 * 1024) p->smem = 120 * 1024;       /* one CTA per SM: TMEM is allocated per CTA */
+                        uint32_t c = 32; while ((int)c < tmem) c <<= 1;
+                        p->tmem_cols = c;
+                        return true;
+                    }
+                }
+        }
+    return false;
+}
+
+PwTcPlan *pw_tc_plan_create(int K, int N, int act, int mode)
+{
+    if (K % 4 || K < 8 || N < 8 || N > 2048) return nullptr;
+    if (mode == 0 && K < 16) return nullptr;                   /* tiny-K layers sit far below the FFMA ridge: the FFMA kernel streams them */
+    if (!encode_fn()) return nullptr;
+    PwTcPlan *p = new PwTcPlan(); memset(p, 0, sizeof *p);
+    p->K = K; p->N = N; p->act = act; p->mode = mode == 3 ? 3 : 2; p->split = p->mode == 2;
+    p->Kc = (K + 31) / 32;
+    p->ksteps_total = (p->Kc - 1) * 4 + ((K - 32 * (p->Kc - 1)) + 7) / 8;
+    p->Kld = (K + 3) & ~3;
+    if (!plan_tiling(p)) { delete p; return nullptr; }
+    int dev = 0; cudaDeviceProp prop;
+    cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
+    p->num_sms = prop.multiProcessorCount;
+    return p;
+}
+
+void pw_tc_plan_destroy(PwTcPlan *p)
+{
+    if (!p) return;
+    cudaFree(p->d_bhi); cudaFree(p->d_blo); cudaFree(p->d_scb);
+    delete p;
+}
+
+const char *pw_tc_mode_name(const PwTcPlan *p) { return p && p->mode == 3 ? "1xtf32" : "3xtf32"; }
+
+int pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStream_t st)
+{
+    if (!p->d_scb && cudaMalloc(&p->d_scb, 2 * (size_t)p->NP * sizeof(float)) != cudaSuccess) { ffb_set_error("pw_tc: cudaMalloc failed"); return -1; }
+    k_scale_bias<<<(p->NP + 255) / 256, 256, 0, st>>>(d_packed, row, p->N, p->NP, p->d_scb, p->d_scb + p->NP);
+    if (p->split) {
+        const size_t n = (size_t)p->N * p->Kld;
+        if (!p->d_bhi && (cudaMalloc(&p->d_bhi, n * sizeof(float)) != cudaSuccess || cudaMalloc(&p->d_blo, n * sizeof(float)) != cudaSuccess)) { ffb_set_error("pw_tc: cudaMalloc failed"); return -1; }
+        k_split_weights<<<(int)((n + 255) / 256), 256, 0, st>>>(d_packed, row, p->N, p->K, p->Kld, p->d_bhi, p->d_blo);
+        if (make_map(&p->tmBh, p->d_bhi, p->K, p->N, p->Kld, p->NS) != 0) return -1;
+        if (make_map(&p->tmBl, p->d_blo, p->K, p->N, p->Kld, p->NS) != 0) return -1;
+    } else {
+        /* 1xTF32: the packed reference rows ARE the K-major weight matrix (row stride K+4 floats) */
+        if (make_map(&p->tmBh, d_packed, p->K, p->N, row, p->NS) != 0) return -1;
+        p->tmBl = p->tmBh;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_pw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { ffb_set_error("pw_tc: cannot raise dynamic smem limit"); return -1; }
+        attr_set = true;
+    }
+    if (cudaGetLastError() != cudaSuccess) { ffb_set_error("pw_tc: weight preparation launch failed"); return -1; }
+    return 0;
+}
+
+int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int coff, long M, cudaStream_t st)
+{
+    CUtensorMap tmA, tmD;
+    if (make_map(&tmA, in, p->K, (uint64_t)M, ldi, BM) != 0) return -1;
+    if (make_map(&tmD, out + coff, p->N, (uint64_t)M, ldo, BM) != 0) return -1;
+    TcArgs a;
+    a.M = M; a.K = p->K; a.Kc = p->Kc; a.ksteps_total = p->ksteps_total; a.NS = p->NS; a.nsl = p->nsl; a.S = p->S; a.OB = p->OB;
+    a.act = p->act; a.split = p->split; a.tiles = (int)((M + BM - 1) / BM); a.tmem_cols = p->tmem_cols;
+    a.scale = p->d_scb; a.bias = p->d_scb + p->NP;
+    long want = (long)a.tiles * p->nsl;
+    int grid = (int)(want < p->num_sms ? want : p->num_sms);
+    grid -= grid % p->nsl;
+    if (grid < p->nsl) grid = p->nsl;
+    k_pw_tc<<<grid, NUM_THREADS, p->smem, st>>>(tmA, p->tmBh, p->tmBl, tmD, a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ffb_set_error("pw_tc launch failed: %s (grid %d smem %zu)", cudaGetErrorString(e), grid, p->smem); return -1; }
+    return 0;
+}
