@@ -13,8 +13,11 @@
  *                          -> swizzled smem staging -> TMA store (coalesced 128-byte rows, clipped at N and M)
  *
  * Numerics.  One TF32 pass keeps 10 mantissa bits per operand and misses the box tolerance by ~0.4 px, so
- * the default is the 3xTF32 split: x = hi + lo with hi = x & ~0x1fff (exactly representable in tf32), lo = x - hi
- * (exact in fp32), and D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi accumulated in fp32 -- error ~2^-21 per product.
+ * the default is the 3xTF32 split: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) (both exactly representable
+ * in tf32, so the result does not depend on how the tensor core truncates its inputs -- measured: it truncates), and
+ * D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi accumulated in fp32.  Round-to-nearest matters: a truncating split leaves an
+ * error of constant sign (~2^-22 per product) that compounds over the 55 pointwise layers of the graph; the rounded
+ * split is zero-mean (~2^-24).
  * W_hi / W_lo are split once at load; A_hi overwrites the TMA-landed tile in place and A_lo goes straight to TENSOR
  * MEMORY (tcgen05.st) and is consumed by the A-from-TMEM form of tcgen05.mma, so the split costs no extra shared memory.
  * Mode 3 (1xTF32) skips the split (raw fp32 bits are fed to the tensor core).
@@ -47,6 +50,14 @@ struct TcArgs {
     uint32_t tmem_cols;
     const float *scale, *bias;          /* [nsl*NS], zero padded */
 };
+
+/* round-to-nearest (ties away) to tf32: the result is an fp32 value whose low 13 mantissa bits are zero */
+__device__ __forceinline__ float tf32_rna(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 
 __device__ __forceinline__ float act_apply(float v, int act)
 {
@@ -197,12 +208,12 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                         float4 *p1 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2 + 1) ^ (row & 7)) << 4));
                         const float4 x0 = *p0, x1 = *p1;
                         float4 h0, h1; uint32_t lo[8];
-                        h0.x = __uint_as_float(__float_as_uint(x0.x) & 0xffffe000u); h0.y = __uint_as_float(__float_as_uint(x0.y) & 0xffffe000u);
-                        h0.z = __uint_as_float(__float_as_uint(x0.z) & 0xffffe000u); h0.w = __uint_as_float(__float_as_uint(x0.w) & 0xffffe000u);
-                        h1.x = __uint_as_float(__float_as_uint(x1.x) & 0xffffe000u); h1.y = __uint_as_float(__float_as_uint(x1.y) & 0xffffe000u);
-                        h1.z = __uint_as_float(__float_as_uint(x1.z) & 0xffffe000u); h1.w = __uint_as_float(__float_as_uint(x1.w) & 0xffffe000u);
-                        lo[0] = __float_as_uint(x0.x - h0.x); lo[1] = __float_as_uint(x0.y - h0.y); lo[2] = __float_as_uint(x0.z - h0.z); lo[3] = __float_as_uint(x0.w - h0.w);
-                        lo[4] = __float_as_uint(x1.x - h1.x); lo[5] = __float_as_uint(x1.y - h1.y); lo[6] = __float_as_uint(x1.z - h1.z); lo[7] = __float_as_uint(x1.w - h1.w);
+                        h0.x = tf32_rna(x0.x); h0.y = tf32_rna(x0.y); h0.z = tf32_rna(x0.z); h0.w = tf32_rna(x0.w);
+                        h1.x = tf32_rna(x1.x); h1.y = tf32_rna(x1.y); h1.z = tf32_rna(x1.z); h1.w = tf32_rna(x1.w);
+                        lo[0] = __float_as_uint(tf32_rna(x0.x - h0.x)); lo[1] = __float_as_uint(tf32_rna(x0.y - h0.y));
+                        lo[2] = __float_as_uint(tf32_rna(x0.z - h0.z)); lo[3] = __float_as_uint(tf32_rna(x0.w - h0.w));
+                        lo[4] = __float_as_uint(tf32_rna(x1.x - h1.x)); lo[5] = __float_as_uint(tf32_rna(x1.y - h1.y));
+                        lo[6] = __float_as_uint(tf32_rna(x1.z - h1.z)); lo[7] = __float_as_uint(tf32_rna(x1.w - h1.w));
                         *p0 = h0; *p1 = h1;
                         tmem_st8(alo + kc * 32 + c2 * 8, lo);
                     }
@@ -230,8 +241,8 @@ __global__ void k_split_weights(const float *__restrict__ flt, int row, int N, i
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int n = i / Kld, k = i - n * Kld;
         const float w = k < K ? flt[(long)n * row + k] : 0.f;
-        const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-        hi[i] = h; lo[i] = w - h;
+        const float h = tf32_rna(w);
+        hi[i] = h; lo[i] = tf32_rna(w - h);
     }
 }
 
@@ -312,7 +323,9 @@ static bool plan_tiling(PwTcPlan *p)
 PwTcPlan *pw_tc_plan_create(int K, int N, int act, int mode)
 {
     if (K % 4 || K < 8 || N < 8 || N > 2048) return nullptr;
-    if (mode == 0 && K < 16) return nullptr;                   /* tiny-K layers sit far below the FFMA ridge: the FFMA kernel streams them */
+    /* auto: measured on B200 (profiles/r1b_pw_kernel_choice.txt) -- with K <= 32 the per-tile pipeline overhead of this kernel
+       exceeds what the FFMA streaming kernel needs for the few FMAs per byte; from K = 48 up the tensor pipe wins */
+    if (mode == 0 && (K < 48 || (N < 16 && K < 96))) return nullptr;
     if (!encode_fn()) return nullptr;
     PwTcPlan *p = new PwTcPlan(); memset(p, 0, sizeof *p);
     p->K = K; p->N = N; p->act = act; p->mode = mode == 3 ? 3 : 2; p->split = p->mode == 2;

@@ -76,5 +76,5 @@ P("sum of per-layer ms", "%.3f" % float(ms.sum()))
 for r in rows: P("L%-3d %-14s %8.4f ms %8.1f GB/s %6.2f TFLOP/s" % r)
 agg = {}
 for i, kn, m, g, tf in rows: agg[kn] = agg.get(kn, 0) + m
-P(json.dumps({k: round(v, 4) for k, v in agg.items()}))
+P(json.dumps({k: round(float(v), 4) for k, v in agg.items()}))
 t = time.time(); net.detect(); P("detect ms", (time.time() - t) * 1e3)
