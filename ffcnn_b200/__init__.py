@@ -365,11 +365,11 @@ class DeviceBuffer:
 class ConvOp:
     """One convolution layer on device NHWC tensors (configs 3 and 4 of BASELINE.json, op-level parity)."""
 
-    def __init__(self, filt: np.ndarray, ic, groups, pad, stride, fs, fn, act, dw5_exact=False, pw_mode=0):
+    def __init__(self, filt: np.ndarray, ic, groups, pad, stride, fs, fn, act, dw5_exact=False, pw_mode=0, dw_mode=0):
         filt = np.ascontiguousarray(filt, np.float32)
         self.geom = (ic, groups, pad, stride, fs, fn, act)
         self.h = lib().ffb_conv_create(filt.ctypes.data_as(C.POINTER(C.c_float)), ic, groups, pad, stride, fs, fn, act,
-                                       (1 if dw5_exact else 0) | (pw_mode << 8))
+                                       (1 if dw5_exact else 0) | (pw_mode << 8) | (dw_mode << 16))
         if not self.h:
             raise FfcnnError(f"ffb_conv_create: {_err()}")
 

@@ -28,6 +28,7 @@
 #include "../../include/conv.h"
 #include "kernels.cuh"
 #include "pw_ffma.cuh"
+#include "dw_tma.cuh"
 #include "pw_tc.h"
 
 using namespace ffb;
@@ -56,7 +57,7 @@ enum ConvKind { CK_GENERIC = 0, CK_PW_FFMA, CK_PW_TC, CK_DW_S1_3, CK_DW_S1_5, CK
 
 struct ffb_conv {
     int ic, groups, pad, stride, fs, fn, act, row, taps;
-    int dw5_exact, pw_mode;
+    int dw5_exact, pw_mode, dw_mode;   /* dw_mode 0 = TMA-fed stencil, 1 = register-window LDG kernel */
     ConvKind kind;
     const float *d_packed;      /* packed reference rows on device */
     float *d_owned_packed;      /* set when this op owns d_packed (standalone ops) */
@@ -103,6 +104,71 @@ static void pw_plan(ffb_conv *op)
         if (found) break;
     }
     op->smem = pw_smem(K, op->fn_pad, op->TM, op->TY);
+}
+
+/* ---- TMA-fed depthwise 3x3 s1 kernel: tile planner + launcher ---- */
+struct DwPlan { int CB, TW, TH, RC, nch, IWb, IHb, ntx, nty, ntc, stages; size_t smem; };
+
+/* Pick channel block / tile / row chunking: one work item (2 px x 4 ch x RC rows) per thread, stage <= 56 KB (3 stages),
+ * minimising  halo re-read factor x shared-memory reads per output, with penalties for idle threads and for thin TMA
+ * rows when the channel block is not the whole (contiguous) pixel. */
+static bool dw_plan(int C, int OH, int OW, DwPlan *p)
+{
+    const size_t stage_limit = 56 * 1024;
+    double best = 1e30; bool ok = false;
+    for (int CB = 4; CB <= C && CB <= 256; CB += 4) {
+        if (C % CB) continue;
+        for (int ntx = 1; ntx <= 40 && ntx <= OW; ntx++) {
+            const int TW = (OW + ntx - 1) / ntx, pairs = (TW + 1) / 2, IWb = 2 * pairs + 2;
+            if (IWb > 256) continue;
+            const int per_chunk = pairs * (CB / 4);
+            if (per_chunk > DW_THREADS) continue;
+            const size_t rowb = (size_t)IWb * CB * 4;
+            int thmax = (int)(stage_limit / rowb) - 2; if (thmax > OH) thmax = OH; if (thmax > 254) thmax = 254;
+            if (thmax < 1) continue;
+            for (int nty = (OH + thmax - 1) / thmax; nty <= OH; nty++) {
+                const int TH = (OH + nty - 1) / nty;
+                int nch = DW_THREADS / per_chunk; if (nch > TH) nch = TH; if (nch < 1) nch = 1;
+                const int RC = (TH + nch - 1) / nch; nch = (TH + RC - 1) / RC;
+                const double halo = (double)IWb * (TH + 2) / ((double)TW * TH);
+                const double lds = 2.0 * (RC + 2) / RC;                       /* LDS.128 per output float4 */
+                const double idle = (double)DW_THREADS / (per_chunk * nch);
+                const double thin = (CB < C && CB * 4 < 256) ? 1.0 + 0.25 * (256.0 / (CB * 4) - 1.0) : 1.0;
+                const double score = (halo + 0.35 * lds) * (0.75 + 0.25 * idle) * thin;
+                if (score < best) {
+                    best = score; ok = true;
+                    p->CB = CB; p->TW = TW; p->TH = TH; p->RC = RC; p->nch = nch; p->IWb = IWb; p->IHb = TH + 2;
+                    p->ntx = (OW + TW - 1) / TW; p->nty = nty; p->ntc = C / CB;
+                }
+                if (RC >= 12 || TH <= 4) break;                               /* shorter tiles only get worse from here */
+            }
+        }
+    }
+    if (!ok) return false;
+    p->stages = 3;
+    const size_t stage = (((size_t)p->IHb * p->IWb * p->CB * 4) + 127) & ~(size_t)127;
+    p->smem = p->stages * stage + 64 + 256;
+    return true;
+}
+
+static int dw_launch(const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t st)
+{
+    static size_t configured = 0;
+    if (pl.smem > configured) {
+        if (cudaFuncSetAttribute(k_dw3s1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) { ffb_set_error("dw_tma: cannot set smem %zu", pl.smem); return -1; }
+        configured = pl.smem;
+    }
+    CUtensorMap tm;
+    const unsigned long long dims[4] = { (unsigned long long)a.C, (unsigned long long)a.W, (unsigned long long)a.H, (unsigned long long)a.N };
+    const unsigned long long strides[3] = { (unsigned long long)a.C * 4, (unsigned long long)a.W * a.C * 4, (unsigned long long)a.H * a.W * a.C * 4 };
+    const unsigned box[4] = { (unsigned)pl.CB, (unsigned)pl.IWb, (unsigned)pl.IHb, 1u };
+    if (ffb_make_tensor_map(&tm, in, 4, dims, strides, box, 0) != 0) return -1;
+    a.CB = pl.CB; a.TW = pl.TW; a.TH = pl.TH; a.RC = pl.RC; a.nch = pl.nch; a.ntx = pl.ntx; a.nty = pl.nty; a.ntc = pl.ntc;
+    a.ntiles = (long)a.N * pl.nty * pl.ntx * pl.ntc; a.stages = pl.stages;
+    const int grid = (int)std::min<long>(a.ntiles, g_num_sms);
+    k_dw3s1_tma<<<grid, DW_THREADS, pl.smem, st>>>(tm, a);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 template <int TM, int TN>
@@ -186,17 +252,26 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
         else                                 e = pw_launch<1, 4>(a, grid, op->smem, st);
         CK(e);
         return 0; }
-    case CK_DW_S1_3: case CK_DW_S1_5: {
+    case CK_DW_S1_3: case CK_DW_S1_5: case CK_DW3_S2:
+        if (op->dw_mode == 0 && kind == CK_DW_S1_3) {
+            DwPlan pl;
+            if (dw_plan(op->ic, oh, ow, &pl)) {
+                DwArgs a; a.out = out; a.wt = wt; a.scale = sc; a.bias = bi; a.N = n; a.H = ih; a.W = iw; a.C = op->ic; a.act = op->act;
+                return dw_launch(in, a, pl, st);
+            }
+        }
+        if (kind == CK_DW3_S2) {
+            const int R = oh >= 40 ? 10 : oh;
+            dim3 grid((ow * op->ic / 4 + 127) / 128, (oh + R - 1) / R, n);
+            k_dw3_s2<<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, oh, ow, R, op->act);
+            CK(cudaGetLastError());
+            return 0;
+        }
+        {
         const int R = ih >= 64 ? 16 : ih >= 32 ? 10 : ih;
         dim3 grid((iw * op->ic / 4 + 127) / 128, (ih + R - 1) / R, n);
         if (kind == CK_DW_S1_3) k_dw_s1<3><<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, R, op->act, -1);
         else                    k_dw_s1<5><<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, R, op->act, skip);
-        CK(cudaGetLastError());
-        return 0; }
-    case CK_DW3_S2: {
-        const int R = oh >= 40 ? 10 : oh;
-        dim3 grid((ow * op->ic / 4 + 127) / 128, (oh + R - 1) / R, n);
-        k_dw3_s2<<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, oh, ow, R, op->act);
         CK(cudaGetLastError());
         return 0; }
     case CK_STEM: {
@@ -229,7 +304,7 @@ struct ffb_engine {
     Tens input;
     std::vector<Buf> bufs;
     float *d_arena = nullptr; size_t arena_floats = 0;
-    int dw5_exact = 0, pw_mode = 0, use_graph = 1, keep_all = 0;
+    int dw5_exact = 0, pw_mode = 0, dw_mode = 0, use_graph = 1, keep_all = 0;
     bool plan_dirty = true;
     cudaGraphExec_t gexec = nullptr; int graph_batch = -1;
     int launches = 0;
@@ -364,7 +439,7 @@ static int engine_prepare_weights(ffb_engine *e)
             e->convs[i] = op;
         }
         op->ic = l->c; op->groups = l->groups; op->pad = l->pad; op->stride = l->stride; op->fs = l->fs; op->fn = l->fn;
-        op->act = l->activation; op->dw5_exact = e->dw5_exact; op->pw_mode = e->pw_mode;
+        op->act = l->activation; op->dw5_exact = e->dw5_exact; op->pw_mode = e->pw_mode; op->dw_mode = e->dw_mode;
         op->d_packed = e->d_packed + (l->filter - net->weight_buf);
         if (op->tc) { pw_tc_plan_destroy(op->tc); op->tc = NULL; }
         if (conv_prepare(op, e->stream) != 0) return -1;
@@ -400,6 +475,7 @@ int ffb_net_attach(NET *net, int device, int max_batch)
     if ((env = getenv("FFCNN_DW5_EXACT"))) e->dw5_exact = atoi(env);
     if ((env = getenv("FFCNN_PW_MODE")))   e->pw_mode = atoi(env);
     if ((env = getenv("FFCNN_GRAPH")))     e->use_graph = atoi(env);
+    if ((env = getenv("FFCNN_DW_MODE")))   e->dw_mode = atoi(env);
     CK(cudaMalloc(&e->d_packed, std::max(1, net->weight_size) * sizeof(float)));
     CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     if (engine_prepare_weights(e) != 0) return -1;
@@ -450,6 +526,7 @@ int ffb_set_option(NET *net, const char *name, int value)
     bool reweight = false;
     if      (!strcmp(name, "dw5_exact")) { reweight = e->dw5_exact != value; e->dw5_exact = value; }
     else if (!strcmp(name, "pw_mode"))   { reweight = e->pw_mode != value; e->pw_mode = value; }
+    else if (!strcmp(name, "dw_mode"))   { reweight = e->dw_mode != value; e->dw_mode = value; }
     else if (!strcmp(name, "graph"))     { e->use_graph = value; }
     else if (!strcmp(name, "keep_all"))  { if (e->keep_all != value) e->plan_dirty = true; e->keep_all = value; }
     else { ffb_set_error("unknown option '%s'", name); return -1; }
@@ -468,6 +545,7 @@ int ffb_get_option(NET *net, const char *name)
     if (!e || !name) return -1;
     if (!strcmp(name, "dw5_exact")) return e->dw5_exact;
     if (!strcmp(name, "pw_mode")) return e->pw_mode;
+    if (!strcmp(name, "dw_mode")) return e->dw_mode;
     if (!strcmp(name, "graph")) return e->use_graph;
     if (!strcmp(name, "keep_all")) return e->keep_all;
     if (!strcmp(name, "max_batch")) return e->max_batch;
@@ -864,7 +942,7 @@ ffb_conv *ffb_conv_create(const float *packed, int ic, int groups, int pad, int 
     if (ensure_device() != 0) return NULL;
     ffb_conv *op = new ffb_conv(); memset(op, 0, sizeof *op);
     op->ic = ic; op->groups = groups; op->pad = pad; op->stride = stride; op->fs = fs; op->fn = fn; op->act = act;
-    op->dw5_exact = flags & 1; op->pw_mode = (flags >> 8) & 0xff;
+    op->dw5_exact = flags & 1; op->pw_mode = (flags >> 8) & 0xff; op->dw_mode = (flags >> 16) & 0xff;
     const int row = FFB_ALIGN(fs * fs * (ic / groups), 4) + 4;
     const size_t bytes = (size_t)fn * row * sizeof(float);
     if (cudaMalloc(&op->d_owned_packed, bytes) != cudaSuccess || cudaMemcpy(op->d_owned_packed, packed, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -915,7 +993,8 @@ extern "C" void groupconv(float *datai, float *dataf, float *datao, int iw, int 
 {
     (void)gc_buffer; (void)gc_bufsize; (void)oc;
     const char *ex = getenv("FFCNN_DW5_EXACT"), *pm = getenv("FFCNN_PW_MODE");
-    const int flags = (ex && atoi(ex) ? 1 : 0) | ((pm ? atoi(pm) : 0) << 8);
+    const char *dm = getenv("FFCNN_DW_MODE");
+    const int flags = (ex && atoi(ex) ? 1 : 0) | ((pm ? atoi(pm) : 0) << 8) | ((dm ? atoi(dm) : 0) << 16);
     ffb_conv *op = ffb_conv_create(dataf, ic, ig, ipad, istride, fs, fn, activation, flags);
     if (!op) { fprintf(stderr, "ffcnn_b200: groupconv: %s\n", ffb_last_error()); return; }
     const int ldi = FFB_ALIGN(ic, 4), ldo = FFB_ALIGN(fn, 4);

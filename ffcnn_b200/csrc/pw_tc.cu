@@ -284,6 +284,19 @@ int make_map(CUtensorMap *m, const void *base, uint64_t cols, uint64_t rows, uin
 
 } // namespace
 
+int ffb_make_tensor_map(CUtensorMap *m, const void *base, int rank, const unsigned long long *dims,
+                        const unsigned long long *strides_bytes, const unsigned *box, int swizzle128)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { ffb_set_error("cuTensorMapEncodeTiled unavailable"); return -1; }
+    cuuint64_t gdim[5], gstr[4]; cuuint32_t bx[5], estr[5] = { 1, 1, 1, 1, 1 };
+    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; if (i + 1 < rank) gstr[i] = strides_bytes[i]; }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ffb_set_error("cuTensorMapEncodeTiled failed (%d), rank %d, box0 %u", (int)r, rank, box[0]); return -1; }
+    return 0;
+}
+
 struct PwTcPlan {
     int K, N, act, mode, split;
     int Kc, ksteps_total, NS, nsl, S, OB, NP, Kld;

@@ -12,3 +12,9 @@ void        pw_tc_plan_destroy(PwTcPlan *p);
 int         pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStream_t st);
 int         pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int coff, long M, cudaStream_t st);
 const char *pw_tc_mode_name(const PwTcPlan *p);
+
+/* generic tiled tensor map over fp32 data: dims/box innermost first, strides_bytes[i] = byte stride of dimension i+1.
+ * swizzle128 != 0 selects CU_TENSOR_MAP_SWIZZLE_128B.  Out-of-bounds elements read as zero. Returns 0 on success. */
+#include <cuda.h>
+int ffb_make_tensor_map(CUtensorMap *m, const void *base, int rank, const unsigned long long *dims,
+                        const unsigned long long *strides_bytes, const unsigned *box, int swizzle128);

@@ -44,7 +44,8 @@ int   ffb_commit_weights(NET *net);
 /* Options (name, value): "dw5_exact" 0 = reproduce conv-v6's dropped kernel row on output row
  * oh-2 of the 5x5 depthwise path (conv-v6.c:422-441; default, the named oracle), 1 = exact math
  * (conv-v0); "pw_mode" 0 = auto, 1 = fp32 FFMA everywhere, 2 = tcgen05 3xTF32 where eligible,
- * 3 = tcgen05 1xTF32; "graph" 1 = replay a captured CUDA graph (default), 0 = plain launches;
+ * 3 = tcgen05 1xTF32; "dw_mode" 0 = TMA-fed shared-memory stencil for the depthwise layers (default), 1 = the
+ * register-window kernel fed by plain loads; "graph" 1 = replay a captured CUDA graph (default), 0 = plain launches;
  * "keep_all" 1 = every layer output gets its own buffer (needed by ffb_layer_output). */
 int  ffb_set_option(NET *net, const char *name, int value);
 int  ffb_get_option(NET *net, const char *name);
@@ -108,7 +109,7 @@ int  ffb_launches_per_forward(NET *net);                 /* kernels enqueued by 
 typedef struct ffb_conv ffb_conv;
 /* Same contract as groupconv (conv.h:4-7) but batched NHWC on device, weights uploaded once.
  * packed_filter: host, fn rows of ALIGN(fs*fs*ic/groups,4)+4 floats.  flags: bit0 = dw5_exact,
- * bits 8..15 = pw_mode. */
+ * bits 8..15 = pw_mode, bits 16..23 = dw_mode. */
 ffb_conv *ffb_conv_create(const float *packed_filter, int ic, int groups, int pad, int stride,
                           int fs, int fn, int activation, int flags);
 void      ffb_conv_destroy(ffb_conv *op);
