@@ -177,7 +177,7 @@ def main():
     for i in range(W):
         step_resident(i)
     net.detect_finish()
-    launches_per_step = 1 + net.launches_per_forward() + 2
+    launches_per_step = (0 if net.get_option("input_fused") == 1 else 1) + net.launches_per_forward() + 2
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

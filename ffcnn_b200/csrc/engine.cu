@@ -66,6 +66,8 @@ struct ffb_conv {
     /* pointwise FFMA tiling */
     int TM, TN, NT, TY; size_t smem;
     PwTcPlan *tc;               /* tcgen05 plan (pw_tc.cu), NULL if not used */
+    const float *h_packed;      /* host copy of the packed rows, only dereferenced during conv_prepare */
+    StemW stemw;                /* stem weights as a kernel-parameter block (constant-bank FFMA operands) */
     char name[48];
 };
 
@@ -171,17 +173,23 @@ static int dw_launch(const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t 
     return 0;
 }
 
-template <int TM, int TN>
-static cudaError_t pw_launch(const PwArgs &a, int grid, size_t smem, cudaStream_t st)
+template <int TM, int TN, bool RES>
+static cudaError_t pw_launch2(const PwArgs &a, int grid, size_t smem, cudaStream_t st)
 {
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_pw_ffma<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_pw_ffma<TM, TN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_pw_ffma<TM, TN><<<grid, 256, smem, st>>>(a);
+    k_pw_ffma<TM, TN, RES><<<grid, 256, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int TM, int TN>
+static cudaError_t pw_launch(const PwArgs &a, int grid, size_t smem, cudaStream_t st)
+{
+    return a.res ? pw_launch2<TM, TN, true>(a, grid, smem, st) : pw_launch2<TM, TN, false>(a, grid, smem, st);
 }
 
 static int conv_prepare(ffb_conv *op, cudaStream_t st)
@@ -201,6 +209,14 @@ static int conv_prepare(ffb_conv *op, cudaStream_t st)
     const char *names[] = { "conv_generic", "pw_ffma", "pw_tcgen05", "dw3x3_s1", "dw5x5_s1", "dw3x3_s2", "stem3x3_s2" };
     snprintf(op->name, sizeof op->name, "%s", names[op->kind]);
     if (op->kind == CK_PW_TC) snprintf(op->name, sizeof op->name, "pw_tcgen05_%s", pw_tc_mode_name(op->tc));
+    if (op->kind == CK_STEM) {
+        if (!op->h_packed) { ffb_set_error("stem conv needs the host copy of its weights"); return -1; }
+        for (int o = 0; o < 8; o++) {
+            const float *r = op->h_packed + (size_t)o * op->row;
+            for (int t = 0; t < 27; t++) op->stemw.w[t * 8 + o] = r[t];
+            op->stemw.s[o] = r[op->row - 4]; op->stemw.b[o] = r[op->row - 3];
+        }
+    }
     if (op->kind == CK_GENERIC) return 0;
     const size_t nfl = (size_t)op->taps * op->fn_pad + 2 * op->fn_pad;
     if (!op->d_prep) CK(cudaMalloc(&op->d_prep, nfl * sizeof(float)));
@@ -222,7 +238,7 @@ static void conv_release(ffb_conv *op)
 
 /* in: [n][ih][iw][ldi], out: [n][oh][ow][ldo] written at channel offset coff */
 static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo, int coff,
-                    int n, int ih, int iw, cudaStream_t st)
+                    int n, int ih, int iw, cudaStream_t st, const float *res = nullptr, int ldr = 0, int act2 = 0)
 {
     const int oh = conv_out_dim(ih, op->fs, op->pad, op->stride), ow = conv_out_dim(iw, op->fs, op->pad, op->stride);
     const float *wt = op->d_prep, *sc = wt ? wt + (size_t)op->taps * op->fn_pad : NULL, *bi = sc ? sc + op->fn_pad : NULL;
@@ -232,24 +248,29 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
     ConvKind kind = op->kind;
     if ((kind == CK_DW_S1_3 || kind == CK_DW_S1_5 || kind == CK_DW3_S2) && (ldi != op->ic || ldo != op->fn || coff != 0)) kind = CK_GENERIC;
     if (kind == CK_STEM && (ldi != 4 || ldo != 8 || coff != 0)) kind = CK_GENERIC;
+    if (res && kind != CK_PW_TC && kind != CK_PW_FFMA) { ffb_set_error("fused shortcut needs a pointwise conv"); return -1; }
     switch (kind) {
     case CK_PW_TC:
-        return pw_tc_run(op->tc, in, ldi, out, ldo, coff, (long)n * ih * iw, st);
+        return pw_tc_run(op->tc, in, ldi, out, ldo, coff, (long)n * ih * iw, st, res, ldr, act2);
     case CK_PW_FFMA: {
         PwArgs a; a.in = in; a.out = out; a.wt = wt; a.scale = sc; a.bias = bi; a.M = (long)n * ih * iw; a.K = op->ic; a.N = op->fn;
         a.ldi = ldi; a.ldo = ldo; a.coff = coff; a.BN = op->fn_pad; a.NT = op->NT; a.TY = op->TY; a.act = op->act;
-        const long tiles = (a.M + (long)op->TM * op->TY - 1) / ((long)op->TM * op->TY);
-        const int per_sm = op->smem <= 100 * 1024 ? 2 : 1;
+        a.res = res; a.ldr = ldr; a.act2 = act2;
+        /* the fused-shortcut variant keeps TM*TN/4 skip vectors live: cap TM at 4 so two CTAs still fit the register file */
+        const int TM = (res && op->TM > 4) ? 4 : op->TM;
+        const size_t smem = pw_smem(op->ic, op->fn_pad, TM, op->TY);
+        const long tiles = (a.M + (long)TM * op->TY - 1) / ((long)TM * op->TY);
+        const int per_sm = smem <= 100 * 1024 ? 2 : 1;
         const int grid = (int)std::max<long>(1, std::min<long>(tiles, (long)g_num_sms * per_sm));
         cudaError_t e = cudaSuccess;
-        if      (op->TM == 8 && op->TN == 8) e = pw_launch<8, 8>(a, grid, op->smem, st);
-        else if (op->TM == 4 && op->TN == 8) e = pw_launch<4, 8>(a, grid, op->smem, st);
-        else if (op->TM == 2 && op->TN == 8) e = pw_launch<2, 8>(a, grid, op->smem, st);
-        else if (op->TM == 1 && op->TN == 8) e = pw_launch<1, 8>(a, grid, op->smem, st);
-        else if (op->TM == 8 && op->TN == 4) e = pw_launch<8, 4>(a, grid, op->smem, st);
-        else if (op->TM == 4 && op->TN == 4) e = pw_launch<4, 4>(a, grid, op->smem, st);
-        else if (op->TM == 2 && op->TN == 4) e = pw_launch<2, 4>(a, grid, op->smem, st);
-        else                                 e = pw_launch<1, 4>(a, grid, op->smem, st);
+        if      (TM == 8 && op->TN == 8) e = pw_launch<8, 8>(a, grid, smem, st);
+        else if (TM == 4 && op->TN == 8) e = pw_launch<4, 8>(a, grid, smem, st);
+        else if (TM == 2 && op->TN == 8) e = pw_launch<2, 8>(a, grid, smem, st);
+        else if (TM == 1 && op->TN == 8) e = pw_launch<1, 8>(a, grid, smem, st);
+        else if (TM == 8 && op->TN == 4) e = pw_launch<8, 4>(a, grid, smem, st);
+        else if (TM == 4 && op->TN == 4) e = pw_launch<4, 4>(a, grid, smem, st);
+        else if (TM == 2 && op->TN == 4) e = pw_launch<2, 4>(a, grid, smem, st);
+        else                             e = pw_launch<1, 4>(a, grid, smem, st);
         CK(e);
         return 0; }
     case CK_DW_S1_3: case CK_DW_S1_5: case CK_DW3_S2:
@@ -276,7 +297,7 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
         return 0; }
     case CK_STEM: {
         dim3 grid((ow + 31) / 32, (oh + 7) / 8, n), block(32, 8);
-        k_stem3x3s2<32, 8><<<grid, block, 0, st>>>(in, out, wt, sc, bi, ih, iw, oh, ow, op->act);
+        k_stem_f32<32, 8><<<grid, block, 0, st>>>(in, out, op->stemw, ih, iw, oh, ow, op->act);
         CK(cudaGetLastError());
         return 0; }
     default: {
@@ -286,6 +307,17 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
         CK(cudaGetLastError());
         return 0; }
     }
+}
+
+/* net_input fused into the stem: BGR u8 frames (frame size == net size) -> layer-0 output */
+static int stem_run_u8(ffb_conv *op, const unsigned char *frames, int pitch, float *out, int n, int ih, int iw,
+                       const float *mean, const float *norm, cudaStream_t st)
+{
+    const int oh = conv_out_dim(ih, 3, 1, 2), ow = conv_out_dim(iw, 3, 1, 2);
+    dim3 grid((ow + 31) / 32, (oh + 7) / 8, n), block(32, 8);
+    k_stem_u8<32, 8><<<grid, block, 0, st>>>(frames, pitch, out, op->stemw, ih, iw, oh, ow, op->act, mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 /* =================================================================================== engine */
@@ -301,10 +333,15 @@ struct ffb_engine {
     float *d_packed = nullptr;
     std::vector<ffb_conv *> convs;          /* per layer, NULL for non-conv */
     std::vector<Tens> outs;                 /* per layer output (aliases share buf) */
+    std::vector<int> fuse_sc;               /* conv layer i also performs shortcut layer fuse_sc[i] (-1: none) */
+    std::vector<char> fused_away;           /* shortcut layer j is computed inside its producer conv */
+    int fuse_shortcut = 1;
     Tens input;
     std::vector<Buf> bufs;
     float *d_arena = nullptr; size_t arena_floats = 0;
-    int dw5_exact = 0, pw_mode = 0, dw_mode = 0, use_graph = 1, keep_all = 0;
+    int dw5_exact = 0, pw_mode = 0, dw_mode = 0, use_graph = 1, keep_all = 0, fuse_input = 1;
+    /* u8 frames of the current batch when net_input is fused into the stem (frame size == net size) */
+    const unsigned char *u8_src = nullptr; int u8_pitch = 0; bool input_fused = false; float in_mean[3] = {0, 0, 0}, in_norm[3] = {0, 0, 0};
     bool plan_dirty = true;
     cudaGraphExec_t gexec = nullptr; int graph_batch = -1;
     int launches = 0;
@@ -372,10 +409,42 @@ static int engine_plan(ffb_engine *e)
     e->input.buf = new_buf(e->input.frame_floats(), -1);
     auto in_of = [&](int i) -> Tens & { return i == 0 ? e->input : e->outs[i - 1]; };
     auto touch = [&](const Tens &t, int at) { if (t.buf >= 0) bufs[t.buf].last = std::max(bufs[t.buf].last, at); };
+    /* shortcut fusion (the cheap half): a pointwise conv whose only reader -- through dropout aliases -- is a
+       shortcut layer adds the skip tensor in its own epilogue and writes the shortcut's output; the conv's own output and
+       the separate add kernel disappear (2 of the 4 tensor passes).  Off under keep_all (every layer output must exist). */
+    e->fuse_sc.assign(L, -1); e->fused_away.assign(L, 0);
+    if (e->fuse_shortcut && !e->keep_all) {
+        std::vector<int> readers(L, 0);                         /* how many non-alias layers read layer k's output */
+        auto producer_of = [&](int k) { while (k >= 0 && (net->layer_list[k].type == LAYER_TYPE_DROPOUT ||
+                                                       (net->layer_list[k].type == LAYER_TYPE_ROUTE && net->layer_list[k].depend_num == 1)))
+                                            k = net->layer_list[k].type == LAYER_TYPE_DROPOUT ? k - 1 : net->layer_list[k].depend_list[0];
+                                        return k; };
+        for (int k = 0; k < L; k++) {
+            const LAYER *l = net->layer_list + k;
+            if (l->type == LAYER_TYPE_DROPOUT || (l->type == LAYER_TYPE_ROUTE && l->depend_num == 1)) continue;
+            if (l->type != LAYER_TYPE_ROUTE && k > 0) { const int p = producer_of(k - 1); if (p >= 0) readers[p]++; }
+            for (int d = 0; d < l->depend_num; d++) { const int p = producer_of(l->depend_list[d]); if (p >= 0) readers[p]++; }
+        }
+        for (int j = 1; j < L; j++) {
+            const LAYER *sl = net->layer_list + j;
+            if (sl->type != LAYER_TYPE_SHORTCUT) continue;
+            const int p = producer_of(j - 1), d = sl->depend_list[0];
+            if (p < 0 || producer_of(d) == p) continue;
+            const ffb_conv *op = net->layer_list[p].type == LAYER_TYPE_CONV ? e->convs[p] : nullptr;
+            if (!op || (op->kind != CK_PW_FFMA && op->kind != CK_PW_TC) || readers[p] != 1 || net->layer_list[p + 1].c % 4) continue;
+            e->fuse_sc[p] = j; e->fused_away[j] = 1;
+        }
+    }
     for (int i = 0; i < L; i++) {
         const LAYER *il = net->layer_list + i, *ol = il + 1;
         Tens &o = e->outs[i];
         o.h = ol->h; o.w = ol->w; o.c = ol->c; o.ld = FFB_ALIGN(ol->c, 4);
+        if (il->type == LAYER_TYPE_CONV && e->fuse_sc[i] >= 0) {
+            /* the conv writes the shortcut's tensor: one buffer, created now, named by both layers */
+            o.buf = new_buf(o.frame_floats(), i); touch(in_of(i), i); touch(e->outs[net->layer_list[e->fuse_sc[i]].depend_list[0]], i); touch(o, i);
+            continue;
+        }
+        if (il->type == LAYER_TYPE_SHORTCUT && e->fused_away[i]) { o = in_of(i); touch(o, i); continue; }
         switch (il->type) {
         case LAYER_TYPE_DROPOUT: o = in_of(i); break;                               /* alias */
         case LAYER_TYPE_ROUTE:
@@ -441,6 +510,7 @@ static int engine_prepare_weights(ffb_engine *e)
         op->ic = l->c; op->groups = l->groups; op->pad = l->pad; op->stride = l->stride; op->fs = l->fs; op->fn = l->fn;
         op->act = l->activation; op->dw5_exact = e->dw5_exact; op->pw_mode = e->pw_mode; op->dw_mode = e->dw_mode;
         op->d_packed = e->d_packed + (l->filter - net->weight_buf);
+        op->h_packed = l->filter;
         if (op->tc) { pw_tc_plan_destroy(op->tc); op->tc = NULL; }
         if (conv_prepare(op, e->stream) != 0) return -1;
     }
@@ -513,6 +583,7 @@ int ffb_commit_weights(NET *net)
     CK(cudaSetDevice(e->device));
     /* keep the host copy coherent with what was broadcast into the device buffer */
     CK(cudaMemcpyAsync(net->weight_buf, e->d_packed, (size_t)net->weight_size * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     if (engine_prepare_weights(e) != 0) return -1;
     CK(cudaStreamSynchronize(e->stream));
     if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; e->graph_batch = -1; }
@@ -528,6 +599,8 @@ int ffb_set_option(NET *net, const char *name, int value)
     else if (!strcmp(name, "pw_mode"))   { reweight = e->pw_mode != value; e->pw_mode = value; }
     else if (!strcmp(name, "dw_mode"))   { reweight = e->dw_mode != value; e->dw_mode = value; }
     else if (!strcmp(name, "graph"))     { e->use_graph = value; }
+    else if (!strcmp(name, "fuse_input")) { e->fuse_input = value; }
+    else if (!strcmp(name, "fuse_shortcut")) { if (e->fuse_shortcut != value) e->plan_dirty = true; e->fuse_shortcut = value; }
     else if (!strcmp(name, "keep_all"))  { if (e->keep_all != value) e->plan_dirty = true; e->keep_all = value; }
     else { ffb_set_error("unknown option '%s'", name); return -1; }
     if (reweight) {
@@ -547,6 +620,9 @@ int ffb_get_option(NET *net, const char *name)
     if (!strcmp(name, "pw_mode")) return e->pw_mode;
     if (!strcmp(name, "dw_mode")) return e->dw_mode;
     if (!strcmp(name, "graph")) return e->use_graph;
+    if (!strcmp(name, "fuse_input")) return e->fuse_input;
+    if (!strcmp(name, "input_fused")) return e->input_fused ? 1 : 0;
+    if (!strcmp(name, "fuse_shortcut")) return e->fuse_shortcut;
     if (!strcmp(name, "keep_all")) return e->keep_all;
     if (!strcmp(name, "max_batch")) return e->max_batch;
     if (!strcmp(name, "batch")) return e->batch;
@@ -610,6 +686,12 @@ int ffb_input_u8(NET *net, const unsigned char *frames, int n, int w, int h, int
     ffb_fit_geometry(w, h, e->input.w, e->input.h, &sw, &sh, &s1, &s2);
     e->s1 = s1; e->s2 = s2; e->batch = n;
     net->s1 = s1; net->s2 = s2;
+    for (int i = 0; i < 3; i++) { e->in_mean[i] = mean[i]; e->in_norm[i] = norm[i]; }
+    /* no resize (frame == net size): the stem reads the u8 frames itself and the fp32 input tensor is never materialised */
+    e->input_fused = e->fuse_input && !e->keep_all && w == e->input.w && h == e->input.h && net->layer_num > 0 &&
+                     net->layer_list[0].type == LAYER_TYPE_CONV && e->convs[0] && e->convs[0]->kind == CK_STEM && e->outs[0].ld == 8;
+    e->u8_src = src; e->u8_pitch = pitch;
+    if (e->input_fused) return 0;
     const long total = (long)n * e->input.h * e->input.w;
     k_input_u8<<<grid_for(total, 256, 16), 256, 0, e->stream>>>(src, e->input.p, n, w, h, pitch, e->input.w, e->input.h, sw, sh, s1, s2,
                                                                 mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]);
@@ -634,6 +716,7 @@ int ffb_input_chw(NET *net, const float *chw, int n, int s1, int s2)
                 e->h_stage[((size_t)f * plane + p) * t.ld + c] = c < t.c ? chw[((size_t)f * t.c + c) * plane + p] : 0.f;
     CK(cudaMemcpyAsync(t.p, e->h_stage, fl * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     e->batch = n; e->s1 = s1; e->s2 = s2; net->s1 = s1; net->s2 = s2;
+    e->input_fused = false;
     return 0;
 }
 
@@ -645,7 +728,12 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
     const int n = e->batch;
     switch (il->type) {
     case LAYER_TYPE_CONV:
-        if (conv_run(e->convs[i], in.p, in.ld, o.p, o.ld, 0, n, in.h, in.w, st) != 0) return -1;
+        if (i == 0 && e->input_fused) {
+            if (stem_run_u8(e->convs[0], e->u8_src, e->u8_pitch, o.p, n, in.h, in.w, e->in_mean, e->in_norm, st) != 0) return -1;
+        } else if (e->fuse_sc[i] >= 0) {
+            const LAYER *sl = net->layer_list + e->fuse_sc[i]; const Tens &r = e->outs[sl->depend_list[0]];
+            if (conv_run(e->convs[i], in.p, in.ld, o.p, o.ld, 0, n, in.h, in.w, st, r.p, r.ld, sl->activation) != 0) return -1;
+        } else if (conv_run(e->convs[i], in.p, in.ld, o.p, o.ld, 0, n, in.h, in.w, st) != 0) return -1;
         (*launches)++;
         break;
     case LAYER_TYPE_MAXPOOL: case LAYER_TYPE_AVGPOOL:
@@ -660,6 +748,7 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         (*launches)++;
         break;
     case LAYER_TYPE_SHORTCUT: {
+        if (e->fused_away[i]) break;                           /* done in the producer conv's epilogue */
         const Tens &s = e->outs[il->depend_list[0]];
         if (s.h != in.h || s.w != in.w || s.c != in.c) { ffb_set_error("shortcut layer %d: shape mismatch", i); return -1; }
         const long n4 = (long)n * o.frame_floats() / 4;       /* ld is a multiple of 4 and identical for all three */
@@ -685,10 +774,10 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
     return 0;
 }
 
-static int run_all(ffb_engine *e, cudaStream_t st)
+static int run_all(ffb_engine *e, cudaStream_t st, int first = 0)
 {
-    int launches = 0;
-    for (int i = 0; i < e->net->pub.layer_num; i++) if (run_layer(e, i, st, &launches) != 0) return -1;
+    int launches = first;
+    for (int i = first; i < e->net->pub.layer_num; i++) if (run_layer(e, i, st, &launches) != 0) return -1;
     e->launches = launches;
     return 0;
 }
@@ -700,21 +789,26 @@ int ffb_forward(NET *net)
     if (e->batch < 1 || !e->d_arena || e->plan_dirty) { ffb_set_error("ffb_forward: no input set for the current plan"); return -1; }
     CK(cudaSetDevice(e->device));
     if (!e->use_graph) return run_all(e, e->stream);
-    if (!e->gexec || e->graph_batch != e->batch) {
+    /* with net_input fused into the stem, layer 0 reads the caller's frame pointer, which changes from batch to batch:
+       it is launched eagerly and the graph covers layers 1.. */
+    const int first = e->input_fused ? 1 : 0;
+    const int gkey = e->batch * 2 + first;
+    if (!e->gexec || e->graph_batch != gkey) {
         if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
         /* one eager pass first: lazily-set function attributes must not happen inside capture */
         if (run_all(e, e->stream) != 0) return -1;
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = run_all(e, e->stream);
+        int rc = run_all(e, e->stream, first);
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         if (rc != 0 || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); if (ce != cudaSuccess) ffb_set_error("graph capture failed: %s", cudaGetErrorString(ce)); return -1; }
         ce = cudaGraphInstantiate(&e->gexec, g, 0);
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) { ffb_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); e->gexec = nullptr; return -1; }
-        e->graph_batch = e->batch;
+        e->graph_batch = gkey;
         return 0;                                               /* the eager pass above already produced this batch's outputs */
     }
+    if (first) { int l = 0; if (run_layer(e, 0, e->stream, &l) != 0) return -1; }
     CK(cudaGraphLaunch(e->gexec, e->stream));
     return 0;
 }
@@ -908,18 +1002,27 @@ int ffb_layer_times(NET *net, float *ms, int nlayers, int reps, int flush_l2)
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     const int L = std::min(nlayers, net->layer_num);
     for (int i = 0; i < L; i++) {
-        float total = 0; int launches = 0;
-        for (int r = 0; r < reps + 1; r++) {                    /* first rep is an untimed warm-up */
-            if (flush_l2) k_fill<<<g_num_sms * 8, 256, 0, e->stream>>>(e->d_flush, (long)e->flush_floats, 0.f);
+        int launches = 0;
+        if (run_layer(e, i, e->stream, &launches) != 0) return -1;          /* untimed warm-up */
+        if (!launches) { ms[i] = 0.f; continue; }
+        float total = 0;
+        if (flush_l2) {                                                       /* cold: one launch per event pair, L2 evicted before each */
+            for (int r = 0; r < reps; r++) {
+                k_fill<<<g_num_sms * 8, 256, 0, e->stream>>>(e->d_flush, (long)e->flush_floats, 0.f);
+                CK(cudaEventRecord(a, e->stream));
+                if (run_layer(e, i, e->stream, &launches) != 0) return -1;
+                CK(cudaEventRecord(b, e->stream));
+                CK(cudaEventSynchronize(b));
+                float t = 0; CK(cudaEventElapsedTime(&t, a, b)); total += t;
+            }
+        } else {                                                              /* back to back: launch latency hidden, as inside the graph */
             CK(cudaEventRecord(a, e->stream));
-            launches = 0;
-            if (run_layer(e, i, e->stream, &launches) != 0) return -1;
+            for (int r = 0; r < reps; r++) if (run_layer(e, i, e->stream, &launches) != 0) return -1;
             CK(cudaEventRecord(b, e->stream));
             CK(cudaEventSynchronize(b));
-            float t = 0; CK(cudaEventElapsedTime(&t, a, b));
-            if (r > 0) total += t;
+            CK(cudaEventElapsedTime(&total, a, b));
         }
-        ms[i] = launches ? total / reps : 0.f;
+        ms[i] = total / reps;
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     return 0;
@@ -949,6 +1052,7 @@ ffb_conv *ffb_conv_create(const float *packed, int ic, int groups, int pad, int 
         ffb_set_error("ffb_conv_create: device allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError())); conv_release(op); return NULL;
     }
     op->d_packed = op->d_owned_packed;
+    op->h_packed = packed;
     if (conv_prepare(op, 0) != 0 || cudaDeviceSynchronize() != cudaSuccess) { conv_release(op); return NULL; }
     return op;
 }

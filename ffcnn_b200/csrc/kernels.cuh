@@ -66,56 +66,108 @@ __global__ void k_input_u8(const uint8_t *__restrict__ frames, float *__restrict
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Stem: dense 3x3 stride-2 pad-1 conv, CI (3, stored at ld 4) -> CO=8 -- the only layer that takes the
- * reference's generic im2row path (conv-v6.c:9-42).  Each CTA stages the (2*TY+1) x (2*TX+1) input
- * halo tile in shared memory with coalesced float4 loads, then every thread produces one output
- * pixel x 8 channels (two float4 stores).  Weights [27][8] + scale/bias sit in shared memory and are
- * read as broadcasts.  Accumulation order channel -> ky -> kx as conv-v0.c:16-25.
+ * Stem: dense 3x3 stride-2 pad-1 conv, 3 -> 8 channels -- the only layer that takes the reference's generic im2row
+ * path (conv-v6.c:9-42).  Each CTA stages the (2*TY+1) x (2*TX+1) input halo tile in shared memory as float4
+ * (R,G,B,0), then every thread produces one output pixel x 8 channels (two float4 stores).
+ * The 216 weights + scale/bias travel as a __grid_constant__ kernel parameter: every lane uses the same weight at the
+ * same time, so each FFMA takes it straight from the constant bank -- no shared-memory or register traffic for weights
+ * (the first version read them with broadcast LDS and was shared-memory bound at 30 % of the HBM roofline).
+ * Accumulation order channel -> ky -> kx as conv-v0.c:16-25.
+ *   k_stem_f32: input is the fp32 NHWC tensor (ld 4) written by k_input_u8 / ffb_input_chw.
+ *   k_stem_u8 : net_input fused in -- reads the BGR u8 frames directly (no resize: frame size == net size) and applies
+ *               (px - mean) * norm while staging, the same float arithmetic as ffcnn.c:281-283, 4x fewer input bytes.
  * ---------------------------------------------------------------------------------------------- */
+struct StemW { float w[27 * 8]; float s[8]; float b[8]; };      /* w[(c*3+ky)*3+kx][oc] */
+
 template <int TX, int TY>
-__global__ void __launch_bounds__(TX * TY)
-k_stem3x3s2(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wt /* [27][8] */,
-            const float *__restrict__ scale, const float *__restrict__ bias,
-            int H, int W, int OH, int OW, int act)
+__device__ __forceinline__ void stem_compute(const float4 (*tile)[2 * TX + 1], const StemW &sw, float *__restrict__ out,
+                                             long f, int OH, int OW, int ox, int oy, int act)
 {
-    constexpr int IW = 2 * TX + 1, IH = 2 * TY + 1;
-    __shared__ float4 tile[IH][IW];
-    __shared__ float  sw[27 * 8 + 16];
-    const int tid = threadIdx.y * TX + threadIdx.x;
-    const int ox0 = blockIdx.x * TX, oy0 = blockIdx.y * TY;
-    const long f = blockIdx.z;
-    const float *img = in + f * (long)H * W * 4;
-    for (int i = tid; i < 27 * 8 + 16; i += TX * TY) sw[i] = i < 216 ? wt[i] : i < 224 ? scale[i - 216] : bias[i - 224];
-    const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
-    for (int i = tid; i < IW * IH; i += TX * TY) {
-        const int tx = i % IW, ty = i / IW, ix = ix0 + tx, iy = iy0 + ty;
-        tile[ty][tx] = (ix >= 0 && ix < W && iy >= 0 && iy < H) ? ldg4(img + ((long)iy * W + ix) * 4) : zero4();
-    }
-    __syncthreads();
-    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
     if (ox >= OW || oy >= OH) return;
     float acc[8];
 #pragma unroll
     for (int o = 0; o < 8; o++) acc[o] = 0.f;
+    float4 p[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[j][k] = tile[2 * threadIdx.y + j][2 * threadIdx.x + k];
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
         for (int j = 0; j < 3; j++)
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const float4 p = tile[2 * threadIdx.y + j][2 * threadIdx.x + k];
-                const float v = c == 0 ? p.x : c == 1 ? p.y : p.z;
-                const float *w8 = sw + ((c * 3 + j) * 3 + k) * 8;
+                const float v = c == 0 ? p[j][k].x : c == 1 ? p[j][k].y : p[j][k].z;
 #pragma unroll
-                for (int o = 0; o < 8; o++) acc[o] = fmaf(v, w8[o], acc[o]);
+                for (int o = 0; o < 8; o++) acc[o] = fmaf(v, sw.w[((c * 3 + j) * 3 + k) * 8 + o], acc[o]);
             }
     float4 r0, r1;
-    r0.x = act_apply(fmaf(acc[0], sw[216], sw[224]), act); r0.y = act_apply(fmaf(acc[1], sw[217], sw[225]), act);
-    r0.z = act_apply(fmaf(acc[2], sw[218], sw[226]), act); r0.w = act_apply(fmaf(acc[3], sw[219], sw[227]), act);
-    r1.x = act_apply(fmaf(acc[4], sw[220], sw[228]), act); r1.y = act_apply(fmaf(acc[5], sw[221], sw[229]), act);
-    r1.z = act_apply(fmaf(acc[6], sw[222], sw[230]), act); r1.w = act_apply(fmaf(acc[7], sw[223], sw[231]), act);
+    r0.x = act_apply(fmaf(acc[0], sw.s[0], sw.b[0]), act); r0.y = act_apply(fmaf(acc[1], sw.s[1], sw.b[1]), act);
+    r0.z = act_apply(fmaf(acc[2], sw.s[2], sw.b[2]), act); r0.w = act_apply(fmaf(acc[3], sw.s[3], sw.b[3]), act);
+    r1.x = act_apply(fmaf(acc[4], sw.s[4], sw.b[4]), act); r1.y = act_apply(fmaf(acc[5], sw.s[5], sw.b[5]), act);
+    r1.z = act_apply(fmaf(acc[6], sw.s[6], sw.b[6]), act); r1.w = act_apply(fmaf(acc[7], sw.s[7], sw.b[7]), act);
     float4 *o = reinterpret_cast<float4 *>(out + (f * (long)OH * OW + (long)oy * OW + ox) * 8);
     o[0] = r0; o[1] = r1;
+}
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY)
+k_stem_f32(const float *__restrict__ in, float *__restrict__ out, const __grid_constant__ StemW sw,
+           int H, int W, int OH, int OW, int act)
+{
+    constexpr int IW = 2 * TX + 1, IH = 2 * TY + 1;
+    __shared__ float4 tile[IH][IW];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int ox0 = blockIdx.x * TX, oy0 = blockIdx.y * TY;
+    const long f = blockIdx.z;
+    const float *img = in + f * (long)H * W * 4;
+    const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+    for (int i = tid; i < IW * IH; i += TX * TY) {
+        const int tx = i % IW, ty = i / IW, ix = ix0 + tx, iy = iy0 + ty;
+        tile[ty][tx] = (ix >= 0 && ix < W && iy >= 0 && iy < H) ? ldg4(img + ((long)iy * W + ix) * 4) : zero4();
+    }
+    __syncthreads();
+    stem_compute<TX, TY>(tile, sw, out, f, OH, OW, ox0 + threadIdx.x, oy0 + threadIdx.y, act);
+}
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY)
+k_stem_u8(const uint8_t *__restrict__ frames, int pitch, float *__restrict__ out, const __grid_constant__ StemW sw,
+          int H, int W, int OH, int OW, int act, float m0, float m1, float m2, float n0, float n1, float n2)
+{
+    constexpr int IW = 2 * TX + 1, IH = 2 * TY + 1;
+    __shared__ float4 tile[IH][IW];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int ox0 = blockIdx.x * TX, oy0 = blockIdx.y * TY;
+    const long f = blockIdx.z;
+    const uint8_t *img = frames + f * (long)H * pitch;
+    const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+    /* all byte loads of this thread are issued before the first is consumed: one DRAM latency per CTA, not one per pixel */
+    constexpr int NIT = (IW * IH + TX * TY - 1) / (TX * TY);
+    unsigned char bgr[NIT][3]; bool ok[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int i = tid + it * TX * TY, tx = i % IW, ty = i / IW, ix = ix0 + tx, iy = iy0 + ty;
+        ok[it] = i < IW * IH && ix >= 0 && ix < W && iy >= 0 && iy < H;
+        const uint8_t *px = img + (long)(ok[it] ? iy : 0) * pitch + (ok[it] ? ix : 0) * 3;
+        bgr[it][0] = __ldg(px); bgr[it][1] = __ldg(px + 1); bgr[it][2] = __ldg(px + 2);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int i = tid + it * TX * TY;
+        if (i < IW * IH) {
+            float4 v = zero4();
+            if (ok[it]) {
+                v.x = ((float)bgr[it][2] - m0) * n0;         /* R */
+                v.y = ((float)bgr[it][1] - m1) * n1;         /* G */
+                v.z = ((float)bgr[it][0] - m2) * n2;         /* B */
+            }
+            tile[i / IW][i % IW] = v;
+        }
+    }
+    __syncthreads();
+    stem_compute<TX, TY>(tile, sw, out, f, OH, OW, ox0 + threadIdx.x, oy0 + threadIdx.y, act);
 }
 
 /* ------------------------------------------------------------------------------------------------

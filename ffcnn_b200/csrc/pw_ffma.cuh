@@ -30,9 +30,10 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 struct PwArgs {
     const float *in; float *out; const float *wt, *scale, *bias;
     long M; int K, N, ldi, ldo, coff, BN, NT, TY, act;
+    const float *res; int ldr, act2;          /* optional fused shortcut (ffcnn.c:418-423): out = act2(conv + res) */
 };
 
-template <int TM, int TN>
+template <int TM, int TN, bool RES>
 __global__ void __launch_bounds__(256) k_pw_ffma(const PwArgs a)
 {
     extern __shared__ __align__(16) float smem[];
@@ -74,6 +75,18 @@ __global__ void __launch_bounds__(256) k_pw_ffma(const PwArgs a)
             for (int i = 0; i < TM; i++)
 #pragma unroll
                 for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+            /* fused shortcut: the skip-tensor loads are issued here so their latency hides behind the FMA loop */
+            const long m0 = tile * BM;
+            float4 rv[RES ? TM : 1][TN / 4];
+            if (RES) {
+#pragma unroll
+                for (int h = 0; h < TN / 4; h++)
+#pragma unroll
+                    for (int i = 0; i < TM; i++) {
+                        const long m = m0 + ty + i * TY; const int n0 = tx * 4 + h * NT * 4;
+                        rv[RES ? i : 0][h] = (m < a.M && n0 < a.N) ? ldg4(a.res + m * a.ldr + n0) : zero4();
+                    }
+            }
             for (int k4 = 0; k4 < kc; k4++) {
                 float4 av[TM];
 #pragma unroll
@@ -95,7 +108,6 @@ __global__ void __launch_bounds__(256) k_pw_ffma(const PwArgs a)
                     }
                 }
             }
-            const long m0 = tile * BM;
 #pragma unroll
             for (int h = 0; h < TN / 4; h++) {
                 const int n0 = tx * 4 + h * NT * 4;
@@ -105,8 +117,13 @@ __global__ void __launch_bounds__(256) k_pw_ffma(const PwArgs a)
                     for (int i = 0; i < TM; i++) {
                         const long m = m0 + ty + i * TY;
                         if (m < a.M) {
-                            const float4 v = make_float4(acc[i][h * 4], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
-                            *reinterpret_cast<float4 *>(a.out + m * a.ldo + a.coff + n0) = epilogue4(v, sc, bi, a.act);
+                            float4 v = epilogue4(make_float4(acc[i][h * 4], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]), sc, bi, a.act);
+                            if (RES) {
+                                const float4 q = rv[RES ? i : 0][h];
+                                v.x = act_apply(v.x + q.x, a.act2); v.y = act_apply(v.y + q.y, a.act2);
+                                v.z = act_apply(v.z + q.z, a.act2); v.w = act_apply(v.w + q.w, a.act2);
+                            }
+                            *reinterpret_cast<float4 *>(a.out + m * a.ldo + a.coff + n0) = v;
                         }
                     }
                 }

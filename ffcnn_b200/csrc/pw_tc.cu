@@ -9,12 +9,13 @@
  *                          the layer's weights once per CTA (resident for the whole persistent loop)
  *   warp 1  MMA issuer   : one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=NS, K=8 per instruction),
  *                          accumulators live in TMEM (double buffered), completion via tcgen05.commit -> mbarrier
- *   warps 2-5            : (a) 3xTF32 split of the activation tile, (b) epilogue: tcgen05.ld -> act(fma(acc, s, b))
- *                          -> swizzled smem staging -> TMA store (coalesced 128-byte rows, clipped at N and M)
+ *   warps 2-5            : (a) 3xTF32 split of the landed activation tile, (b) epilogue: tcgen05.ld -> act(fma(acc, s, b))
+ *                          [+ fused shortcut add] -> swizzled smem staging -> TMA store (coalesced 128-byte rows, clipped
+ *                          at N and M).  (Separate split / epilogue warp groups were tried and measured slower: r1d.)
  *
  * Numerics.  One TF32 pass keeps 10 mantissa bits per operand and misses the box tolerance by ~0.4 px, so
- * the default is the 3xTF32 split: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) (both exactly representable
- * in tf32, so the result does not depend on how the tensor core truncates its inputs -- measured: it truncates), and
+ * the default is the 3xTF32 split: x = hi + lo with hi = rna_tf32(x) (exactly representable in tf32, so it does not
+ * matter that the tensor core truncates its inputs -- measured: it does) and lo = x - hi (exact, zero-mean), and
  * D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi accumulated in fp32.  Round-to-nearest matters: a truncating split leaves an
  * error of constant sign (~2^-22 per product) that compounds over the 55 pointwise layers of the graph; the rounded
  * split is zero-mean (~2^-24).
@@ -40,8 +41,8 @@ namespace {
 
 constexpr int BM = 128;                 /* pixels per tile = UMMA M */
 constexpr int A_SUB = BM * 128;         /* bytes of one [128 x 32 fp32] sub-tile */
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 256;          /* warps 2-9: 3xTF32 split + epilogue, two threads per tile row (alternate 8/16-column units) */
+constexpr int NUM_THREADS = 64 + EPI_THREADS;
 
 struct TcArgs {
     long M;
@@ -49,6 +50,7 @@ struct TcArgs {
     int tiles;                          /* M tiles */
     uint32_t tmem_cols;
     const float *scale, *bias;          /* [nsl*NS], zero padded */
+    const float *res; int ldr, act2, N; /* optional fused shortcut (ffcnn.c:418-423): out = act2(conv + res[m][n]) */
 };
 
 /* round-to-nearest (ties away) to tf32: the result is an fp32 value whose low 13 mantissa bits are zero */
@@ -59,10 +61,17 @@ __device__ __forceinline__ float tf32_rna(float x)
     return __uint_as_float(r);
 }
 
-__device__ __forceinline__ float act_apply(float v, int act)
+/* Same rounding with two full-rate integer ops (cvt.rna.tf32 issues on the quarter-rate conversion pipe and was the
+ * bottleneck of the split warps): adding half a tf32 ulp to the magnitude bits and clearing the low 13 rounds to nearest,
+ * ties away from zero. */
+__device__ __forceinline__ float tf32_round(float x)
 {
-    return act == 2 ? (v > 0.f ? v : 0.1f * v) : act == 1 ? fmaxf(v, 0.f) : v;
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+
+/* activation as a negative-side slope: linear 1, relu 0, leaky 0.1 (utils.h:15-23) -- branch free in the epilogue */
+__device__ __forceinline__ float act_slope(int act) { return act == 2 ? 0.1f : act == 1 ? 0.f : 1.f; }
+__device__ __forceinline__ float act_apply(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
@@ -94,7 +103,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
-    for (int i = threadIdx.x; i < NS; i += NUM_THREADS) { sSc[i] = a.scale[slice * NS + i]; sBi[i] = a.bias[slice * NS + i]; }
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) { sSc[i] = a.scale[slice * NS + i]; sBi[i] = a.bias[slice * NS + i]; }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -153,36 +162,52 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             }
         }
     } else {
-        /* ===================== split + epilogue warps (one thread per tile row) ===================== */
+        /* ===================== split + epilogue warps (two threads per tile row) ===================== */
         const int q = warp & 3;                              /* TMEM lane quarter this warp may access */
+        const int half = (warp - 2) >> 2;                    /* which alternate unit of the row this warp handles */
         const int row = q * 32 + lane;
-        const int et = threadIdx.x - 64;                     /* 0..127 */
+        const int et = threadIdx.x - 64;                     /* 0..255 */
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int nchunks = (NS + 31) / 32;
+        const float slope1 = act_slope(a.act), slope2 = act_slope(a.act2);
         int ob = 0;
 
         auto epilogue = [&](int t, int it) {
             const int ab = it & 1; const uint32_t aph = (it >> 1) & 1;
+            const long m = (long)t * BM + row;
+            const bool has_res = a.res != nullptr && m < a.M;
             mbar_wait(tfull + ab, aph);
             tc_fence_after_sync();
             for (int j = 0; j < nchunks; j++) {
                 uint8_t *stage = sO + (size_t)ob * A_SUB;
                 if (et == 0) { if (a.OB == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
                 named_bar_sync(1, EPI_THREADS);              /* staging buffer `ob` is free again */
-                const int halves = (NS - j * 32) >= 32 ? 2 : 1;
-                for (int hf = 0; hf < halves; hf++) {
+                const int cl = j * 32 + half * 16;           /* this warp's 16 columns inside the slice */
+                if (cl < NS) {
+                    float4 rv[4];
+                    if (has_res) {                           /* skip tensor of the fused shortcut: loads issued before the TMEM read */
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const int n0 = slice * NS + cl + 4 * c;
+                            rv[c] = n0 < a.N ? __ldg(reinterpret_cast<const float4 *>(a.res + m * a.ldr + n0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
                     uint32_t r[16];
-                    tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32 + hf * 16, r);
+                    tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + cl, r);
                     tmem_ld_wait();
-                    const float *sc = sSc + j * 32 + hf * 16, *bi = sBi + j * 32 + hf * 16;
+                    const float *sc = sSc + cl, *bi = sBi + cl;
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         float4 v;
-                        v.x = act_apply(fmaf(__uint_as_float(r[4 * c + 0]), sc[4 * c + 0], bi[4 * c + 0]), a.act);
-                        v.y = act_apply(fmaf(__uint_as_float(r[4 * c + 1]), sc[4 * c + 1], bi[4 * c + 1]), a.act);
-                        v.z = act_apply(fmaf(__uint_as_float(r[4 * c + 2]), sc[4 * c + 2], bi[4 * c + 2]), a.act);
-                        v.w = act_apply(fmaf(__uint_as_float(r[4 * c + 3]), sc[4 * c + 3], bi[4 * c + 3]), a.act);
-                        const int chunk = hf * 4 + c;
+                        v.x = act_apply(fmaf(__uint_as_float(r[4 * c + 0]), sc[4 * c + 0], bi[4 * c + 0]), slope1);
+                        v.y = act_apply(fmaf(__uint_as_float(r[4 * c + 1]), sc[4 * c + 1], bi[4 * c + 1]), slope1);
+                        v.z = act_apply(fmaf(__uint_as_float(r[4 * c + 2]), sc[4 * c + 2], bi[4 * c + 2]), slope1);
+                        v.w = act_apply(fmaf(__uint_as_float(r[4 * c + 3]), sc[4 * c + 3], bi[4 * c + 3]), slope1);
+                        if (has_res) {
+                            v.x = act_apply(v.x + rv[c].x, slope2); v.y = act_apply(v.y + rv[c].y, slope2);
+                            v.z = act_apply(v.z + rv[c].z, slope2); v.w = act_apply(v.w + rv[c].w, slope2);
+                        }
+                        const int chunk = half * 4 + c;
                         *reinterpret_cast<float4 *>(stage + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
                     }
                 }
@@ -201,22 +226,22 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 mbar_wait(full + s, ph);
                 uint8_t *arow = sA + (size_t)s * Kc * A_SUB + row * 128;
                 const uint32_t alo = tmem_base + lane_addr + alo_col0 + s * Kc * 32;
-                for (int kc = 0; kc < Kc; kc++) {
-#pragma unroll
-                    for (int c2 = 0; c2 < 4; c2++) {
-                        float4 *p0 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2) ^ (row & 7)) << 4));
-                        float4 *p1 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2 + 1) ^ (row & 7)) << 4));
-                        const float4 x0 = *p0, x1 = *p1;
-                        float4 h0, h1; uint32_t lo[8];
-                        h0.x = tf32_rna(x0.x); h0.y = tf32_rna(x0.y); h0.z = tf32_rna(x0.z); h0.w = tf32_rna(x0.w);
-                        h1.x = tf32_rna(x1.x); h1.y = tf32_rna(x1.y); h1.z = tf32_rna(x1.z); h1.w = tf32_rna(x1.w);
-                        lo[0] = __float_as_uint(tf32_rna(x0.x - h0.x)); lo[1] = __float_as_uint(tf32_rna(x0.y - h0.y));
-                        lo[2] = __float_as_uint(tf32_rna(x0.z - h0.z)); lo[3] = __float_as_uint(tf32_rna(x0.w - h0.w));
-                        lo[4] = __float_as_uint(tf32_rna(x1.x - h1.x)); lo[5] = __float_as_uint(tf32_rna(x1.y - h1.y));
-                        lo[6] = __float_as_uint(tf32_rna(x1.z - h1.z)); lo[7] = __float_as_uint(tf32_rna(x1.w - h1.w));
-                        *p0 = h0; *p1 = h1;
-                        tmem_st8(alo + kc * 32 + c2 * 8, lo);
-                    }
+#pragma unroll 2
+                for (int u = half; u < Kc * 4; u += 2) {     /* unit u = 8 consecutive k of this row (two 16-byte chunks) */
+                    const int kc = u >> 2, c2 = u & 3;
+                    float4 *p0 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2) ^ (row & 7)) << 4));
+                    float4 *p1 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2 + 1) ^ (row & 7)) << 4));
+                    const float4 x0 = *p0, x1 = *p1;
+                    float4 h0, h1; uint32_t lo[8];
+                    h0.x = tf32_round(x0.x); h0.y = tf32_round(x0.y); h0.z = tf32_round(x0.z); h0.w = tf32_round(x0.w);
+                    h1.x = tf32_round(x1.x); h1.y = tf32_round(x1.y); h1.z = tf32_round(x1.z); h1.w = tf32_round(x1.w);
+                    /* lo = x - hi is exact, symmetric about 0 and has <= 13 significant bits; the tensor core drops the last two */
+                    lo[0] = __float_as_uint(x0.x - h0.x); lo[1] = __float_as_uint(x0.y - h0.y);
+                    lo[2] = __float_as_uint(x0.z - h0.z); lo[3] = __float_as_uint(x0.w - h0.w);
+                    lo[4] = __float_as_uint(x1.x - h1.x); lo[5] = __float_as_uint(x1.y - h1.y);
+                    lo[6] = __float_as_uint(x1.z - h1.z); lo[7] = __float_as_uint(x1.w - h1.w);
+                    *p0 = h0; *p1 = h1;
+                    tmem_st8(alo + u * 8, lo);
                 }
                 fence_proxy_async_smem();                    /* in-place A_hi writes -> visible to the tensor core (async proxy) */
                 tmem_st_wait();
@@ -385,7 +410,8 @@ int pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStream_t st)
     return 0;
 }
 
-int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int coff, long M, cudaStream_t st)
+int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int coff, long M, cudaStream_t st,
+              const float *res, int ldr, int act2)
 {
     CUtensorMap tmA, tmD;
     if (make_map(&tmA, in, p->K, (uint64_t)M, ldi, BM) != 0) return -1;
@@ -394,6 +420,7 @@ int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int co
     a.M = M; a.K = p->K; a.Kc = p->Kc; a.ksteps_total = p->ksteps_total; a.NS = p->NS; a.nsl = p->nsl; a.S = p->S; a.OB = p->OB;
     a.act = p->act; a.split = p->split; a.tiles = (int)((M + BM - 1) / BM); a.tmem_cols = p->tmem_cols;
     a.scale = p->d_scb; a.bias = p->d_scb + p->NP;
+    a.res = res; a.ldr = ldr; a.act2 = act2; a.N = p->N;
     long want = (long)a.tiles * p->nsl;
     int grid = (int)(want < p->num_sms ? want : p->num_sms);
     grid -= grid % p->nsl;

@@ -10,7 +10,9 @@ struct PwTcPlan;
 PwTcPlan   *pw_tc_plan_create(int K, int N, int act, int mode);
 void        pw_tc_plan_destroy(PwTcPlan *p);
 int         pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStream_t st);
-int         pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int coff, long M, cudaStream_t st);
+/* res != NULL fuses the following shortcut layer: out = act2(conv(in) + res[m][0..N)), res row stride ldr floats */
+int         pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int coff, long M, cudaStream_t st,
+                      const float *res, int ldr, int act2);
 const char *pw_tc_mode_name(const PwTcPlan *p);
 
 /* generic tiled tensor map over fp32 data: dims/box innermost first, strides_bytes[i] = byte stride of dimension i+1.

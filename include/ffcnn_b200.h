@@ -46,7 +46,9 @@ int   ffb_commit_weights(NET *net);
  * (conv-v0); "pw_mode" 0 = auto, 1 = fp32 FFMA everywhere, 2 = tcgen05 3xTF32 where eligible,
  * 3 = tcgen05 1xTF32; "dw_mode" 0 = TMA-fed shared-memory stencil for the depthwise layers (default), 1 = the
  * register-window kernel fed by plain loads; "graph" 1 = replay a captured CUDA graph (default), 0 = plain launches;
- * "keep_all" 1 = every layer output gets its own buffer (needed by ffb_layer_output). */
+ * "keep_all" 1 = every layer output gets its own buffer (needed by ffb_layer_output); "fuse_input" 1 (default) = when
+ * the frames already have the net's size, the stem kernel reads the u8 frames itself (net_input fused, no fp32 input
+ * tensor) -- the frame buffer handed to ffb_input_u8 must then stay valid until ffb_forward's work has completed. */
 int  ffb_set_option(NET *net, const char *name, int value);
 int  ffb_get_option(NET *net, const char *name);
 

@@ -65,7 +65,7 @@ t = time.time(); K = 10
 for rep in range(K): net.forward()
 net.sync(); dt = (time.time() - t) / K
 P("batch", B, "forward ms", "%.3f" % (dt * 1e3), "frames/s", "%.0f" % (B / dt), "launches", net.launches_per_forward(), "arena MB", net.get_option("arena_mb"))
-ms = net.layer_times(reps=5)
+ms = net.layer_times(reps=10)
 tot_b = 0; rows = []
 for i in range(net.layer_num):
     b, fl, kn = net.layer_cost(i)
