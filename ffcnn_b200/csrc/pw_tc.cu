@@ -41,17 +41,25 @@ namespace {
 
 constexpr int BM = 128;                 /* pixels per tile = UMMA M */
 constexpr int A_SUB = BM * 128;         /* bytes of one [128 x 32 fp32] sub-tile */
-constexpr int EPI_THREADS = 256;          /* warps 2-9: 3xTF32 split + epilogue, two threads per tile row (alternate 8/16-column units) */
-constexpr int NUM_THREADS = 64 + EPI_THREADS;
+constexpr int EPI_THREADS = 256;          /* one split+epilogue group = 8 warps, two threads per tile row */
+constexpr int MAX_GROUPS = 2;             /* groups take alternate tiles (group g owns accumulator buffer g) */
+constexpr int MAX_THREADS = 64 + MAX_GROUPS * EPI_THREADS;
 
 struct TcArgs {
     long M;
-    int K, Kc, ksteps_total, NS, nsl, S, OB, act, split;
+    int K, Kc, ksteps_total, NS, nsl, S, G, act, split;   /* G = number of split+epilogue warp groups */
     int tiles;                          /* M tiles */
     uint32_t tmem_cols;
     const float *scale, *bias;          /* [nsl*NS], zero padded */
     const float *res; int ldr, act2, N; /* optional fused shortcut (ffcnn.c:418-423): out = act2(conv + res[m][n]) */
+    long long *trace;                   /* developer timeline (tools/tc_trace.py): CTA 0 stamps [role][iteration][event] */
 };
+
+#ifdef FFB_TC_TRACE
+#define TRACE(role, it, ev) do { if (a.trace && blockIdx.x == 0 && (it) < 64) a.trace[((role) * 64 + (it)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(role, it, ev) do { } while (0)
+#endif
 
 /* round-to-nearest (ties away) to tf32: the result is an fp32 value whose low 13 mantissa bits are zero */
 __device__ __forceinline__ float tf32_rna(float x)
@@ -73,7 +81,7 @@ __device__ __forceinline__ float tf32_round(float x)
 __device__ __forceinline__ float act_slope(int act) { return act == 2 ? 0.1f : act == 1 ? 0.f : 1.f; }
 __device__ __forceinline__ float act_apply(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
         const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmD, const TcArgs a)
 {
@@ -85,7 +93,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     uint8_t *sBl = sBh + (size_t)Kc * b_sub;
     uint8_t *sA  = sBl + (a.split ? (size_t)Kc * b_sub : 0);
     uint8_t *sO  = sA + (size_t)S * Kc * A_SUB;
-    float   *sSc = reinterpret_cast<float *>(sO + (size_t)a.OB * A_SUB);
+    float   *sSc = reinterpret_cast<float *>(sO + (size_t)a.G * 8 * 4096);
     float   *sBi = sSc + NS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBi + NS);
     uint64_t *full = bars, *empty = bars + S, *conv = bars + 2 * S, *tfull = bars + 3 * S, *tempty = tfull + 2, *bfull = tempty + 2;
@@ -122,6 +130,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             for (int t = group; t < a.tiles; t += ngroups, it++) {
                 const int s = it % S; const uint32_t ph = (it / S) & 1;
                 mbar_wait(empty + s, ph ^ 1);
+                TRACE(0, it, 0);
                 mbar_arrive_expect_tx(full + s, (uint32_t)Kc * A_SUB);
                 for (int kc = 0; kc < Kc; kc++) tma_load_2d(sA + ((size_t)s * Kc + kc) * A_SUB, &tmA, kc * 32, t * BM, full + s);
             }
@@ -136,7 +145,9 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 const int s = it % S; const uint32_t ph = (it / S) & 1;
                 const int ab = it & 1; const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(a.split ? conv + s : full + s, ph);
+                TRACE(1, it, 0);
                 mbar_wait(tempty + ab, aph ^ 1);
+                TRACE(1, it, 1);
                 tc_fence_after_sync();
                 const uint32_t d = tmem_base + acc_col0 + ab * NS;
                 const uint32_t a_base = smem_u32(sA + (size_t)s * Kc * A_SUB);
@@ -159,100 +170,126 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 }
                 tc_commit(empty + s);            /* smem stage (and its A_lo columns) reusable once these MMAs retire */
                 tc_commit(tfull + ab);           /* accumulator ready for the epilogue */
+                TRACE(1, it, 2);
             }
         }
     } else {
         /* ===================== split + epilogue warps (two threads per tile row) ===================== */
         const int q = warp & 3;                              /* TMEM lane quarter this warp may access */
-        const int half = (warp - 2) >> 2;                    /* which alternate unit of the row this warp handles */
+        const int grp = (warp - 2) >> 3;                     /* warp group: takes the tiles with it % G == grp */
+        const int half = ((warp - 2) >> 2) & 1;              /* which alternate unit of the row this warp handles */
         const int row = q * 32 + lane;
-        const int et = threadIdx.x - 64;                     /* 0..255 */
+        const int et = threadIdx.x - 64 - grp * EPI_THREADS + (grp ? 1024 : 0);   /* 0 only for the first thread of group 0 (trace) */
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int nchunks = (NS + 31) / 32;
         const float slope1 = act_slope(a.act), slope2 = act_slope(a.act2);
-        int ob = 0;
+        /* warp-private staging: this warp's [32 rows x 128 B] box, 1024-byte aligned, SWIZZLE_128B like the tensor map.
+           No CTA-level barrier anywhere in the epilogue: a warp stages its rows, __syncwarp()s and stores its own box. */
+        uint8_t *stage = sO + (size_t)(warp - 2) * 4096;
+        const uint32_t stage_addr = smem_u32(stage), sc_addr = smem_u32(sSc), bi_addr = smem_u32(sBi);
 
         auto epilogue = [&](int t, int it) {
             const int ab = it & 1; const uint32_t aph = (it >> 1) & 1;
             const long m = (long)t * BM + row;
             const bool has_res = a.res != nullptr && m < a.M;
+            if (et == 0) TRACE(3, it, 0);
             mbar_wait(tfull + ab, aph);
+            if (et == 0) TRACE(3, it, 1);
             tc_fence_after_sync();
-            for (int j = 0; j < nchunks; j++) {
-                uint8_t *stage = sO + (size_t)ob * A_SUB;
-                if (et == 0) { if (a.OB == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-                named_bar_sync(1, EPI_THREADS);              /* staging buffer `ob` is free again */
-                const int cl = j * 32 + half * 16;           /* this warp's 16 columns inside the slice */
-                if (cl < NS) {
-                    float4 rv[4];
-                    if (has_res) {                           /* skip tensor of the fused shortcut: loads issued before the TMEM read */
+            for (int j = half; j < nchunks; j += 2) {        /* this warp's 32-column chunks of its 32 rows */
+                const int ncols = min(32, NS - j * 32);
+                uint32_t r[2][16];
+                tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32, r[0]);
+                if (ncols > 16) tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32 + 16, r[1]);
+                if (lane == 0) tma_store_wait_read<0>();     /* the previous box of this warp has left shared memory */
+                __syncwarp();
+                tmem_ld_wait();
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    const int cl = j * 32 + hf * 16;
+                    if (hf * 16 < ncols) {
+                        float4 rv[4];
+                        if (has_res) {                       /* skip tensor of the fused shortcut */
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const int n0 = slice * NS + cl + 4 * c;
+                                rv[c] = n0 < a.N ? __ldg(reinterpret_cast<const float4 *>(a.res + m * a.ldr + n0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
-                            const int n0 = slice * NS + cl + 4 * c;
-                            rv[c] = n0 < a.N ? __ldg(reinterpret_cast<const float4 *>(a.res + m * a.ldr + n0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 sc = lds128(sc_addr + (cl + 4 * c) * 4), bi = lds128(bi_addr + (cl + 4 * c) * 4);
+                            float4 v;
+                            v.x = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 0]), sc.x, bi.x), slope1);
+                            v.y = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 1]), sc.y, bi.y), slope1);
+                            v.z = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 2]), sc.z, bi.z), slope1);
+                            v.w = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 3]), sc.w, bi.w), slope1);
+                            if (has_res) {
+                                v.x = act_apply(v.x + rv[c].x, slope2); v.y = act_apply(v.y + rv[c].y, slope2);
+                                v.z = act_apply(v.z + rv[c].z, slope2); v.w = act_apply(v.w + rv[c].w, slope2);
+                            }
+                            const int chunk = hf * 4 + c;
+                            sts128(stage_addr + lane * 128 + ((chunk ^ (lane & 7)) << 4), v);
                         }
-                    }
-                    uint32_t r[16];
-                    tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + cl, r);
-                    tmem_ld_wait();
-                    const float *sc = sSc + cl, *bi = sBi + cl;
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        float4 v;
-                        v.x = act_apply(fmaf(__uint_as_float(r[4 * c + 0]), sc[4 * c + 0], bi[4 * c + 0]), slope1);
-                        v.y = act_apply(fmaf(__uint_as_float(r[4 * c + 1]), sc[4 * c + 1], bi[4 * c + 1]), slope1);
-                        v.z = act_apply(fmaf(__uint_as_float(r[4 * c + 2]), sc[4 * c + 2], bi[4 * c + 2]), slope1);
-                        v.w = act_apply(fmaf(__uint_as_float(r[4 * c + 3]), sc[4 * c + 3], bi[4 * c + 3]), slope1);
-                        if (has_res) {
-                            v.x = act_apply(v.x + rv[c].x, slope2); v.y = act_apply(v.y + rv[c].y, slope2);
-                            v.z = act_apply(v.z + rv[c].z, slope2); v.w = act_apply(v.w + rv[c].w, slope2);
-                        }
-                        const int chunk = half * 4 + c;
-                        *reinterpret_cast<float4 *>(stage + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
                     }
                 }
-                if (j == nchunks - 1) { tc_fence_before_sync(); mbar_arrive(tempty + ab); }   /* accumulator drained */
                 fence_proxy_async_smem();
-                named_bar_sync(1, EPI_THREADS);
-                if (et == 0) { tma_store_2d(&tmD, stage, slice * NS + j * 32, t * BM); tma_store_commit(); }
-                ob = (ob + 1) % a.OB;
+                __syncwarp();
+                if (lane == 0) { tma_store_2d(&tmD, stage, slice * NS + j * 32, t * BM + q * 32); tma_store_commit(); }
             }
+            tc_fence_before_sync();
+            mbar_arrive(tempty + ab);                        /* accumulator drained (all 256 threads arrive) */
+            if (et == 0) TRACE(3, it, 2);
         };
 
-        int it = 0, prev_t = -1;
+        int it = 0, prev_t = -1, prev_it = -1;
         for (int t = group; t < a.tiles; t += ngroups, it++) {
+            if (it % a.G != grp) continue;
             if (a.split) {
                 const int s = it % S; const uint32_t ph = (it / S) & 1;
+                if (et == 0) TRACE(2, it, 0);
                 mbar_wait(full + s, ph);
-                uint8_t *arow = sA + (size_t)s * Kc * A_SUB + row * 128;
+                if (et == 0) TRACE(2, it, 1);
+                const uint32_t arow = smem_u32(sA + (size_t)s * Kc * A_SUB + row * 128);
                 const uint32_t alo = tmem_base + lane_addr + alo_col0 + s * Kc * 32;
-#pragma unroll 2
-                for (int u = half; u < Kc * 4; u += 2) {     /* unit u = 8 consecutive k of this row (two 16-byte chunks) */
-                    const int kc = u >> 2, c2 = u & 3;
-                    float4 *p0 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2) ^ (row & 7)) << 4));
-                    float4 *p1 = reinterpret_cast<float4 *>(arow + (size_t)kc * A_SUB + (((2 * c2 + 1) ^ (row & 7)) << 4));
-                    const float4 x0 = *p0, x1 = *p1;
-                    float4 h0, h1; uint32_t lo[8];
-                    h0.x = tf32_round(x0.x); h0.y = tf32_round(x0.y); h0.z = tf32_round(x0.z); h0.w = tf32_round(x0.w);
-                    h1.x = tf32_round(x1.x); h1.y = tf32_round(x1.y); h1.z = tf32_round(x1.z); h1.w = tf32_round(x1.w);
-                    /* lo = x - hi is exact, symmetric about 0 and has <= 13 significant bits; the tensor core drops the last two */
-                    lo[0] = __float_as_uint(x0.x - h0.x); lo[1] = __float_as_uint(x0.y - h0.y);
-                    lo[2] = __float_as_uint(x0.z - h0.z); lo[3] = __float_as_uint(x0.w - h0.w);
-                    lo[4] = __float_as_uint(x1.x - h1.x); lo[5] = __float_as_uint(x1.y - h1.y);
-                    lo[6] = __float_as_uint(x1.z - h1.z); lo[7] = __float_as_uint(x1.w - h1.w);
-                    *p0 = h0; *p1 = h1;
-                    tmem_st8(alo + u * 8, lo);
+                for (int ub = half; ub < Kc * 4; ub += 4) {  /* 2 units (of 8 consecutive k each) per pass, all loads issued first */
+                    float4 x[2][2]; uint32_t pp[2][2];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const int u = ub + 2 * i, kc = u >> 2, c2 = u & 3;
+                        pp[i][0] = arow + kc * A_SUB + (((2 * c2) ^ (row & 7)) << 4);
+                        pp[i][1] = arow + kc * A_SUB + (((2 * c2 + 1) ^ (row & 7)) << 4);
+                        if (u < Kc * 4) { x[i][0] = lds128(pp[i][0]); x[i][1] = lds128(pp[i][1]); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const int u = ub + 2 * i;
+                        if (u < Kc * 4) {
+                            const float4 x0 = x[i][0], x1 = x[i][1];
+                            float4 h0, h1; uint32_t lo[8];
+                            h0.x = tf32_round(x0.x); h0.y = tf32_round(x0.y); h0.z = tf32_round(x0.z); h0.w = tf32_round(x0.w);
+                            h1.x = tf32_round(x1.x); h1.y = tf32_round(x1.y); h1.z = tf32_round(x1.z); h1.w = tf32_round(x1.w);
+                            /* lo = x - hi is exact, symmetric about 0 and has <= 13 significant bits; the tensor core drops the last two */
+                            lo[0] = __float_as_uint(x0.x - h0.x); lo[1] = __float_as_uint(x0.y - h0.y);
+                            lo[2] = __float_as_uint(x0.z - h0.z); lo[3] = __float_as_uint(x0.w - h0.w);
+                            lo[4] = __float_as_uint(x1.x - h1.x); lo[5] = __float_as_uint(x1.y - h1.y);
+                            lo[6] = __float_as_uint(x1.z - h1.z); lo[7] = __float_as_uint(x1.w - h1.w);
+                            sts128(pp[i][0], h0); sts128(pp[i][1], h1);
+                            tmem_st8(alo + u * 8, lo);
+                        }
+                    }
                 }
                 fence_proxy_async_smem();                    /* in-place A_hi writes -> visible to the tensor core (async proxy) */
                 tmem_st_wait();
                 tc_fence_before_sync();
                 mbar_arrive(conv + s);
+                if (et == 0) TRACE(2, it, 2);
             }
-            if (prev_t >= 0) epilogue(prev_t, it - 1);
-            prev_t = t;
+            if (prev_t >= 0) epilogue(prev_t, prev_it);
+            prev_t = t; prev_it = it;
         }
-        if (prev_t >= 0) epilogue(prev_t, it - 1);
-        if (et == 0) tma_store_wait_all<0>();
+        if (prev_t >= 0) epilogue(prev_t, prev_it);
+        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before_sync();
@@ -322,6 +359,9 @@ int ffb_make_tensor_map(CUtensorMap *m, const void *base, int rank, const unsign
     return 0;
 }
 
+static long long *g_tc_trace = nullptr;
+extern "C" void ffb_tc_set_trace(long long *dev_buf) { g_tc_trace = dev_buf; }   /* developer hook, effective only in -DFFB_TC_TRACE builds */
+
 struct PwTcPlan {
     int K, N, act, mode, split;
     int Kc, ksteps_total, NS, nsl, S, OB, NP, Kld;
@@ -342,8 +382,8 @@ static bool plan_tiling(PwTcPlan *p)
             if (NS > 256) continue;
             const size_t B = (size_t)(p->split ? 2 : 1) * p->Kc * NS * 128;
             for (int S = (minS == 2 ? 4 : 1); S >= minS; S--)
-                for (int OB = 2; OB >= 1; OB--) {
-                    const size_t smem = B + (size_t)S * p->Kc * A_SUB + (size_t)OB * A_SUB + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
+                for (int OB = (p->Kc <= 3 ? MAX_GROUPS : 1); OB >= 1; OB--) {   /* OB = warp groups (a second one pays off when tiles are small); staging = 8 warps x 4 KB each */
+                    const size_t smem = B + (size_t)S * p->Kc * A_SUB + (size_t)OB * 8 * 4096 + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
                     const int tmem = 2 * NS + (p->split ? S * p->Kc * 32 : 0);
                     if (smem <= limit && tmem <= 512) {
                         p->NS = NS; p->nsl = nsl; p->S = S; p->OB = OB; p->NP = nsl * NS;
@@ -361,9 +401,10 @@ static bool plan_tiling(PwTcPlan *p)
 PwTcPlan *pw_tc_plan_create(int K, int N, int act, int mode)
 {
     if (K % 4 || K < 8 || N < 8 || N > 2048) return nullptr;
-    /* auto: measured on B200 (profiles/r1b_pw_kernel_choice.txt) -- with K <= 32 the per-tile pipeline overhead of this kernel
-       exceeds what the FFMA streaming kernel needs for the few FMAs per byte; from K = 48 up the tensor pipe wins */
-    if (mode == 0 && (K < 48 || (N < 16 && K < 96))) return nullptr;
+    /* auto: measured on B200 (profiles/r1e_pw_kernel_choice.txt) -- for K <= 8 or N <= 8 a 128-pixel tile carries so few bytes
+       that this kernel's fixed per-tile latencies (mbarrier hand-offs, proxy fence, TMA store issue) exceed what the FFMA
+       streaming kernel needs; from K, N >= 16 the tensor pipe wins */
+    if (mode == 0 && (K < 16 || N < 16)) return nullptr;
     if (!encode_fn()) return nullptr;
     PwTcPlan *p = new PwTcPlan(); memset(p, 0, sizeof *p);
     p->K = K; p->N = N; p->act = act; p->mode = mode == 3 ? 3 : 2; p->split = p->mode == 2;
@@ -415,17 +456,18 @@ int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int co
 {
     CUtensorMap tmA, tmD;
     if (make_map(&tmA, in, p->K, (uint64_t)M, ldi, BM) != 0) return -1;
-    if (make_map(&tmD, out + coff, p->N, (uint64_t)M, ldo, BM) != 0) return -1;
+    if (make_map(&tmD, out + coff, p->N, (uint64_t)M, ldo, 32) != 0) return -1;      /* one warp's rows per store box */
     TcArgs a;
-    a.M = M; a.K = p->K; a.Kc = p->Kc; a.ksteps_total = p->ksteps_total; a.NS = p->NS; a.nsl = p->nsl; a.S = p->S; a.OB = p->OB;
+    a.M = M; a.K = p->K; a.Kc = p->Kc; a.ksteps_total = p->ksteps_total; a.NS = p->NS; a.nsl = p->nsl; a.S = p->S; a.G = p->OB;
     a.act = p->act; a.split = p->split; a.tiles = (int)((M + BM - 1) / BM); a.tmem_cols = p->tmem_cols;
     a.scale = p->d_scb; a.bias = p->d_scb + p->NP;
     a.res = res; a.ldr = ldr; a.act2 = act2; a.N = p->N;
+    a.trace = g_tc_trace;
     long want = (long)a.tiles * p->nsl;
     int grid = (int)(want < p->num_sms ? want : p->num_sms);
     grid -= grid % p->nsl;
     if (grid < p->nsl) grid = p->nsl;
-    k_pw_tc<<<grid, NUM_THREADS, p->smem, st>>>(tmA, p->tmBh, p->tmBl, tmD, a);
+    k_pw_tc<<<grid, 64 + p->OB * EPI_THREADS, p->smem, st>>>(tmA, p->tmBh, p->tmBl, tmD, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffb_set_error("pw_tc launch failed: %s (grid %d smem %zu)", cudaGetErrorString(e), grid, p->smem); return -1; }
     return 0;

@@ -20,6 +20,19 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+/* explicit shared-space 128-bit accesses on 32-bit shared addresses: pointers carved out of the dynamic smem blob lose
+ * their address space and nvcc falls back to generic LD/ST (slower, and ordered against every other generic access) */
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 /* ---------------------------------------------------------------- mbarrier */
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

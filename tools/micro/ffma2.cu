@@ -1,0 +1,42 @@
+// microbenchmark: FFMA vs FFMA2 (fma.rn.f32x2) issue throughput on sm_100a. nvcc -gencode arch=compute_100a,code=sm_100a -O3 ffma2.cu -o ffma2
+#include <cstdio>
+#include <cuda_runtime.h>
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{ unsigned long long r; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+template <int MODE> __global__ void k(float *out, int iters, float s)
+{
+    float a[16]; unsigned long long p[8];
+    for (int i = 0; i < 16; i++) a[i] = threadIdx.x * 0.001f + i;
+    for (int i = 0; i < 8; i++) { float2 t = make_float2(a[2 * i], a[2 * i + 1]); p[i] = *reinterpret_cast<unsigned long long *>(&t); }
+    float2 sv = make_float2(s, s); unsigned long long s2 = *reinterpret_cast<unsigned long long *>(&sv);
+    for (int it = 0; it < iters; it++) {
+        if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], s, 0.5f);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) p[i] = fma2(p[i], s2, s2);
+        }
+    }
+    float acc = 0;
+    for (int i = 0; i < 16; i++) acc += a[i];
+    for (int i = 0; i < 8; i++) { float2 t = *reinterpret_cast<float2 *>(&p[i]); acc += t.x + t.y; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+int main()
+{
+    float *d; cudaMalloc(&d, 148 * 8 * 256 * 4);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 20000;
+    for (int mode = 0; mode < 2; mode++) {
+        for (int rep = 0; rep < 2; rep++) {
+            cudaEventRecord(e0);
+            if (mode == 0) k<0><<<148 * 8, 256>>>(d, iters, 0.999f); else k<1><<<148 * 8, 256>>>(d, iters, 0.999f);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double fmas = 148.0 * 8 * 256 * 16.0 * iters;
+            printf("%s: %.3f ms  %.1f TFLOP/s (fp32 FMA = 2 flop)\n", mode ? "FFMA2" : "FFMA ", ms, 2 * fmas / ms / 1e9);
+        }
+    }
+    return 0;
+}
