@@ -94,6 +94,8 @@ def lib():
         "ffb_boxes": (C.c_int, [NP, C.c_int, C.POINTER(C.POINTER(BBOX))]),
         "ffb_raw_boxes": (C.c_int, [NP, C.c_int, C.POINTER(C.POINTER(BBOX))]),
         "ffb_detect_batch_u8": (C.c_int, [NP, vp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]),
+        "ffb_submit_u8": (C.c_int, [NP, vp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]),
+        "ffb_collect": (C.c_int, [NP]),
         "ffb_layer_output": (C.c_long, [NP, C.c_int, C.c_int, fp, C.c_long]),
         "ffb_layer_times": (C.c_int, [NP, fp, C.c_int, C.c_int, C.c_int]),
         "ffb_layer_cost": (C.c_int, [NP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_char_p, C.c_int]),
@@ -129,7 +131,7 @@ EXPORTS = ["ffb_last_error", "ffb_device_count", "ffb_net_parse", "ffb_net_attac
            "ffb_commit_weights", "ffb_set_option", "ffb_get_option", "ffb_set_stream", "ffb_get_stream", "ffb_sync",
            "ffb_input_u8", "ffb_input_chw", "ffb_forward", "ffb_detect", "ffb_detect_enqueue", "ffb_detect_finish",
            "ffb_last_d2h_bytes", "ffb_boxes", "ffb_raw_boxes",
-           "ffb_detect_batch_u8", "ffb_layer_output", "ffb_layer_times", "ffb_layer_cost", "ffb_launches_per_forward",
+           "ffb_detect_batch_u8", "ffb_submit_u8", "ffb_collect", "ffb_layer_output", "ffb_layer_times", "ffb_layer_cost", "ffb_launches_per_forward",
            "ffb_conv_create", "ffb_conv_destroy", "ffb_conv_run", "ffb_conv_kernel_name", "ffb_dev_alloc", "ffb_dev_free",
            "ffb_copy_h2d", "ffb_copy_d2h", "ffb_host_alloc_pinned", "ffb_host_free_pinned", "ffb_chw_to_nhwc",
            "ffb_nhwc_to_chw", "net_load", "net_free", "net_input", "net_forward", "net_dump", "net_profile", "groupconv",
@@ -283,6 +285,13 @@ class Net:
     def detect_batch_u8(self, frames, n: int, w: int, h: int, pitch: int):
         ptr = frames if isinstance(frames, int) else np.ascontiguousarray(frames, np.uint8).ctypes.data
         _check(self._L.ffb_detect_batch_u8(self.p, ptr, n, w, h, pitch, None, None), "ffb_detect_batch_u8")
+
+    def submit_u8(self, frames, n: int, w: int, h: int, pitch: int):
+        ptr = frames if isinstance(frames, int) else np.ascontiguousarray(frames, np.uint8).ctypes.data
+        _check(self._L.ffb_submit_u8(self.p, ptr, n, w, h, pitch, None, None), "ffb_submit_u8")
+
+    def collect(self):
+        _check(self._L.ffb_collect(self.p), "ffb_collect")
 
     def layer_output(self, layer: int, frame: int = 0) -> np.ndarray | None:
         n = _check(self._L.ffb_layer_output(self.p, layer, frame, None, 0), "ffb_layer_output")

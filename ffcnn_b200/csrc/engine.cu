@@ -352,6 +352,11 @@ struct ffb_engine {
     Candidate *d_cand = nullptr, *h_cand = nullptr; int *d_count = nullptr, *h_count = nullptr; int cand_cap = 0;
     std::vector<std::vector<BBOX>> boxes, raw;
     int s1 = 1, s2 = 1; size_t d2h_bytes = 0;
+    /* submit/collect pipeline: two device frame slots filled on a copy stream while the previous batch computes */
+    cudaStream_t copy_stream = nullptr; unsigned char *d_slot[2] = { nullptr, nullptr }; size_t slot_cap[2] = { 0, 0 };
+    cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr };
+    long submitted = 0, collected = 0;
+    struct SlotMeta { int n, w, h, pitch; float mean[3], norm[3]; bool has_mean, has_norm; } slot_meta[2];
     /* L2 flush scratch for ffb_layer_times */
     float *d_flush = nullptr; size_t flush_floats = 0;
 };
@@ -389,6 +394,8 @@ void ffb_engine_destroy(ffb_engine *e)
     for (ffb_conv *c : e->convs) conv_release(c);
     cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_cand); cudaFree(e->d_count); cudaFree(e->d_flush);
     cudaFreeHost(e->h_stage); cudaFreeHost(e->h_cand); cudaFreeHost(e->h_count);
+    for (int i = 0; i < 2; i++) { cudaFree(e->d_slot[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]); }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -926,6 +933,52 @@ int ffb_detect_batch_u8(NET *net, const unsigned char *frames_host, int n, int w
     if (ffb_input_u8(net, frames_host, n, w, h, pitch, mean, norm, 0) != 0) return -1;
     if (ffb_forward(net) != 0) return -1;
     return ffb_detect(net);
+}
+
+/* ---- pipelined end-to-end path: H2D of batch i+1 overlaps the forward pass and the host decode of batch i ---- */
+int ffb_submit_u8(NET *net, const unsigned char *frames_host, int n, int w, int h, int pitch, const float *mean, const float *norm)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    if (!frames_host || n < 1 || w < 1 || h < 1 || pitch < 3 * w) { ffb_set_error("ffb_submit_u8: bad arguments"); return -1; }
+    if (e->submitted - e->collected >= 2) { ffb_set_error("ffb_submit_u8: two batches already in flight, call ffb_collect first"); return -1; }
+    CK(cudaSetDevice(e->device));
+    if (!e->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming)); }
+    }
+    const int slot = (int)(e->submitted & 1);
+    const size_t bytes = (size_t)n * h * pitch;
+    if (bytes > e->slot_cap[slot]) {
+        CK(cudaStreamSynchronize(e->stream)); CK(cudaStreamSynchronize(e->copy_stream));
+        cudaFree(e->d_slot[slot]); e->d_slot[slot] = nullptr; e->slot_cap[slot] = 0;
+        CK(cudaMalloc(&e->d_slot[slot], bytes)); e->slot_cap[slot] = bytes;
+    }
+    if (e->submitted >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->ev_free[slot], 0));     /* the batch that used this slot has consumed it */
+    CK(cudaMemcpyAsync(e->d_slot[slot], frames_host, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
+    ffb_engine::SlotMeta &m = e->slot_meta[slot];
+    m.n = n; m.w = w; m.h = h; m.pitch = pitch; m.has_mean = mean != nullptr; m.has_norm = norm != nullptr;
+    for (int i = 0; i < 3; i++) { m.mean[i] = mean ? mean[i] : 0.f; m.norm[i] = norm ? norm[i] : 0.f; }
+    e->submitted++;
+    return 0;
+}
+
+int ffb_collect(NET *net)
+{
+    ffb_engine *e = engine_of(net);
+    if (!e) return -1;
+    if (e->collected >= e->submitted) { ffb_set_error("ffb_collect: nothing submitted"); return -1; }
+    CK(cudaSetDevice(e->device));
+    const int slot = (int)(e->collected & 1);
+    const ffb_engine::SlotMeta &m = e->slot_meta[slot];
+    CK(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
+    if (ffb_input_u8(net, e->d_slot[slot], m.n, m.w, m.h, m.pitch, m.has_mean ? m.mean : nullptr, m.has_norm ? m.norm : nullptr, 1) != 0) return -1;
+    if (ffb_forward(net) != 0) return -1;
+    CK(cudaEventRecord(e->ev_free[slot], e->stream));
+    if (ffb_detect_enqueue(net) < 0) return -1;
+    e->collected++;
+    return ffb_detect_finish(net);
 }
 
 /* net_forward(): host CHW input tensor -> boxes, one frame (the reference's own entry point) */
