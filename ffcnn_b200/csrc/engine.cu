@@ -111,12 +111,16 @@ static void pw_plan(ffb_conv *op)
 /* ---- TMA-fed depthwise 3x3 s1 kernel: tile planner + launcher ---- */
 struct DwPlan { int CB, TW, TH, RC, nch, IWb, IHb, ntx, nty, ntc, stages; size_t smem; };
 
-/* Pick channel block / tile / row chunking: one work item (2 px x 4 ch x RC rows) per thread, stage <= 56 KB (3 stages),
+/* Pick channel block / tile / row chunking: one work item (2 px x 4 ch x RC rows) per thread, stage <= 108 KB (2 stages),
  * minimising  halo re-read factor x shared-memory reads per output, with penalties for idle threads and for thin TMA
  * rows when the channel block is not the whole (contiguous) pixel. */
 static bool dw_plan(int C, int OH, int OW, DwPlan *p)
 {
-    const size_t stage_limit = 56 * 1024;
+    /* developer overrides for tile-shape sweeps (tools/op_bench.py): FFCNN_DW_STAGE_KB, FFCNN_DW_STAGES */
+    static const int env_kb = getenv("FFCNN_DW_STAGE_KB") ? atoi(getenv("FFCNN_DW_STAGE_KB")) : 0;
+    static const int env_st = getenv("FFCNN_DW_STAGES") ? atoi(getenv("FFCNN_DW_STAGES")) : 0;
+    const int stages = env_st ? env_st : 2;
+    const size_t stage_limit = (size_t)(env_kb ? env_kb : 108) * 1024;   /* measured (profiles/r1f_dw_tile_sweep.txt): few big tiles beat many small ones */
     double best = 1e30; bool ok = false;
     for (int CB = 4; CB <= C && CB <= 256; CB += 4) {
         if (C % CB) continue;
@@ -147,7 +151,7 @@ static bool dw_plan(int C, int OH, int OW, DwPlan *p)
         }
     }
     if (!ok) return false;
-    p->stages = 3;
+    p->stages = stages;
     const size_t stage = (((size_t)p->IHb * p->IWb * p->CB * 4) + 127) & ~(size_t)127;
     p->smem = p->stages * stage + 64 + 256;
     return true;
