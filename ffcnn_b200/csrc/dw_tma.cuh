@@ -52,6 +52,7 @@ k_dw3s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
         sm100::fence_barrier_init();
     }
     __syncthreads();
+    pdl_trigger(); pdl_wait();
 
     auto issue = [&](long tile, int s) {
         long r = tile;

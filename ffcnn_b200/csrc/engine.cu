@@ -43,6 +43,8 @@ using namespace ffb;
     } while (0)
 
 static int g_num_sms = 148;
+namespace sm100 { int g_ffb_pdl = 0; }     /* programmatic dependent launch between the kernels of a forward pass: FFCNN_PDL=1 enables. Measured (r1g): back-to-back launches of one layer gain 6 %, the captured graph gains nothing (3.44 vs 3.40 ms) -- the big CTAs (>= 120 KB smem) cannot co-reside with their predecessor -- so it stays off by default. */
+using sm100::launch_pdl;
 
 static inline int grid_for(long total, int block, int waves = 8)
 {
@@ -172,8 +174,7 @@ static int dw_launch(const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t 
     a.CB = pl.CB; a.TW = pl.TW; a.TH = pl.TH; a.RC = pl.RC; a.nch = pl.nch; a.ntx = pl.ntx; a.nty = pl.nty; a.ntc = pl.ntc;
     a.ntiles = (long)a.N * pl.nty * pl.ntx * pl.ntc; a.stages = pl.stages;
     const int grid = (int)std::min<long>(a.ntiles, g_num_sms);
-    k_dw3s1_tma<<<grid, DW_THREADS, pl.smem, st>>>(tm, a);
-    CK(cudaGetLastError());
+    CK(launch_pdl(k_dw3s1_tma, dim3(grid), dim3(DW_THREADS), pl.smem, st, tm, a));
     return 0;
 }
 
@@ -186,8 +187,7 @@ static cudaError_t pw_launch2(const PwArgs &a, int grid, size_t smem, cudaStream
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_pw_ffma<TM, TN, RES><<<grid, 256, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(k_pw_ffma<TM, TN, RES>, dim3(grid), dim3(256), smem, st, a);
 }
 
 template <int TM, int TN>
@@ -288,27 +288,23 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
         if (kind == CK_DW3_S2) {
             const int R = oh >= 40 ? 10 : oh;
             dim3 grid((ow * op->ic / 4 + 127) / 128, (oh + R - 1) / R, n);
-            k_dw3_s2<<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, oh, ow, R, op->act);
-            CK(cudaGetLastError());
+            CK(launch_pdl(k_dw3_s2, grid, dim3(128), 0, st, in, out, wt, sc, bi, ih, iw, op->ic, oh, ow, R, op->act));
             return 0;
         }
         {
         const int R = ih >= 64 ? 16 : ih >= 32 ? 10 : ih;
         dim3 grid((iw * op->ic / 4 + 127) / 128, (ih + R - 1) / R, n);
-        if (kind == CK_DW_S1_3) k_dw_s1<3><<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, R, op->act, -1);
-        else                    k_dw_s1<5><<<grid, 128, 0, st>>>(in, out, wt, sc, bi, ih, iw, op->ic, R, op->act, skip);
-        CK(cudaGetLastError());
+        if (kind == CK_DW_S1_3) CK(launch_pdl(k_dw_s1<3>, grid, dim3(128), 0, st, in, out, wt, sc, bi, ih, iw, op->ic, R, op->act, -1));
+        else                    CK(launch_pdl(k_dw_s1<5>, grid, dim3(128), 0, st, in, out, wt, sc, bi, ih, iw, op->ic, R, op->act, skip));
         return 0; }
     case CK_STEM: {
         dim3 grid((ow + 31) / 32, (oh + 7) / 8, n), block(32, 8);
-        k_stem_f32<32, 8><<<grid, block, 0, st>>>(in, out, op->stemw, ih, iw, oh, ow, op->act);
-        CK(cudaGetLastError());
+        CK(launch_pdl(k_stem_f32<32, 8>, grid, block, 0, st, in, out, op->stemw, ih, iw, oh, ow, op->act));
         return 0; }
     default: {
         const long total = (long)n * oh * ow * op->fn;
-        k_conv_generic<<<grid_for(total, 256, 16), 256, 0, st>>>(in, out + coff, op->d_packed, n, ih, iw, op->ic, ldi, oh, ow, op->fn, ldo,
-                                                                 op->groups, op->pad, op->stride, op->fs, op->row, op->act, skip);
-        CK(cudaGetLastError());
+        CK(launch_pdl(k_conv_generic, dim3(grid_for(total, 256, 16)), dim3(256), 0, st, in, out + coff, op->d_packed, n, ih, iw, op->ic, ldi, oh, ow, op->fn, ldo,
+                      op->groups, op->pad, op->stride, op->fs, op->row, op->act, skip));
         return 0; }
     }
 }
@@ -319,8 +315,7 @@ static int stem_run_u8(ffb_conv *op, const unsigned char *frames, int pitch, flo
 {
     const int oh = conv_out_dim(ih, 3, 1, 2), ow = conv_out_dim(iw, 3, 1, 2);
     dim3 grid((ow + 31) / 32, (oh + 7) / 8, n), block(32, 8);
-    k_stem_u8<32, 8><<<grid, block, 0, st>>>(frames, pitch, out, op->stemw, ih, iw, oh, ow, op->act, mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]);
-    CK(cudaGetLastError());
+    CK(launch_pdl(k_stem_u8<32, 8>, grid, block, 0, st, (const uint8_t *)frames, pitch, out, op->stemw, ih, iw, oh, ow, op->act, mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]));
     return 0;
 }
 
@@ -557,6 +552,7 @@ int ffb_net_attach(NET *net, int device, int max_batch)
     if ((env = getenv("FFCNN_PW_MODE")))   e->pw_mode = atoi(env);
     if ((env = getenv("FFCNN_GRAPH")))     e->use_graph = atoi(env);
     if ((env = getenv("FFCNN_DW_MODE")))   e->dw_mode = atoi(env);
+    if ((env = getenv("FFCNN_PDL")))       sm100::g_ffb_pdl = atoi(env);
     CK(cudaMalloc(&e->d_packed, std::max(1, net->weight_size) * sizeof(float)));
     CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     if (engine_prepare_weights(e) != 0) return -1;
@@ -704,9 +700,8 @@ int ffb_input_u8(NET *net, const unsigned char *frames, int n, int w, int h, int
     e->u8_src = src; e->u8_pitch = pitch;
     if (e->input_fused) return 0;
     const long total = (long)n * e->input.h * e->input.w;
-    k_input_u8<<<grid_for(total, 256, 16), 256, 0, e->stream>>>(src, e->input.p, n, w, h, pitch, e->input.w, e->input.h, sw, sh, s1, s2,
-                                                                mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]);
-    CK(cudaGetLastError());
+    CK(launch_pdl(k_input_u8, dim3(grid_for(total, 256, 16)), dim3(256), 0, e->stream, (const uint8_t *)src, e->input.p, n, w, h, pitch, e->input.w, e->input.h, sw, sh, s1, s2,
+                  mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]));
     return 0;
 }
 
@@ -749,13 +744,13 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         break;
     case LAYER_TYPE_MAXPOOL: case LAYER_TYPE_AVGPOOL:
         if (in.c % 4) { ffb_set_error("pool layer %d: channels %d not a multiple of 4", i, in.c); return -1; }
-        k_pool<<<grid_for((long)n * o.h * o.w * (o.c / 4), 128), 128, 0, st>>>(in.p, o.p, n, in.h, in.w, in.c, in.ld, o.h, o.w, o.ld, 0,
-                                                                              il->fs, il->stride, il->type == LAYER_TYPE_MAXPOOL);
+        CK(launch_pdl(k_pool, dim3(grid_for((long)n * o.h * o.w * (o.c / 4), 128)), dim3(128), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.h, o.w, o.ld, 0,
+                      il->fs, il->stride, (int)(il->type == LAYER_TYPE_MAXPOOL)));
         (*launches)++;
         break;
     case LAYER_TYPE_UPSAMPLE:
         if (in.c % 4) { ffb_set_error("upsample layer %d: channels %d not a multiple of 4", i, in.c); return -1; }
-        k_upsample<<<grid_for((long)n * o.h * o.w * (o.c / 4), 128), 128, 0, st>>>(in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride);
+        CK(launch_pdl(k_upsample, dim3(grid_for((long)n * o.h * o.w * (o.c / 4), 128)), dim3(128), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride));
         (*launches)++;
         break;
     case LAYER_TYPE_SHORTCUT: {
@@ -763,7 +758,7 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         const Tens &s = e->outs[il->depend_list[0]];
         if (s.h != in.h || s.w != in.w || s.c != in.c) { ffb_set_error("shortcut layer %d: shape mismatch", i); return -1; }
         const long n4 = (long)n * o.frame_floats() / 4;       /* ld is a multiple of 4 and identical for all three */
-        k_shortcut<<<grid_for(n4, 256), 256, 0, st>>>(in.p, s.p, o.p, n4, il->activation);
+        CK(launch_pdl(k_shortcut, dim3(grid_for(n4, 256)), dim3(256), 0, st, (const float *)in.p, (const float *)s.p, o.p, n4, il->activation));
         (*launches)++;
         break; }
     case LAYER_TYPE_ROUTE:
@@ -772,8 +767,8 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
             for (int d = 0; d < il->depend_num; d++) {
                 const Tens &s = e->outs[il->depend_list[d]];
                 const long px = (long)n * s.h * s.w;
-                if (s.c % 4 == 0 && coff % 4 == 0) k_concat<<<grid_for(px * (s.c / 4), 256), 256, 0, st>>>(s.p, o.p, px, s.c, s.ld, o.ld, coff);
-                else k_copy_strided<<<grid_for(px * s.c, 256), 256, 0, st>>>(s.p, o.p, px, s.c, s.ld, o.ld, coff);
+                if (s.c % 4 == 0 && coff % 4 == 0) CK(launch_pdl(k_concat, dim3(grid_for(px * (s.c / 4), 256)), dim3(256), 0, st, (const float *)s.p, o.p, px, s.c, s.ld, o.ld, coff));
+                else CK(launch_pdl(k_copy_strided, dim3(grid_for(px * s.c, 256)), dim3(256), 0, st, (const float *)s.p, o.p, px, s.c, s.ld, o.ld, coff));
                 coff += s.c; (*launches)++;
             }
         }
@@ -862,9 +857,8 @@ int ffb_detect_enqueue(NET *net)
         const LAYER *yl = net->layer_list + h.layer; const Tens &t = e->outs[h.layer - 1];
         if (t.c != 3 * (5 + yl->class_num)) { ffb_set_error("yolo layer %d: %d channels, expected %d", h.layer, t.c, 3 * (5 + yl->class_num)); return -1; }
         const long warps = (long)n * h.cells;
-        k_yolo_filter<<<(int)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(t.p, n, h.cells, t.ld, yl->class_num, 0, h.key_base,
-                                                                              yl->ignore_thres, e->d_cand, e->d_count, e->cand_cap);
-        CK(cudaGetLastError());
+        CK(launch_pdl(k_yolo_filter, dim3((int)((warps * 32 + 255) / 256)), dim3(256), 0, e->stream, (const float *)t.p, n, h.cells, t.ld, yl->class_num, 0, h.key_base,
+                      yl->ignore_thres, e->d_cand, e->d_count, e->cand_cap));
     }
     CK(cudaMemcpyAsync(e->h_count, e->d_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     return (int)heads.size();

@@ -16,8 +16,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "sm100.cuh"
 
 namespace ffb {
+
+using sm100::pdl_trigger;
+using sm100::pdl_wait;
 
 __device__ __forceinline__ float act_apply(float v, int act)
 {
@@ -51,6 +55,7 @@ __global__ void k_input_u8(const uint8_t *__restrict__ frames, float *__restrict
                            int n, int w, int h, int pitch, int W, int H, int sw, int sh, int s1, int s2,
                            float m0, float m1, float m2, float n0, float n1, float n2)
 {
+    pdl_trigger(); pdl_wait();
     const long total = (long)n * H * W;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W), y = (int)((i / W) % H); const long f = i / ((long)W * H);
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(TX * TY)
 k_stem_f32(const float *__restrict__ in, float *__restrict__ out, const __grid_constant__ StemW sw,
            int H, int W, int OH, int OW, int act)
 {
+    pdl_trigger(); pdl_wait();
     constexpr int IW = 2 * TX + 1, IH = 2 * TY + 1;
     __shared__ float4 tile[IH][IW];
     const int tid = threadIdx.y * TX + threadIdx.x;
@@ -136,6 +142,7 @@ __global__ void __launch_bounds__(TX * TY)
 k_stem_u8(const uint8_t *__restrict__ frames, int pitch, float *__restrict__ out, const __grid_constant__ StemW sw,
           int H, int W, int OH, int OW, int act, float m0, float m1, float m2, float n0, float n1, float n2)
 {
+    pdl_trigger(); pdl_wait();
     constexpr int IW = 2 * TX + 1, IH = 2 * TY + 1;
     __shared__ float4 tile[IH][IW];
     const int tid = threadIdx.y * TX + threadIdx.x;
@@ -185,6 +192,7 @@ k_dw_s1(const float *__restrict__ in, float *__restrict__ out, const float *__re
         const float *__restrict__ scale, const float *__restrict__ bias,
         int H, int W, int C, int R, int act, int skip_row0_at)
 {
+    pdl_trigger(); pdl_wait();
     constexpr int P = FS / 2;
     const int rowlen = W * C;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) * 4;           /* float offset inside a row */
@@ -244,6 +252,7 @@ k_dw3_s2(const float *__restrict__ in, float *__restrict__ out, const float *__r
          const float *__restrict__ scale, const float *__restrict__ bias,
          int H, int W, int C, int OH, int OW, int R, int act)
 {
+    pdl_trigger(); pdl_wait();
     const int orow = OW * C, irow = W * C;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (q >= orow) return;
@@ -292,6 +301,7 @@ __global__ void k_conv_generic(const float *__restrict__ in, float *__restrict__
                                int n, int H, int W, int C, int ldi, int OH, int OW, int OC, int ldo,
                                int groups, int pad, int stride, int fs, int row, int act, int skip_row0_at)
 {
+    pdl_trigger(); pdl_wait();
     const int cpg = C / groups, opg = OC / groups;
     const long total = (long)n * OH * OW * OC;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -323,6 +333,7 @@ __global__ void k_conv_generic(const float *__restrict__ in, float *__restrict__
 __global__ void k_pool(const float *__restrict__ in, float *__restrict__ out, int n, int H, int W, int C, int ldi,
                        int OH, int OW, int ldo, int coff, int fs, int stride, int is_max)
 {
+    pdl_trigger(); pdl_wait();
     const int c4n = C / 4;
     const long total = (long)n * OH * OW * c4n;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -348,6 +359,7 @@ __global__ void k_pool(const float *__restrict__ in, float *__restrict__ out, in
 __global__ void k_upsample(const float *__restrict__ in, float *__restrict__ out, int n, int H, int W, int C, int ldi,
                            int ldo, int coff, int s)
 {
+    pdl_trigger(); pdl_wait();
     const int c4n = C / 4, OH = H * s, OW = W * s;
     const long total = (long)n * OH * OW * c4n;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -362,6 +374,7 @@ __global__ void k_upsample(const float *__restrict__ in, float *__restrict__ out
 /* shortcut (ffcnn.c:418-423): out = act(a + b), both operands dense (ld == c), flat float4 stream */
 __global__ void k_shortcut(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long n4, int act)
 {
+    pdl_trigger(); pdl_wait();
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const float4 x = ldg4(a + 4 * i), y = ldg4(b + 4 * i);
         float4 r;
@@ -374,6 +387,7 @@ __global__ void k_shortcut(const float *__restrict__ a, const float *__restrict_
 /* route (ffcnn.c:425-434): copy one source into channel range [coff, coff+C) of the concat tensor */
 __global__ void k_concat(const float *__restrict__ in, float *__restrict__ out, long pixels, int C, int ldi, int ldo, int coff)
 {
+    pdl_trigger(); pdl_wait();
     const int c4n = C / 4;
     const long total = pixels * c4n;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -385,6 +399,7 @@ __global__ void k_concat(const float *__restrict__ in, float *__restrict__ out, 
 /* scalar variants for channel counts that are not a multiple of 4 (only reachable through odd cfgs) */
 __global__ void k_copy_strided(const float *__restrict__ in, float *__restrict__ out, long pixels, int C, int ldi, int ldo, int coff)
 {
+    pdl_trigger(); pdl_wait();
     const long total = pixels * C;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C); const long p = i / C;
@@ -444,6 +459,7 @@ struct Candidate { int frame, key, cls; float bs, cs, tx, ty, tw, th; };
 __global__ void k_yolo_filter(const float *__restrict__ head, int n, int cells, int ld, int classes, int head_index,
                               int key_base, float thresh, Candidate *__restrict__ list, int *__restrict__ counter, int cap)
 {
+    pdl_trigger(); pdl_wait();
     const int lane = threadIdx.x & 31;
     const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     if (warp >= (long)n * cells) return;

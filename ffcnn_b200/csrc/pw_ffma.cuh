@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) k_pw_ffma(const PwArgs a)
 
     for (int i = tid; i < K * BN / 4; i += 256) reinterpret_cast<float4 *>(Ws)[i] = ldg4(a.wt + 4 * i);
     for (int i = tid; i < BN; i += 256) { Ss[i] = a.scale[i]; Ss[BN + i] = a.bias[i]; }
+    pdl_trigger(); pdl_wait();             /* weights are static; everything below reads the previous layer's output */
 
     const int kc = K / 4;
     auto prefetch = [&](long tile, int buf) {

@@ -109,23 +109,25 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, EPI_THREADS); }
         mbar_init(bfull, 1);
         fence_barrier_init();
+        /* the layer's weights do not depend on the previous kernel: fetch them before the PDL wait */
+        mbar_arrive_expect_tx(bfull, (uint32_t)((a.split ? 2 : 1) * Kc) * b_sub);
+        for (int kc = 0; kc < Kc; kc++) {
+            tma_load_2d(sBh + (size_t)kc * b_sub, &tmBh, kc * 32, slice * NS, bfull);
+            if (a.split) tma_load_2d(sBl + (size_t)kc * b_sub, &tmBl, kc * 32, slice * NS, bfull);
+        }
     }
     if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
     for (int i = threadIdx.x; i < NS; i += blockDim.x) { sSc[i] = a.scale[slice * NS + i]; sBi[i] = a.bias[slice * NS + i]; }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    pdl_trigger(); pdl_wait();             /* from here on the kernel touches the previous layer's output */
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_col0 = 0, alo_col0 = 2 * NS;
 
     if (warp == 0) {
         /* ===================== TMA producer ===================== */
         if (elect_one()) {
-            mbar_arrive_expect_tx(bfull, (uint32_t)((a.split ? 2 : 1) * Kc) * b_sub);
-            for (int kc = 0; kc < Kc; kc++) {
-                tma_load_2d(sBh + (size_t)kc * b_sub, &tmBh, kc * 32, slice * NS, bfull);
-                if (a.split) tma_load_2d(sBl + (size_t)kc * b_sub, &tmBl, kc * 32, slice * NS, bfull);
-            }
             int it = 0;
             for (int t = group; t < a.tiles; t += ngroups, it++) {
                 const int s = it % S; const uint32_t ph = (it / S) & 1;
@@ -467,8 +469,7 @@ int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int co
     int grid = (int)(want < p->num_sms ? want : p->num_sms);
     grid -= grid % p->nsl;
     if (grid < p->nsl) grid = p->nsl;
-    k_pw_tc<<<grid, 64 + p->OB * EPI_THREADS, p->smem, st>>>(tmA, p->tmBh, p->tmBl, tmD, a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(k_pw_tc, dim3(grid), dim3(64 + p->OB * EPI_THREADS), p->smem, st, tmA, p->tmBh, p->tmBl, tmD, a);
     if (e != cudaSuccess) { ffb_set_error("pw_tc launch failed: %s (grid %d smem %zu)", cudaGetErrorString(e), grid, p->smem); return -1; }
     return 0;
 }

@@ -143,6 +143,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+/* ---------------------------------------------------------------- programmatic dependent launch (PDL) */
+/* Every kernel of the forward pass is launched with programmatic stream serialization: its CTAs may start while the previous
+ * kernel drains.  pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as resources free up; pdl_wait() blocks
+ * until the PREVIOUS kernel has completed and flushed its writes -- it must precede the first access to activations. */
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 /* ---------------------------------------------------------------- descriptors */
 /* K-major operand tile in SWIZZLE_128B layout: rows of 128 bytes (32 tf32), 8-row groups 1024 B apart.
  * bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
@@ -157,6 +164,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
 {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+/* host: launch with the PDL attribute (falls back to a plain launch when pdl == 0) */
+extern int g_ffb_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_ffb_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 } // namespace sm100
