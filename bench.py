@@ -240,6 +240,13 @@ def main():
                 if lt[i] > 0:
                     print("L%-3d %-16s %8.4f ms %8.1f GB/s  %5.1f%% of HBM peak" % (i, name, lt[i], by * B / (lt[i] * 1e-3) / 1e9,
                                                                                   100 * by * B / (lt[i] * 1e-3) / 1e9 / peak), file=sys.stderr)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+            if top in tj:
+                traffic = dict(tj[top])
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -254,7 +261,7 @@ def main():
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_share_of_step": tg["ms"] / total_ms, "layers_in_kernel": tg["layers"],
+                         "traffic": traffic["traffic"] if traffic else None, "traffic_of": traffic, "peak_source": peak_src, "kernel_share_of_step": tg["ms"] / total_ms, "layers_in_kernel": tg["layers"],
                          "whole_graph": {"achieved": ALG_BYTES_PER_FRAME * B * K / (ms * 1e-3) / 1e9 / 1, "frac": ALG_BYTES_PER_FRAME * B * K / (ms * 1e-3) / 1e9 / peak,
                                          "alg_bytes_per_frame": ALG_BYTES_PER_FRAME},
                          "by_kernel": {k: {"ms": round(v["ms"], 4), "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
