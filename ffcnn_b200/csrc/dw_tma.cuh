@@ -28,8 +28,9 @@ namespace ffb {
 constexpr int DW_THREADS = 384;
 
 struct DwArgs {
-    float *out; const float *wt, *scale, *bias;     /* wt: [9][C] tap-major */
-    int N, H, W, C;
+    float *out; const float *wt, *scale, *bias;     /* wt: [FS*FS][C] tap-major */
+    int N, H, W, C, OH, OW;                          /* input and output geometry (OH = H, OW = W for stride 1) */
+    int IWb, IHb, skip_row0_at;                      /* TMA box extent in pixels; conv-v6 5x5 quirk row (-1: none) */
     int CB, TW, TH, RC, nch;                         /* channel block, output tile, rows per work item, row chunks */
     int ntx, nty, ntc; long ntiles;
     int stages, act;
@@ -40,7 +41,7 @@ k_dw3s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
 {
     extern __shared__ uint8_t dw_smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
-    const int S = a.stages, IWb = 2 * ((a.TW + 1) / 2) + 2, IHb = a.TH + 2;   /* box width covers whole pixel pairs */
+    const int S = a.stages, IWb = a.IWb, IHb = a.IHb;            /* box = output tile (whole pixel pairs) + 1-pixel halo */
     const uint32_t stage_bytes = (uint32_t)IHb * IWb * a.CB * 4;
     const uint32_t stage_stride = (stage_bytes + 127) & ~127u;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_stride);
@@ -131,6 +132,194 @@ k_dw3s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
             }
         }
         __syncthreads();                                          /* everyone is done with stage s before it is refilled */
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Common prologue of the TMA-fed stencils: barrier ring, tile decode, TMA issue.  ORGX/ORGY map an output tile origin to
+ * the input box origin (stride * origin - pad).
+ * ---------------------------------------------------------------------------------------------------------------- */
+struct DwTile { int tc, tx, ty, n; };
+__device__ __forceinline__ DwTile dw_decode(long tile, const DwArgs &a)
+{
+    DwTile t; long r = tile;
+    t.tc = (int)(r % a.ntc); r /= a.ntc;
+    t.tx = (int)(r % a.ntx); r /= a.ntx;
+    t.ty = (int)(r % a.nty); t.n = (int)(r / a.nty);
+    return t;
+}
+
+/* Depthwise 3x3, stride 2, pad 1 (conv-v6.c:233-287).  Same structure as k_dw3s1_tma; the input box of an output tile
+ * TW x TH is (2*TW+1) x (2*TH+1) pixels starting at (2*x0-1, 2*y0-1).  A thread owns 2 adjacent output pixels x 4 channels
+ * x RC rows: per output row it loads two new 5-column input rows (the third is carried over from the row above). */
+__global__ void __launch_bounds__(DW_THREADS)
+k_dw3s2_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
+{
+    extern __shared__ uint8_t dw_smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
+    const int S = a.stages;
+    const uint32_t stage_bytes = (uint32_t)a.IHb * a.IWb * a.CB * 4;
+    const uint32_t stage_stride = (stage_bytes + 127) & ~127u;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_stride);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        sm100::tma_prefetch_desc(&tmIn);
+        for (int s = 0; s < S; s++) sm100::mbar_init(full + s, 1);
+        sm100::fence_barrier_init();
+    }
+    __syncthreads();
+    pdl_trigger(); pdl_wait();
+    auto issue = [&](long tile, int s) {
+        const DwTile t = dw_decode(tile, a);
+        sm100::mbar_arrive_expect_tx(full + s, stage_bytes);
+        sm100::tma_load_4d(smem + (size_t)s * stage_stride, &tmIn, t.tc * a.CB, 2 * t.tx * a.TW - 1, 2 * t.ty * a.TH - 1, t.n, full + s);
+    };
+    const long first = blockIdx.x, step = gridDim.x;
+    if (tid == 0)
+        for (int s = 0; s < S - 1; s++) if (first + s * step < a.ntiles) issue(first + s * step, s);
+
+    const int cb4 = a.CB / 4, pairs = (a.TW + 1) / 2, per_chunk = pairs * cb4;
+    const bool worker = tid < per_chunk * a.nch;
+    const int ch = tid / per_chunk, jj0 = tid - ch * per_chunk;
+    const int xp = jj0 / cb4, c = (jj0 - xp * cb4) * 4;
+    const int xl = 2 * xp;
+    const int yl0 = ch * a.RC, yl1_tile = min(a.TH, yl0 + a.RC);
+    const int srow = a.IWb * a.CB;
+    const int col_off = (2 * xl) * a.CB + c;                      /* input column 2*xl of box row 0 */
+    float4 wv[9], sc, bi; int wc0 = -1;
+
+    long it = 0;
+    for (long tile = first; tile < a.ntiles; tile += step, it++) {
+        const int s = (int)(it % S); const uint32_t ph = (uint32_t)((it / S) & 1);
+        if (tid == 0) { const long nx = tile + (long)(S - 1) * step; if (nx < a.ntiles) issue(nx, (int)((it + S - 1) % S)); }
+        const DwTile t = dw_decode(tile, a);
+        const int ox = t.tx * a.TW + xl, oy0 = t.ty * a.TH, c0 = t.tc * a.CB + c;
+        if (worker && c0 != wc0) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) wv[k] = ldg4(a.wt + k * a.C + c0);
+            sc = ldg4(a.scale + c0); bi = ldg4(a.bias + c0); wc0 = c0;
+        }
+        sm100::mbar_wait(full + s, ph);
+        if (worker && ox < a.OW) {
+            const float *col = reinterpret_cast<const float *>(smem + (size_t)s * stage_stride) + col_off;
+            const int yl1 = min(yl1_tile, a.OH - oy0);
+            const bool two = (xl + 1 < a.TW) && (ox + 1 < a.OW);
+            float *dst = a.out + (((long)t.n * a.OH + oy0) * a.OW + ox) * a.C + c0;
+            const long orow = (long)a.OW * a.C;
+            float4 top[5], mid[5], bot[5];
+            auto load_row = [&](float4 (&r)[5], int yrow) {
+                const float *rp = col + yrow * srow;
+#pragma unroll
+                for (int k = 0; k < 5; k++) r[k] = *reinterpret_cast<const float4 *>(rp + k * a.CB);
+            };
+            load_row(top, 2 * yl0);
+            for (int yl = yl0; yl < yl1; yl++) {
+                load_row(mid, 2 * yl + 1);
+                load_row(bot, 2 * yl + 2);
+                float4 acc0 = zero4(), acc1 = zero4();
+#pragma unroll
+                for (int k = 0; k < 3; k++) { fma4(acc0, top[k], wv[k]);     fma4(acc1, top[k + 2], wv[k]); }
+#pragma unroll
+                for (int k = 0; k < 3; k++) { fma4(acc0, mid[k], wv[3 + k]); fma4(acc1, mid[k + 2], wv[3 + k]); }
+#pragma unroll
+                for (int k = 0; k < 3; k++) { fma4(acc0, bot[k], wv[6 + k]); fma4(acc1, bot[k + 2], wv[6 + k]); }
+                float *o = dst + yl * orow;
+                *reinterpret_cast<float4 *>(o) = epilogue4(acc0, sc, bi, a.act);
+                if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4(acc1, sc, bi, a.act);
+#pragma unroll
+                for (int k = 0; k < 5; k++) top[k] = bot[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* Depthwise 5x5, stride 1, pad 2 (conv-v6.c:291-465).  25 weight vectors do not fit the register budget next to a 5-row
+ * window, so the loop is kernel-row outer: for each kernel row j the thread keeps that row's 5 weight vectors and adds
+ * its contribution to the RC x 2 output accumulators it owns (6 LDS.128 per output row and kernel row).  Accumulation
+ * order stays kernel-row -> kernel-column.  skip_row0_at: conv-v6 drops kernel row 0 on output row oh-2 (422-441). */
+constexpr int DW5_RC = 4;
+__global__ void __launch_bounds__(DW_THREADS)
+k_dw5s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
+{
+    extern __shared__ uint8_t dw_smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
+    const int S = a.stages;
+    const uint32_t stage_bytes = (uint32_t)a.IHb * a.IWb * a.CB * 4;
+    const uint32_t stage_stride = (stage_bytes + 127) & ~127u;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_stride);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        sm100::tma_prefetch_desc(&tmIn);
+        for (int s = 0; s < S; s++) sm100::mbar_init(full + s, 1);
+        sm100::fence_barrier_init();
+    }
+    __syncthreads();
+    pdl_trigger(); pdl_wait();
+    auto issue = [&](long tile, int s) {
+        const DwTile t = dw_decode(tile, a);
+        sm100::mbar_arrive_expect_tx(full + s, stage_bytes);
+        sm100::tma_load_4d(smem + (size_t)s * stage_stride, &tmIn, t.tc * a.CB, t.tx * a.TW - 2, t.ty * a.TH - 2, t.n, full + s);
+    };
+    const long first = blockIdx.x, step = gridDim.x;
+    if (tid == 0)
+        for (int s = 0; s < S - 1; s++) if (first + s * step < a.ntiles) issue(first + s * step, s);
+
+    const int cb4 = a.CB / 4, pairs = (a.TW + 1) / 2, per_chunk = pairs * cb4;
+    const bool worker = tid < per_chunk * a.nch;
+    const int ch = tid / per_chunk, jj0 = tid - ch * per_chunk;
+    const int xp = jj0 / cb4, c = (jj0 - xp * cb4) * 4;
+    const int xl = 2 * xp;
+    const int yl0 = ch * a.RC, yl1_tile = min(a.TH, yl0 + a.RC);   /* a.RC <= DW5_RC */
+    const int srow = a.IWb * a.CB;
+    const int col_off = xl * a.CB + c;
+
+    long it = 0;
+    for (long tile = first; tile < a.ntiles; tile += step, it++) {
+        const int s = (int)(it % S); const uint32_t ph = (uint32_t)((it / S) & 1);
+        if (tid == 0) { const long nx = tile + (long)(S - 1) * step; if (nx < a.ntiles) issue(nx, (int)((it + S - 1) % S)); }
+        const DwTile t = dw_decode(tile, a);
+        const int ox = t.tx * a.TW + xl, oy0 = t.ty * a.TH, c0 = t.tc * a.CB + c;
+        sm100::mbar_wait(full + s, ph);
+        if (worker && ox < a.W) {
+            const float *col = reinterpret_cast<const float *>(smem + (size_t)s * stage_stride) + col_off;
+            const int yl1 = min(yl1_tile, a.H - oy0);
+            const bool two = (xl + 1 < a.TW) && (ox + 1 < a.W);
+            float4 acc[DW5_RC][2];
+#pragma unroll
+            for (int r = 0; r < DW5_RC; r++) { acc[r][0] = zero4(); acc[r][1] = zero4(); }
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                float4 w[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) w[k] = ldg4(a.wt + (j * 5 + k) * a.C + c0);
+#pragma unroll
+                for (int r = 0; r < DW5_RC; r++) {
+                    const int yl = yl0 + r;
+                    if (yl < yl1 && !(j == 0 && oy0 + yl == a.skip_row0_at)) {
+                        const float *rp = col + (yl + j) * srow;
+                        float4 v[6];
+#pragma unroll
+                        for (int k = 0; k < 6; k++) v[k] = *reinterpret_cast<const float4 *>(rp + k * a.CB);
+#pragma unroll
+                        for (int k = 0; k < 5; k++) { fma4(acc[r][0], v[k], w[k]); fma4(acc[r][1], v[k + 1], w[k]); }
+                    }
+                }
+            }
+            const float4 sc = ldg4(a.scale + c0), bi = ldg4(a.bias + c0);
+            float *dst = a.out + (((long)t.n * a.H + oy0) * a.W + ox) * a.C + c0;
+            const long orow = (long)a.W * a.C;
+#pragma unroll
+            for (int r = 0; r < DW5_RC; r++) {
+                const int yl = yl0 + r;
+                if (yl < yl1) {
+                    float *o = dst + yl * orow;
+                    *reinterpret_cast<float4 *>(o) = epilogue4(acc[r][0], sc, bi, a.act);
+                    if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4(acc[r][1], sc, bi, a.act);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

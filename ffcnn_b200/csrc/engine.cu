@@ -110,13 +110,13 @@ static void pw_plan(ffb_conv *op)
     op->smem = pw_smem(K, op->fn_pad, op->TM, op->TY);
 }
 
-/* ---- TMA-fed depthwise 3x3 s1 kernel: tile planner + launcher ---- */
+/* ---- TMA-fed depthwise kernels (3x3 s1, 3x3 s2, 5x5 s1): tile planner + launcher ---- */
 struct DwPlan { int CB, TW, TH, RC, nch, IWb, IHb, ntx, nty, ntc, stages; size_t smem; };
 
-/* Pick channel block / tile / row chunking: one work item (2 px x 4 ch x RC rows) per thread, stage <= 108 KB (2 stages),
+/* Pick channel block / output tile / row chunking: one work item (2 px x 4 ch x RC rows) per thread, stage <= 108 KB (2 stages),
  * minimising  halo re-read factor x shared-memory reads per output, with penalties for idle threads and for thin TMA
- * rows when the channel block is not the whole (contiguous) pixel. */
-static bool dw_plan(int C, int OH, int OW, DwPlan *p)
+ * rows when the channel block is not the whole (contiguous) pixel.  FS/stride select the box geometry; max_rc caps RC. */
+static bool dw_plan(int C, int OH, int OW, int FS, int stride, int max_rc, DwPlan *p)
 {
     /* developer overrides for tile-shape sweeps (tools/op_bench.py): FFCNN_DW_STAGE_KB, FFCNN_DW_STAGES */
     static const int env_kb = getenv("FFCNN_DW_STAGE_KB") ? atoi(getenv("FFCNN_DW_STAGE_KB")) : 0;
@@ -127,25 +127,29 @@ static bool dw_plan(int C, int OH, int OW, DwPlan *p)
     for (int CB = 4; CB <= C && CB <= 256; CB += 4) {
         if (C % CB) continue;
         for (int ntx = 1; ntx <= 40 && ntx <= OW; ntx++) {
-            const int TW = (OW + ntx - 1) / ntx, pairs = (TW + 1) / 2, IWb = 2 * pairs + 2;
+            const int TW = (OW + ntx - 1) / ntx, pairs = (TW + 1) / 2, TWp = 2 * pairs;
+            const int IWb = (TWp - 1) * stride + FS;
             if (IWb > 256) continue;
             const int per_chunk = pairs * (CB / 4);
             if (per_chunk > DW_THREADS) continue;
             const size_t rowb = (size_t)IWb * CB * 4;
-            int thmax = (int)(stage_limit / rowb) - 2; if (thmax > OH) thmax = OH; if (thmax > 254) thmax = 254;
-            if (thmax < 1) continue;
+            int ihmax = (int)(stage_limit / rowb); if (ihmax > 256) ihmax = 256;
+            int thmax = (ihmax - FS) / stride + 1; if (thmax > OH) thmax = OH;
+            if (ihmax < FS || thmax < 1) continue;
             for (int nty = (OH + thmax - 1) / thmax; nty <= OH; nty++) {
-                const int TH = (OH + nty - 1) / nty;
+                const int TH = (OH + nty - 1) / nty, IHb = (TH - 1) * stride + FS;
                 int nch = DW_THREADS / per_chunk; if (nch > TH) nch = TH; if (nch < 1) nch = 1;
-                const int RC = (TH + nch - 1) / nch; nch = (TH + RC - 1) / RC;
-                const double halo = (double)IWb * (TH + 2) / ((double)TW * TH);
-                const double lds = 2.0 * (RC + 2) / RC;                       /* LDS.128 per output float4 */
+                int RC = (TH + nch - 1) / nch;
+                if (RC > max_rc) { RC = max_rc; if ((TH + RC - 1) / RC * per_chunk > DW_THREADS) continue; }
+                nch = (TH + RC - 1) / RC;
+                const double halo = (double)IWb * IHb / ((double)TW * stride * TH * stride);
+                const double lds = FS == 3 && stride == 1 ? 2.0 * (RC + 2) / RC : FS == 3 ? 5.0 * (2 * RC + 1) / (2.0 * RC) : 15.0;
                 const double idle = (double)DW_THREADS / (per_chunk * nch);
                 const double thin = (CB < C && CB * 4 < 256) ? 1.0 + 0.25 * (256.0 / (CB * 4) - 1.0) : 1.0;
-                const double score = (halo + 0.35 * lds) * (0.75 + 0.25 * idle) * thin;
+                const double score = (halo + 0.35 * lds / stride) * (0.75 + 0.25 * idle) * thin;
                 if (score < best) {
                     best = score; ok = true;
-                    p->CB = CB; p->TW = TW; p->TH = TH; p->RC = RC; p->nch = nch; p->IWb = IWb; p->IHb = TH + 2;
+                    p->CB = CB; p->TW = TW; p->TH = TH; p->RC = RC; p->nch = nch; p->IWb = IWb; p->IHb = IHb;
                     p->ntx = (OW + TW - 1) / TW; p->nty = nty; p->ntc = C / CB;
                 }
                 if (RC >= 12 || TH <= 4) break;                               /* shorter tiles only get worse from here */
@@ -159,12 +163,13 @@ static bool dw_plan(int C, int OH, int OW, DwPlan *p)
     return true;
 }
 
-static int dw_launch(const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t st)
+typedef void (*DwKernel)(const CUtensorMap, const DwArgs);
+
+static int dw_launch(DwKernel kernel, size_t *configured, const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t st)
 {
-    static size_t configured = 0;
-    if (pl.smem > configured) {
-        if (cudaFuncSetAttribute(k_dw3s1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) { ffb_set_error("dw_tma: cannot set smem %zu", pl.smem); return -1; }
-        configured = pl.smem;
+    if (pl.smem > *configured) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) { ffb_set_error("dw_tma: cannot set smem %zu", pl.smem); return -1; }
+        *configured = pl.smem;
     }
     CUtensorMap tm;
     const unsigned long long dims[4] = { (unsigned long long)a.C, (unsigned long long)a.W, (unsigned long long)a.H, (unsigned long long)a.N };
@@ -172,9 +177,10 @@ static int dw_launch(const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t 
     const unsigned box[4] = { (unsigned)pl.CB, (unsigned)pl.IWb, (unsigned)pl.IHb, 1u };
     if (ffb_make_tensor_map(&tm, in, 4, dims, strides, box, 0) != 0) return -1;
     a.CB = pl.CB; a.TW = pl.TW; a.TH = pl.TH; a.RC = pl.RC; a.nch = pl.nch; a.ntx = pl.ntx; a.nty = pl.nty; a.ntc = pl.ntc;
+    a.IWb = pl.IWb; a.IHb = pl.IHb;
     a.ntiles = (long)a.N * pl.nty * pl.ntx * pl.ntc; a.stages = pl.stages;
     const int grid = (int)std::min<long>(a.ntiles, g_num_sms);
-    CK(launch_pdl(k_dw3s1_tma, dim3(grid), dim3(DW_THREADS), pl.smem, st, tm, a));
+    CK(launch_pdl(kernel, dim3(grid), dim3(DW_THREADS), pl.smem, st, tm, a));
     return 0;
 }
 
@@ -278,12 +284,13 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
         CK(e);
         return 0; }
     case CK_DW_S1_3: case CK_DW_S1_5: case CK_DW3_S2:
-        if (op->dw_mode == 0 && kind == CK_DW_S1_3) {
-            DwPlan pl;
-            if (dw_plan(op->ic, oh, ow, &pl)) {
-                DwArgs a; a.out = out; a.wt = wt; a.scale = sc; a.bias = bi; a.N = n; a.H = ih; a.W = iw; a.C = op->ic; a.act = op->act;
-                return dw_launch(in, a, pl, st);
-            }
+        if (op->dw_mode == 0) {
+            DwPlan pl; static size_t cfg_s1 = 0, cfg_s2 = 0, cfg_5 = 0;
+            DwArgs a; a.out = out; a.wt = wt; a.scale = sc; a.bias = bi; a.N = n; a.H = ih; a.W = iw; a.C = op->ic; a.OH = oh; a.OW = ow;
+            a.act = op->act; a.skip_row0_at = skip;
+            if (kind == CK_DW_S1_3 && dw_plan(op->ic, oh, ow, 3, 1, 1 << 20, &pl)) return dw_launch(k_dw3s1_tma, &cfg_s1, in, a, pl, st);
+            if (kind == CK_DW3_S2 && dw_plan(op->ic, oh, ow, 3, 2, 1 << 20, &pl)) return dw_launch(k_dw3s2_tma, &cfg_s2, in, a, pl, st);
+            if (kind == CK_DW_S1_5 && dw_plan(op->ic, oh, ow, 5, 1, DW5_RC, &pl)) return dw_launch(k_dw5s1_tma, &cfg_5, in, a, pl, st);
         }
         if (kind == CK_DW3_S2) {
             const int R = oh >= 40 ? 10 : oh;

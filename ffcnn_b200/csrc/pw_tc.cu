@@ -28,6 +28,7 @@
  */
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "pw_tc.h"
@@ -100,6 +101,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TRACE(5, 1, 0);
     const int slice = blockIdx.x % a.nsl, group = blockIdx.x / a.nsl, ngroups = gridDim.x / a.nsl;
 
     if (warp == 0 && elect_one()) {
@@ -122,6 +124,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     __syncthreads();
     tc_fence_after_sync();
     pdl_trigger(); pdl_wait();             /* from here on the kernel touches the previous layer's output */
+    if (threadIdx.x == 0) TRACE(5, 1, 1);
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_col0 = 0, alo_col0 = 2 * NS;
 
@@ -296,6 +299,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 
     tc_fence_before_sync();
     __syncthreads();
+    if (threadIdx.x == 0) TRACE(5, 1, 2);
     if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, a.tmem_cols); }
 }
 

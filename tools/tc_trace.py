@@ -23,7 +23,8 @@ L.ffb_tc_set_trace(None)
 t = buf.cpu().numpy().reshape(6, 64, 4)
 t0 = t[t > 0].min()
 names = ["producer: empty-ok", "mma: A-ready, acc-free, committed", "split: enter, landed, done", "epilogue: enter, acc-ready, done"]
-for it in range(3, 14):
+print("kernel entry %d, setup done %d, all roles done %d (cycles, CTA 0)" % tuple(int(v - t0) if v else -1 for v in t[5, 1, :3]))
+for it in list(range(0, 3)) + list(range(3, 8)):
     row = []
     for r in range(4):
         row.append(" ".join("%6d" % (v - t0) if v else "     -" for v in t[r, it, :3]))
