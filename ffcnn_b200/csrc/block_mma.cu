@@ -1,0 +1,183 @@
+/*
+ * block_mma.cu -- planner, weight preparation and launcher of the fused inverted-residual block kernel
+ * (block_mma.cuh).  The kernel is instantiated for the channel/stride combinations of yolo-fastest-1.1
+ * (KS1 = ceil(cin/8), NT3 = ceil(cout/8)); other combinations report "unsupported" and the engine keeps
+ * the three separate layers.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "block_mma.h"
+#include "pw_tc.h"
+#include "block_mma.cuh"
+
+extern "C" void ffb_set_error(const char *fmt, ...);
+
+using namespace ffb;
+
+struct BlkPlan {
+    int cin, cexp, cout, S, H, W, OH, OW, res;
+    int KS1, NT3, MTW, MINB, G, GC, NC, TH, TW, HH, HW, SEs, xrows, chunk_floats, occ;
+    int XH, XW, xo, yo, frame;
+    float slope1, sloped, slope3, slope_res;
+    size_t smem;
+    float *d_chunks, *d_sb3;
+    int row1, rowd, row3;
+    int num_sms;
+    char desc[96];
+};
+
+typedef void (*BlkKernel)(const CUtensorMap, const BlkArgs);
+struct BlkInst { int KS1, NT3, S, MTW, GC, MINB; BlkKernel fn; size_t configured; };
+
+#define INST(K, N, S, M, G, B) { K, N, S, M, G, B, k_block_mma<K, N, S, M, G, B>, 0 }
+#define INST3(K, N, S, G) INST(K, N, S, 1, G, 2), INST(K, N, S, 2, G, 2), INST(K, N, S, 4, G, 2)
+#define INST2(K, N, S, G) INST(K, N, S, 1, G, 2), INST(K, N, S, 2, G, 2)
+static BlkInst g_inst[] = {
+    INST3(1, 1, 1, 1), INST3(1, 1, 1, 2), INST3(1, 1, 1, 3),      /* 8->8->4, 4->8->4, 8->32->8, 8->48->8 */
+    INST3(1, 1, 2, 1), INST3(1, 1, 2, 2),                         /* 4->24->8 s2, 8->32->8 s2 */
+    INST3(1, 2, 1, 1), INST3(1, 2, 1, 3),                         /* 8->48->16 */
+    INST3(2, 2, 1, 1), INST3(2, 2, 1, 2), INST3(2, 2, 1, 3),      /* 16->96->16 */
+    INST2(2, 3, 2, 1), INST2(2, 3, 2, 2), INST2(2, 3, 2, 3),      /* 16->96->24 s2 */
+    INST2(3, 3, 1, 1), INST2(3, 3, 1, 3),                         /* 24->136->24 */
+    INST2(3, 6, 2, 1), INST2(3, 6, 2, 3),                         /* 24->136->48 s2 */
+    INST2(6, 6, 1, 1), INST2(6, 6, 1, 2),                         /* 48->224->48 */
+};
+#undef INST3
+#undef INST2
+#undef INST
+
+static BlkInst *find_inst(int KS1, int NT3, int S, int MTW, int GC)      /* MTW / GC == 0: any */
+{
+    for (BlkInst &i : g_inst) if (i.KS1 == KS1 && i.NT3 == NT3 && i.S == S && (!MTW || i.MTW == MTW) && (!GC || i.GC == GC)) return &i;
+    return nullptr;
+}
+
+static float slope_of(int act) { return act == 2 ? 0.1f : act == 1 ? 0.f : 1.f; }
+
+/* Tile search: minimise an estimate of SM cycles per output pixel (tensor pipe: 2.14 clk per m16n8k8 on the SM, measured
+ * with tools/micro/mma_sync.cu; FFMA/issue work of the depthwise stage; barrier and tile-start latencies), subject to
+ * the shared-memory budget.  FFCNN_BLK_TILE_<OH>="TH,TW,GC" overrides the choice for blocks with that output height. */
+static bool plan_tile(BlkPlan *p)
+{
+    const int S = p->S, KS1 = p->KS1, NT3 = p->NT3, G = p->G, SXs = 8 * KS1 + 4;
+    int fTH = 0, fTW = 0, fGC = 0;
+    char key[48]; snprintf(key, sizeof key, "FFCNN_BLK_TILE_%d", p->OH);
+    if (const char *ov = getenv(key)) sscanf(ov, "%d,%d,%d", &fTH, &fTW, &fGC);
+    double best = 1e30; bool ok = false;
+    for (int GC = 1; GC <= G && GC <= 4; GC++) {
+        if (G % GC || (fGC && GC != fGC)) continue;
+        const int NC = G / GC, SEs = 16 * GC + (S == 1 ? 8 : 4);
+        const BlkChunk off(GC, KS1, NT3);
+        for (int TW = 2; TW <= p->OW && TW <= 80; TW += 2) {
+            if (fTW && TW != fTW) continue;
+            for (int TH = 1; TH <= p->OH && TH <= 80; TH++) {
+                if (fTH && TH != fTH) continue;
+                const int M3 = (TH * TW + 15) / 16, MTW = (M3 + BLK_WARPS - 1) / BLK_WARPS;
+                const BlkInst *inst = find_inst(KS1, NT3, S, MTW, GC);
+                if (!inst) continue;
+                const int HH = (TH - 1) * S + 3, HW = (TW - 1) * S + 3;
+                const bool frame = TH >= p->OH && TW >= p->OW;        /* the halo ring is all padding: fetch / expand the image only */
+                const int XH = frame ? p->H : HH, XW = frame ? p->W : HW;
+                if (XH > 256 || XW > 256) continue;
+                const int M1 = (XH * XW + 15) / 16, xrows = 32 * ((M1 + 1) / 2);
+                const size_t smem = 4 * (size_t)(128 + 2 * xrows + 2 * off.total + 3 * xrows * SXs + HH * HW * SEs) + 128;
+                if (smem > 225 * 1024) continue;
+                int occ = (int)((228 * 1024) / (smem + 1024)); if (occ > inst->MINB) occ = inst->MINB; if (occ < 1) occ = 1;
+                const double rounds_e = (double)(((M1 + 1) / 2 * GC + BLK_WARPS - 1) / BLK_WARPS) / GC;   /* work item = (m-tile pair, group) */
+                const double t_mma = 2.14 * (rounds_e * BLK_WARPS * 2 * G * KS1 * 6 + (double)MTW * BLK_WARPS * G * 6 * NT3);
+                const double t_alu = ((double)MTW * BLK_WARPS * G * (S == 1 ? 190 : 205) + rounds_e * BLK_WARPS * G * (30 + 28 * KS1)) / 4;
+                const double t_fix = NC * 2 * 160.0 + 2500.0;
+                const double t_tile = occ >= 2 ? std::max(t_mma, t_alu) + 0.35 * std::min(t_mma, t_alu) + 0.5 * t_fix : t_mma + t_alu + t_fix;
+                const double waste = (double)((p->OH + TH - 1) / TH * TH) * ((p->OW + TW - 1) / TW * TW) / ((double)p->OH * p->OW);
+                /* tiles per SM: few, big tiles quantise badly when a frame is one or two tiles */
+                const double score = t_tile / (TH * TW) * waste;
+                if (score < best) {
+                    best = score; ok = true;
+                    p->GC = GC; p->NC = NC; p->SEs = SEs; p->TH = TH; p->TW = TW; p->HH = HH; p->HW = HW; p->MTW = MTW; p->MINB = inst->MINB;
+                    p->xrows = xrows; p->chunk_floats = off.total; p->smem = smem; p->occ = occ;
+                    p->XH = XH; p->XW = XW; p->frame = frame; p->xo = p->yo = frame ? 1 : 0;
+                }
+            }
+        }
+    }
+    return ok;
+}
+
+BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, int act1, int actd, int act3, int res, int act_res)
+{
+    if (cin < 1 || cexp < 1 || cout < 1 || cin % 4 || cexp % 4 || cout % 2 || (stride != 1 && stride != 2)) return nullptr;
+    if (res && (stride != 1 || cin != cout)) return nullptr;
+    BlkPlan *p = new BlkPlan(); memset(p, 0, sizeof *p);
+    p->cin = cin; p->cexp = cexp; p->cout = cout; p->S = stride; p->H = h; p->W = w; p->res = res;
+    p->OH = (h - 3 + 2) / stride + 1; p->OW = (w - 3 + 2) / stride + 1;
+    if (p->OW % 2 || p->OH < 1) { delete p; return nullptr; }
+    p->KS1 = (cin + 7) / 8; p->NT3 = (cout + 7) / 8; p->G = (cexp + 15) / 16;
+    /* round up to an instantiated (KS1, NT3) pair: zero-padded K / N lanes cost tensor work, not correctness */
+    bool found = false;
+    for (int k = p->KS1; k <= 6 && !found; k++)
+        for (int n = p->NT3; n <= 6 && !found; n++)
+            if (find_inst(k, n, stride, 0, 0)) { p->KS1 = k; p->NT3 = n; found = true; }
+    if (!found) { delete p; return nullptr; }
+    p->slope1 = slope_of(act1); p->sloped = slope_of(actd); p->slope3 = slope_of(act3); p->slope_res = slope_of(act_res);
+    p->row1 = ((cin + 3) & ~3) + 4; p->rowd = 16; p->row3 = ((cexp + 3) & ~3) + 4;
+    if (!plan_tile(p)) { delete p; return nullptr; }
+    int dev = 0; cudaDeviceProp prop;
+    cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
+    p->num_sms = prop.multiProcessorCount;
+    snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s tile %dx%d%s gc%d mtw%d smem %zuKB occ%d", cin, cexp, cout, stride, res ? "+res" : "",
+             p->TH, p->TW, p->frame ? " (frame)" : "", p->GC, p->MTW, p->smem >> 10, p->occ);
+    return p;
+}
+
+void blk_plan_destroy(BlkPlan *p)
+{
+    if (!p) return;
+    cudaFree(p->d_chunks); cudaFree(p->d_sb3);
+    delete p;
+}
+
+const char *blk_describe(const BlkPlan *p) { return p ? p->desc : ""; }
+
+int blk_prepare(BlkPlan *p, const float *p1, const float *pd, const float *p3, cudaStream_t st)
+{
+    const size_t nfl = (size_t)p->NC * p->chunk_floats;
+    if (!p->d_chunks && (cudaMalloc(&p->d_chunks, nfl * sizeof(float)) != cudaSuccess || cudaMalloc(&p->d_sb3, 16 * p->NT3 * sizeof(float)) != cudaSuccess)) {
+        ffb_set_error("block_mma: cudaMalloc failed"); return -1;
+    }
+    k_prep_block<<<(int)((nfl + 16 * p->NT3 + 255) / 256), 256, 0, st>>>(p1, p->row1, p->cin, pd, p->rowd, p3, p->row3, p->cexp, p->cout,
+                                                                         p->KS1, p->NT3, p->GC, p->NC, p->d_chunks, p->d_sb3);
+    if (cudaGetLastError() != cudaSuccess) { ffb_set_error("block_mma: weight preparation launch failed"); return -1; }
+    return 0;
+}
+
+int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st)
+{
+    BlkInst *inst = find_inst(p->KS1, p->NT3, p->S, p->MTW, p->GC);
+    if (!inst) { ffb_set_error("block_mma: no kernel instance"); return -1; }
+    if (p->smem > inst->configured) {
+        if (cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess) { ffb_set_error("block_mma: cannot set smem %zu", p->smem); return -1; }
+        inst->configured = p->smem;
+    }
+    BlkArgs a;
+    a.x = x; a.y = y; a.wchunks = p->d_chunks; a.sb3 = p->d_sb3;
+    a.N = n; a.H = p->H; a.W = p->W; a.OH = p->OH; a.OW = p->OW; a.ldx = ldx; a.ldy = ldy; a.cout = p->cout;
+    a.TH = p->TH; a.TW = p->TW; a.HH = p->HH; a.HW = p->HW; a.ntx = (p->OW + p->TW - 1) / p->TW; a.nty = (p->OH + p->TH - 1) / p->TH;
+    a.ntiles = (long)n * a.ntx * a.nty;
+    a.NC = p->NC; a.xrows = p->xrows;
+    a.XH = p->XH; a.XW = p->XW; a.xo = p->xo; a.yo = p->yo; a.frame = p->frame;
+    a.inv_tpf = 1.0f / (float)(a.ntx * a.nty); a.inv_ntx = 1.0f / (float)a.ntx;
+    CUtensorMap tm;
+    const int SXs = 8 * p->KS1 + 4;
+    const unsigned long long dims[4] = { (unsigned long long)ldx, (unsigned long long)p->W, (unsigned long long)p->H, (unsigned long long)n };
+    const unsigned long long strides[3] = { (unsigned long long)ldx * 4, (unsigned long long)p->W * ldx * 4, (unsigned long long)p->H * p->W * ldx * 4 };
+    const unsigned box[4] = { (unsigned)SXs, (unsigned)p->XW, (unsigned)p->XH, 1u };
+    if (ffb_make_tensor_map(&tm, x, 4, dims, strides, box, 0) != 0) return -1;
+    a.slope1 = p->slope1; a.sloped = p->sloped; a.slope3 = p->slope3; a.slope_res = p->slope_res; a.res = p->res;
+    const int grid = (int)std::min<long>(a.ntiles, (long)p->num_sms * p->occ);
+    cudaError_t e = sm100::launch_pdl(inst->fn, dim3(grid), dim3(BLK_THREADS), p->smem, st, tm, a);
+    if (e != cudaSuccess) { ffb_set_error("block_mma launch failed: %s (grid %d smem %zu)", cudaGetErrorString(e), grid, p->smem); return -1; }
+    return 0;
+}

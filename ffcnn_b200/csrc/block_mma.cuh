@@ -1,0 +1,437 @@
+/*
+ * block_mma.cuh -- one kernel per inverted-residual block of the graph (block fusion):
+ *
+ *     x --1x1 expand, BN, act--> e --3x3 depthwise (stride 1|2), BN, act--> d --1x1 project, BN, act--> [+ x] --> y
+ *
+ * i.e. three groupconv calls (conv-v6.c:46-91, 96-287) plus the optional dropout/shortcut pair (ffcnn.c:412-423) that
+ * net_forward (ffcnn.c:476-520) runs as separate layers.  Unfused, the expanded tensors e and d (6x the channels of x
+ * and y) make four trips through HBM; here they never leave the SM: a CTA owns a TH x TW tile of output pixels of one
+ * frame, keeps x's halo tile in shared memory, and walks the expanded channels in chunks of 16*GC:
+ *
+ *   stage A (expand)   E[halo px][chunk] = act(s1 * (X . W1^T) + b1)  on the tensor cores (mma.sync m16n8k8 tf32,
+ *                      3xTF32 split, fp32 accumulate), written to shared memory; pixels outside the image are never
+ *                      computed -- their rows stay zero, which is exactly the depthwise conv's zero padding
+ *   stage B (dw+proj)  every lane computes the 3x3 depthwise outputs of 2 pixels x 4 channels from shared memory
+ *                      (FFMA, tap order ky,kx as conv-v0.c:16-25), applies BN+act, and the results ARE the A fragments
+ *                      of the projection GEMM (rows = pixels, K = expanded channels): they are split hi/lo in
+ *                      registers and multiplied into per-warp accumulators that persist across chunks
+ *   epilogue           act(s3 * acc + b3) [+ x from the shared-memory tile, act] -> float2 stores
+ *
+ * Weights travel pre-arranged in fragment order ("chunks", built once by k_prep_block) and stream through a
+ * double-buffered cp.async ring, so shared memory holds one chunk of E, not the whole expanded tile: 60-110 KB per CTA,
+ * two CTAs per SM, one in its tensor-heavy stage while the other runs FFMAs.
+ *
+ * The fragment <-> tensor index maps are free permutations of M (pixels), N and K (channels); they are chosen so that
+ * every shared-memory access is a conflict-free 64/128-bit access:
+ *   expand   A row g   <-> tile pixel 2g,  row g+8 <-> pixel 2g+1;  k col t <-> cin 8ks+2t, col t+4 <-> cin 8ks+2t+1
+ *            n-tile pair (2 x 8 cols) <-> 16 channels: col 2t'+j of tile ntl <-> channel 4t' + 2ntl + j
+ *   project  A row g/g+8 <-> output pixels (ty, tx), (ty, tx+1);  k-step kk col t <-> channel 4t+2kk, col t+4 <-> 4t+2kk+1
+ *
+ * Numerics: 3xTF32 with a rounded split (hi = rna_tf32(x), lo = x - hi exact; D = lo*hi' + hi*lo' + hi*hi'), the same
+ * scheme as pw_tc.cu -- fp32-equivalent (see DESIGN.md "Numerics of the tensor-core path").
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cuda.h>
+#include "sm100.cuh"
+
+namespace ffb {
+
+using sm100::pdl_trigger;
+using sm100::pdl_wait;
+
+__device__ __forceinline__ void blk_fma4(float4 &acc, const float4 v, const float4 w)
+{
+    acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y);
+    acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
+}
+__device__ __forceinline__ float4 blk_zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+constexpr int BLK_THREADS = 256;
+constexpr int BLK_WARPS = BLK_THREADS / 32;
+
+struct BlkArgs {
+    const float *x; float *y;
+    const float *wchunks;                 /* [NC][chunk_floats], fragment order (k_prep_block) */
+    const float *sb3;                     /* [2][8*NT3] projection scale, bias (zero padded) */
+    int N, H, W, OH, OW, ldx, ldy, cout;
+    int TH, TW, HH, HW, ntx, nty; long ntiles;
+    int NC, xrows;
+    int XH, XW, xo, yo, frame;            /* x-tile box and its offset inside the halo; frame: one tile covers the whole image */
+    float inv_tpf, inv_ntx;
+    float slope1, sloped, slope3, slope_res; int res;
+};
+
+/* per-chunk section offsets (floats) */
+struct BlkChunk {
+    int w1, s1, b1, wd, sd, bd, w2, total;
+    __host__ __device__ constexpr BlkChunk(int GC, int KS1, int NT3)
+        : w1(0), s1(GC * 2 * KS1 * 128), b1(s1 + GC * 16), wd(b1 + GC * 16), sd(wd + GC * 144), bd(sd + GC * 16),
+          w2(bd + GC * 16), total(w2 + GC * 2 * NT3 * 128) {}
+};
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+/* x = hi + lo, hi = x rounded to nearest tf32 (two integer ops), lo exact */
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+
+/* activation with negative-side slope in [0, 1] (leaky 0.1, relu 0, linear 1; utils.h:15-23): max(v, slope*v) */
+__device__ __forceinline__ float slope_act(float v, float slope) { return fmaxf(v, v * slope); }
+__device__ __forceinline__ float4 bn_act4(float4 a, float4 s, float4 b, float slope)
+{
+    float4 r;
+    r.x = slope_act(fmaf(a.x, s.x, b.x), slope); r.y = slope_act(fmaf(a.y, s.y, b.y), slope);
+    r.z = slope_act(fmaf(a.z, s.z, b.z), slope); r.w = slope_act(fmaf(a.w, s.w, b.w), slope);
+    return r;
+}
+
+/* 1-D bulk copy global -> shared, completion (bytes) on an mbarrier; size multiple of 16, both addresses 16-byte aligned */
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(sm100::smem_u32(bar)) : "memory");
+}
+
+struct BlkTile { int n, oy0, ox0, th, tw, iy0, ix0; };
+
+template <int S>
+__device__ __forceinline__ BlkTile blk_tile(const BlkArgs &a, long tile)
+{
+    BlkTile g;
+    const int tiles_per_frame = a.ntx * a.nty;
+    g.n = (int)(((float)tile + 0.5f) * a.inv_tpf);                        /* exact: tile < 2^22, |error| << 0.5 / tiles_per_frame */
+    const int tr = (int)(tile - (long)g.n * tiles_per_frame), tyi = (int)(((float)tr + 0.5f) * a.inv_ntx), txi = tr - tyi * a.ntx;
+    g.oy0 = tyi * a.TH; g.ox0 = txi * a.TW;
+    g.th = min(a.TH, a.OH - g.oy0); g.tw = min(a.TW, a.OW - g.ox0);
+    g.iy0 = g.oy0 * S - 1; g.ix0 = g.ox0 * S - 1;                        /* image coordinates of halo pixel (0,0) */
+    return g;
+}
+
+/*
+ * Shared-memory x tile = one TMA box [XH][XW][SXs] of the NHWC tensor at (ix0 + xo, iy0 + yo): out-of-image pixels and the
+ * channel lanes beyond the tensor's (box wider than the tensor) arrive as zeros, which gives the padded, bank-conflict-free
+ * pixel stride SXs = 8*KS1 + 4 for free.  Normally the box is the whole halo (xo = yo = 0); when one tile covers the whole
+ * image ("frame mode") the halo ring lies entirely outside the image, the box is just the image (xo = yo = 1) and the ring
+ * rows of E are cleared once per kernel.  Once landed, the tile is split in place into tf32 hi (same buffer) and lo (sXl).
+ */
+template <int KS1, int NT3, int S, int MTW, int GC, int MINB>
+__global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_constant__ CUtensorMap tmX, const BlkArgs a)
+{
+    extern __shared__ __align__(128) float4 blk_smem4[];
+    float *smem = reinterpret_cast<float *>(blk_smem4);
+    constexpr int CIN_P = 8 * KS1, SXs = CIN_P + 4, COUT_P = 8 * NT3, XV = CIN_P / 4;
+    constexpr int SEs = 16 * GC + (S == 1 ? 8 : 4);       /* E pixel stride (floats): conflict-free 128-bit stencil loads */
+    constexpr int MH = MTW > 2 ? 2 : MTW;                 /* m-tiles whose A fragments are live at once in stage B */
+    constexpr BlkChunk off(GC, KS1, NT3);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int HW = a.HW;
+    float    *sSB3 = smem;                                          /* 96 floats */
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 96);       /* full_x[2], full_w[2] */
+    int2     *sMap = reinterpret_cast<int2 *>(smem + 128);          /* [xrows]: x-tile pixel -> { byte offset of its E row or -1, hy | hx << 16 } */
+    float    *sW = smem + 128 + 2 * a.xrows;
+    float    *sXB = sW + 2 * off.total;                             /* [2][xrows * SXs]: hi after the split pass */
+    float    *sXl = sXB + 2 * a.xrows * SXs;                        /* [xrows * SXs]: lo of the current tile */
+    float    *sE = sXl + a.xrows * SXs;
+    uint64_t *full_x = bars, *full_w = bars + 2;
+    const uint32_t sE_addr = sm100::smem_u32(sE), sW_addr = sm100::smem_u32(sW);
+    const uint32_t x_bytes = (uint32_t)a.XH * a.XW * SXs * 4;
+    constexpr uint32_t w_bytes = (uint32_t)off.total * 4;
+    const int XP = a.XH * a.XW, npairs = (((XP + 15) >> 4) + 1) >> 1, M3 = (a.TH * a.TW + 15) >> 4;
+
+    if (tid == 0) {
+        sm100::tma_prefetch_desc(&tmX);
+        for (int i = 0; i < 4; i++) sm100::mbar_init(bars + i, 1);
+        sm100::fence_barrier_init();
+    }
+    if (tid < 2 * COUT_P) sSB3[tid] = a.sb3[tid];
+    for (int xp = tid; xp < a.xrows; xp += BLK_THREADS) {
+        const int ry = xp / a.XW, rx = xp - ry * a.XW, hy = ry + a.yo, hx = rx + a.xo;
+        sMap[xp] = make_int2(xp < XP ? (hy * HW + hx) * SEs * 4 : -1, hy | (hx << 16));
+    }
+    for (int i = tid; i < a.HH * HW * SEs / 4; i += BLK_THREADS) reinterpret_cast<float4 *>(sE)[i] = blk_zero4();
+    /* tile-independent lane geometry: this lane's two output pixels (ty, tx), (ty, tx+1) of every m-tile its warp owns */
+    uint32_t dwrow[MTW][3]; int tyx[MTW];
+#pragma unroll
+    for (int mi = 0; mi < MTW; mi++) {
+        const int qq = (warp + BLK_WARPS * mi) * 16 + 2 * g, qc = min(qq, a.TH * a.TW - 2);
+        const int ty = qc / a.TW, tx = qc - ty * a.TW;
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) dwrow[mi][dy] = sE_addr + (uint32_t)(((ty * S + dy) * HW + tx * S) * SEs + 4 * t) * 4;
+        tyx[mi] = qq < a.TH * a.TW ? (ty << 16 | tx) : (0x7fff << 16);          /* invalid rows fail the ty < th test */
+    }
+    const int nmi = warp < M3 ? (M3 - warp + BLK_WARPS - 1) / BLK_WARPS : 0;    /* m-tiles this warp owns (warp-uniform) */
+    constexpr int step_pair = BLK_WARPS / GC, step_grp = BLK_WARPS - step_pair * GC;
+    __syncthreads();
+    pdl_trigger(); pdl_wait();
+
+    auto load_x = [&](long tile, int b) {                                       /* one thread */
+        const BlkTile q = blk_tile<S>(a, tile);
+        sm100::fence_proxy_async_smem();                  /* the split pass wrote this buffer through the generic proxy */
+        sm100::mbar_arrive_expect_tx(full_x + b, x_bytes);
+        sm100::tma_load_4d(sXB + b * a.xrows * SXs, &tmX, 0, q.ix0 + a.xo, q.iy0 + a.yo, q.n, full_x + b);
+    };
+    auto load_chunk = [&](int c, int wb) {                                      /* one thread */
+        sm100::mbar_arrive_expect_tx(full_w + wb, w_bytes);
+        bulk_load(sW_addr + (uint32_t)wb * w_bytes, a.wchunks + (long)c * off.total, w_bytes, full_w + wb);
+    };
+    if (tid == 0 && (long)blockIdx.x < a.ntiles) { load_x(blockIdx.x, 0); load_chunk(0, 0); }
+    /* weights: with a single chunk they stay resident for the whole kernel; otherwise the two-slot ring runs continuously
+       across tiles (chunk (c+1) % NC is requested while chunk c is being used), so no tile ever waits for L2 */
+    const bool w_resident = a.NC == 1;
+    uint32_t it = 0, cs = 0;                                                    /* tiles / weight chunks consumed so far by this CTA */
+    for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+        const BlkTile q = blk_tile<S>(a, tile);
+        const int xb = it & 1;
+        float *sX = sXB + xb * a.xrows * SXs;
+        const bool border = !a.frame && (q.iy0 < 0 || q.ix0 < 0 || q.iy0 + a.HH > a.H || q.ix0 + HW > a.W);
+
+        __syncthreads();                                  /* the previous tile no longer reads sW / sE / sXl / the other x buffer */
+        const bool last_tile = tile + gridDim.x >= a.ntiles;
+        if (tid == 0 && !last_tile) load_x(tile + gridDim.x, xb ^ 1);
+        float pacc[MTW][NT3][4];
+#pragma unroll
+        for (int mi = 0; mi < MTW; mi++)
+#pragma unroll
+            for (int nt = 0; nt < NT3; nt++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) pacc[mi][nt][j] = 0.f;
+        sm100::mbar_wait(full_x + xb, (it >> 1) & 1);
+        /* split pass: x -> hi (in place) + lo, once per tile instead of once per use */
+        for (int i = tid; i < XP * XV; i += BLK_THREADS) {
+            const int xp = i / XV, c4 = i - xp * XV;
+            float4 *ph = reinterpret_cast<float4 *>(sX + xp * SXs + c4 * 4), *pl = reinterpret_cast<float4 *>(sXl + xp * SXs + c4 * 4);
+            const float4 v = *ph; float4 h, l; uint32_t hh, ll;
+            split_tf32(v.x, hh, ll); h.x = __uint_as_float(hh); l.x = __uint_as_float(ll);
+            split_tf32(v.y, hh, ll); h.y = __uint_as_float(hh); l.y = __uint_as_float(ll);
+            split_tf32(v.z, hh, ll); h.z = __uint_as_float(hh); l.z = __uint_as_float(ll);
+            split_tf32(v.w, hh, ll); h.w = __uint_as_float(hh); l.w = __uint_as_float(ll);
+            *ph = h; *pl = l;
+        }
+
+        for (int c = 0; c < a.NC; c++, cs++) {
+            const int wb = w_resident ? 0 : cs & 1;
+            sm100::mbar_wait(full_w + wb, w_resident ? 0 : (cs >> 1) & 1);
+            __syncthreads();                              /* split pass visible (c == 0) / every warp done with chunk c-1: E and the other weight buffer are free */
+            if (tid == 0 && !w_resident && !(last_tile && c + 1 == a.NC)) load_chunk(c + 1 < a.NC ? c + 1 : 0, wb ^ 1);
+            const float *wc = sW + wb * off.total;
+            const float *wl4 = wc + lane * 4, *wt4 = wc + 4 * t;
+
+            /* ---------------- stage A: expand GEMM; work item = (pair of m-tiles, 16-channel group) ---------------- */
+            {
+                int pair = warp / GC, grp = warp - pair * GC;
+                while (pair < npairs) {
+                    const int mt0 = pair * 2;
+                    float acc[2][2][4];
+#pragma unroll
+                    for (int m = 0; m < 2; m++)
+#pragma unroll
+                        for (int ntl = 0; ntl < 2; ntl++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[m][ntl][j] = 0.f;
+                    const int xoff = (mt0 * 16 + 2 * g) * SXs + 2 * t;
+#pragma unroll
+                    for (int ks = 0; ks < KS1; ks++) {
+                        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                        for (int m = 0; m < 2; m++) {
+                            const float2 h0 = *reinterpret_cast<const float2 *>(sX + xoff + m * 16 * SXs + 8 * ks), h1 = *reinterpret_cast<const float2 *>(sX + xoff + m * 16 * SXs + SXs + 8 * ks);
+                            const float2 l0 = *reinterpret_cast<const float2 *>(sXl + xoff + m * 16 * SXs + 8 * ks), l1 = *reinterpret_cast<const float2 *>(sXl + xoff + m * 16 * SXs + SXs + 8 * ks);
+                            ah[m][0] = __float_as_uint(h0.x); ah[m][1] = __float_as_uint(h1.x); ah[m][2] = __float_as_uint(h0.y); ah[m][3] = __float_as_uint(h1.y);
+                            al[m][0] = __float_as_uint(l0.x); al[m][1] = __float_as_uint(l1.x); al[m][2] = __float_as_uint(l0.y); al[m][3] = __float_as_uint(l1.y);
+                        }
+                        uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+                        for (int ntl = 0; ntl < 2; ntl++) {
+                            const float4 b = *reinterpret_cast<const float4 *>(wl4 + off.w1 + ((grp * 2 + ntl) * KS1 + ks) * 128);   /* hi0 hi1 lo0 lo1 */
+                            bh[ntl][0] = __float_as_uint(b.x); bh[ntl][1] = __float_as_uint(b.y); bl[ntl][0] = __float_as_uint(b.z); bl[ntl][1] = __float_as_uint(b.w);
+                        }
+                        /* the three 3xTF32 terms of one accumulator are dependent: issue each term across the four
+                           independent accumulators so the tensor pipe always has independent work in flight */
+#pragma unroll
+                        for (int m = 0; m < 2; m++)
+#pragma unroll
+                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[m][ntl], al[m], bh[ntl][0], bh[ntl][1]);
+#pragma unroll
+                        for (int m = 0; m < 2; m++)
+#pragma unroll
+                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[m][ntl], ah[m], bl[ntl][0], bl[ntl][1]);
+#pragma unroll
+                        for (int m = 0; m < 2; m++)
+#pragma unroll
+                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[m][ntl], ah[m], bh[ntl][0], bh[ntl][1]);
+                    }
+                    const float4 s1 = *reinterpret_cast<const float4 *>(wt4 + off.s1 + grp * 16);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(wt4 + off.b1 + grp * 16);
+#pragma unroll
+                    for (int m = 0; m < 2; m++)
+#pragma unroll
+                        for (int r = 0; r < 2; r++) {
+                            const int2 mp = sMap[(mt0 + m) * 16 + 2 * g + r];
+                            if (mp.x >= 0) {
+                                float4 v = make_float4(acc[m][0][2 * r], acc[m][0][2 * r + 1], acc[m][1][2 * r], acc[m][1][2 * r + 1]);
+                                v = bn_act4(v, s1, b1, a.slope1);
+                                if (border) {             /* halo pixels outside the image are the depthwise conv's zero padding */
+                                    const int iy = q.iy0 + (mp.y & 0xffff), ix = q.ix0 + (mp.y >> 16);
+                                    if ((unsigned)iy >= (unsigned)a.H || (unsigned)ix >= (unsigned)a.W) v = blk_zero4();
+                                }
+                                sm100::sts128(sE_addr + mp.x + (grp * 16 + 4 * t) * 4, v);
+                            }
+                        }
+                    pair += step_pair; grp += step_grp;
+                    if (GC > 1 && grp >= GC) { grp -= GC; pair++; }
+                }
+            }
+            __syncthreads();
+
+            /* ---------------- stage B: depthwise 3x3 in registers -> projection GEMM ---------------- */
+#pragma unroll
+            for (int grp = 0; grp < GC; grp++) {
+                float4 wd[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) wd[k] = *reinterpret_cast<const float4 *>(wt4 + off.wd + (grp * 9 + k) * 16);
+                const float4 sd = *reinterpret_cast<const float4 *>(wt4 + off.sd + grp * 16);
+                const float4 bd = *reinterpret_cast<const float4 *>(wt4 + off.bd + grp * 16);
+#pragma unroll
+                for (int mh = 0; mh < MTW; mh += MH) {
+                    if (mh < nmi) {
+                        uint32_t ah[MH][2][4], al[MH][2][4];
+#pragma unroll
+                        for (int mj = 0; mj < MH; mj++) {
+                            const int mi = mh + mj;
+                            float4 d0 = blk_zero4(), d1 = blk_zero4();
+#pragma unroll
+                            for (int dy = 0; dy < 3; dy++) {
+                                const uint32_t row = dwrow[mi][dy] + grp * 64;
+                                constexpr uint32_t px = SEs * 4;
+                                if (S == 1) {
+                                    const float4 e0 = sm100::lds128(row), e1 = sm100::lds128(row + px), e2 = sm100::lds128(row + 2 * px), e3 = sm100::lds128(row + 3 * px);
+                                    blk_fma4(d0, e0, wd[dy * 3]); blk_fma4(d0, e1, wd[dy * 3 + 1]); blk_fma4(d0, e2, wd[dy * 3 + 2]);
+                                    blk_fma4(d1, e1, wd[dy * 3]); blk_fma4(d1, e2, wd[dy * 3 + 1]); blk_fma4(d1, e3, wd[dy * 3 + 2]);
+                                } else {
+                                    const float4 e0 = sm100::lds128(row), e1 = sm100::lds128(row + px), e2 = sm100::lds128(row + 2 * px),
+                                                 e3 = sm100::lds128(row + 3 * px), e4 = sm100::lds128(row + 4 * px);
+                                    blk_fma4(d0, e0, wd[dy * 3]); blk_fma4(d0, e1, wd[dy * 3 + 1]); blk_fma4(d0, e2, wd[dy * 3 + 2]);
+                                    blk_fma4(d1, e2, wd[dy * 3]); blk_fma4(d1, e3, wd[dy * 3 + 1]); blk_fma4(d1, e4, wd[dy * 3 + 2]);
+                                }
+                            }
+                            d0 = bn_act4(d0, sd, bd, a.sloped); d1 = bn_act4(d1, sd, bd, a.sloped);
+                            split_tf32(d0.x, ah[mj][0][0], al[mj][0][0]); split_tf32(d1.x, ah[mj][0][1], al[mj][0][1]);
+                            split_tf32(d0.y, ah[mj][0][2], al[mj][0][2]); split_tf32(d1.y, ah[mj][0][3], al[mj][0][3]);
+                            split_tf32(d0.z, ah[mj][1][0], al[mj][1][0]); split_tf32(d1.z, ah[mj][1][1], al[mj][1][1]);
+                            split_tf32(d0.w, ah[mj][1][2], al[mj][1][2]); split_tf32(d1.w, ah[mj][1][3], al[mj][1][3]);
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 2; kk++) {
+                            uint32_t bh[NT3][2], bl[NT3][2];
+#pragma unroll
+                            for (int nt = 0; nt < NT3; nt++) {
+                                const float4 b = *reinterpret_cast<const float4 *>(wl4 + off.w2 + ((grp * 2 + kk) * NT3 + nt) * 128);
+                                bh[nt][0] = __float_as_uint(b.x); bh[nt][1] = __float_as_uint(b.y); bl[nt][0] = __float_as_uint(b.z); bl[nt][1] = __float_as_uint(b.w);
+                            }
+#pragma unroll
+                            for (int mj = 0; mj < MH; mj++)
+#pragma unroll
+                                for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mh + mj][nt], al[mj][kk], bh[nt][0], bh[nt][1]);
+#pragma unroll
+                            for (int mj = 0; mj < MH; mj++)
+#pragma unroll
+                                for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mh + mj][nt], ah[mj][kk], bl[nt][0], bl[nt][1]);
+#pragma unroll
+                            for (int mj = 0; mj < MH; mj++)
+#pragma unroll
+                                for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mh + mj][nt], ah[mj][kk], bh[nt][0], bh[nt][1]);
+                        }
+                    }
+                }
+            }
+        }
+
+        /* ---------------- block epilogue: BN + act [+ shortcut from the resident x tile] -> y ---------------- */
+#pragma unroll
+        for (int mi = 0; mi < MTW; mi++) {
+            const int ty = tyx[mi] >> 16, tx = tyx[mi] & 0xffff;
+            if (ty < q.th && tx < q.tw) {
+                float *yp = a.y + (((long)q.n * a.OH + q.oy0 + ty) * a.OW + q.ox0 + tx) * a.ldy;
+                const int xc = ((ty + 1 - a.yo) * a.XW + tx + 1 - a.xo) * SXs;           /* centre pixel; S == 1 whenever res is set */
+#pragma unroll
+                for (int nt = 0; nt < NT3; nt++) {
+                    const int co = 8 * nt + 2 * t;
+                    if (co < a.cout) {
+                        const float2 s3 = *reinterpret_cast<const float2 *>(sSB3 + co), b3 = *reinterpret_cast<const float2 *>(sSB3 + COUT_P + co);
+                        float2 v0, v1;
+                        v0.x = slope_act(fmaf(pacc[mi][nt][0], s3.x, b3.x), a.slope3); v0.y = slope_act(fmaf(pacc[mi][nt][1], s3.y, b3.y), a.slope3);
+                        v1.x = slope_act(fmaf(pacc[mi][nt][2], s3.x, b3.x), a.slope3); v1.y = slope_act(fmaf(pacc[mi][nt][3], s3.y, b3.y), a.slope3);
+                        if (a.res) {                      /* x = hi + lo exactly */
+                            const float2 h0 = *reinterpret_cast<const float2 *>(sX + xc + co), h1 = *reinterpret_cast<const float2 *>(sX + xc + SXs + co);
+                            const float2 l0 = *reinterpret_cast<const float2 *>(sXl + xc + co), l1 = *reinterpret_cast<const float2 *>(sXl + xc + SXs + co);
+                            v0.x = slope_act(v0.x + (h0.x + l0.x), a.slope_res); v0.y = slope_act(v0.y + (h0.y + l0.y), a.slope_res);
+                            v1.x = slope_act(v1.x + (h1.x + l1.x), a.slope_res); v1.y = slope_act(v1.y + (h1.y + l1.y), a.slope_res);
+                        }
+                        *reinterpret_cast<float2 *>(yp + co) = v0;
+                        *reinterpret_cast<float2 *>(yp + a.ldy + co) = v1;               /* tw is even: pixel tx+1 is inside the tile */
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* Build the fragment-ordered weight chunks of one block from the three convs' packed reference rows
+ * (ffcnn.c:218-234: [weights..., pad, scale', bias', mean, var] per filter). */
+__global__ void k_prep_block(const float *__restrict__ p1, int row1, int cin, const float *__restrict__ pd, int rowd,
+                             const float *__restrict__ p3, int row3, int cexp, int cout, int KS1, int NT3, int GC, int NC,
+                             float *__restrict__ chunks, float *__restrict__ sb3)
+{
+    const BlkChunk off(GC, KS1, NT3);
+    const long total = (long)NC * off.total;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total + 16 * NT3; i += (long)gridDim.x * blockDim.x) {
+        if (i >= total) {                                  /* projection scale / bias */
+            const int k = (int)(i - total), co = k % (8 * NT3), which = k / (8 * NT3);
+            sb3[k] = co < cout ? p3[(long)co * row3 + row3 - 4 + which] : 0.f;
+            continue;
+        }
+        const int c = (int)(i / off.total), r = (int)(i - (long)c * off.total);
+        float v = 0.f; bool is_w = false; int lohalf = 0;
+        if (r < off.s1) {
+            const int lane4 = r % 128; int rest = r / 128;
+            const int ks = rest % KS1; rest /= KS1;
+            const int ntl = rest % 2, grp = rest / 2, lane = lane4 >> 2, j = lane4 & 1, g = lane >> 2, t = lane & 3;
+            const int ch = (c * GC + grp) * 16 + 4 * (g >> 1) + 2 * ntl + (g & 1), ci = 8 * ks + 2 * t + j;
+            if (ch < cexp && ci < cin) v = p1[(long)ch * row1 + ci];
+            is_w = true; lohalf = (lane4 >> 1) & 1;
+        } else if (r < off.wd) {
+            const int rr = r - off.s1, which = rr / (GC * 16), ch = c * GC * 16 + rr % (GC * 16);
+            if (ch < cexp) v = p1[(long)ch * row1 + row1 - 4 + which];
+        } else if (r < off.sd) {
+            const int rr = r - off.wd, grp = rr / 144, tap = (rr % 144) / 16, ch = (c * GC + grp) * 16 + rr % 16;
+            if (ch < cexp) v = pd[(long)ch * rowd + tap];
+        } else if (r < off.w2) {
+            const int rr = r - off.sd, which = rr / (GC * 16), ch = c * GC * 16 + rr % (GC * 16);
+            if (ch < cexp) v = pd[(long)ch * rowd + rowd - 4 + which];
+        } else {
+            const int rr = r - off.w2, lane4 = rr % 128; int rest = rr / 128;
+            const int nt = rest % NT3; rest /= NT3;
+            const int kk = rest % 2, grp = rest / 2, lane = lane4 >> 2, j = lane4 & 1, g = lane >> 2, t = lane & 3;
+            const int co = 8 * nt + g, ch = (c * GC + grp) * 16 + 4 * t + 2 * kk + j;
+            if (co < cout && ch < cexp) v = p3[(long)co * row3 + ch];
+            is_w = true; lohalf = (lane4 >> 1) & 1;
+        }
+        if (is_w) {                                        /* fragment floats are stored pre-split: hi0 hi1 lo0 lo1 per lane */
+            uint32_t hi, lo; split_tf32(v, hi, lo);
+            v = __uint_as_float(lohalf ? lo : hi);
+        }
+        chunks[i] = v;
+    }
+}
+
+} // namespace ffb

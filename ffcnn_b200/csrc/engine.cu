@@ -30,6 +30,7 @@
 #include "pw_ffma.cuh"
 #include "dw_tma.cuh"
 #include "pw_tc.h"
+#include "block_mma.h"
 
 using namespace ffb;
 
@@ -342,6 +343,13 @@ struct ffb_engine {
     std::vector<int> fuse_sc;               /* conv layer i also performs shortcut layer fuse_sc[i] (-1: none) */
     std::vector<char> fused_away;           /* shortcut layer j is computed inside its producer conv */
     int fuse_shortcut = 1;
+    /* fused inverted-residual blocks (block_mma.cu): expand conv `first`, depthwise first+1, projection first+2 and, when
+       sc >= 0, the shortcut layer sc run as ONE kernel launched in the slot of layer `first` */
+    struct Block { int first, sc; BlkPlan *plan; };
+    std::vector<Block> blocks;
+    std::vector<int> blk_at;                /* per layer: index into blocks if the layer is a block's first conv, else -1 */
+    std::vector<char> in_block;             /* per layer: computed inside a block (its own launch slot is empty) */
+    int fuse_block = 1;
     Tens input;
     std::vector<Buf> bufs;
     float *d_arena = nullptr; size_t arena_floats = 0;
@@ -398,12 +406,75 @@ void ffb_engine_destroy(ffb_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     engine_free_plan(e);
     for (ffb_conv *c : e->convs) conv_release(c);
+    for (ffb_engine::Block &b : e->blocks) blk_plan_destroy(b.plan);
     cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_cand); cudaFree(e->d_count); cudaFree(e->d_flush);
     cudaFreeHost(e->h_stage); cudaFreeHost(e->h_cand); cudaFreeHost(e->h_count);
     for (int i = 0; i < 2; i++) { cudaFree(e->d_slot[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]); }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
+}
+
+/* through dropout / single-input route aliases: the layer that really produced what layer k outputs */
+static int producer_of(const NET *net, int k)
+{
+    while (k >= 0 && (net->layer_list[k].type == LAYER_TYPE_DROPOUT || (net->layer_list[k].type == LAYER_TYPE_ROUTE && net->layer_list[k].depend_num == 1)))
+        k = net->layer_list[k].type == LAYER_TYPE_DROPOUT ? k - 1 : net->layer_list[k].depend_list[0];
+    return k;
+}
+
+/* how many non-alias layers read each layer's output (the static form of the reference's refcounts, ffcnn.c:481-487) */
+static std::vector<int> count_readers(const NET *net)
+{
+    const int L = net->layer_num;
+    std::vector<int> readers(L, 0);
+    for (int k = 0; k < L; k++) {
+        const LAYER *l = net->layer_list + k;
+        if (l->type == LAYER_TYPE_DROPOUT || (l->type == LAYER_TYPE_ROUTE && l->depend_num == 1)) continue;
+        if (l->type != LAYER_TYPE_ROUTE && k > 0) { const int p = producer_of(net, k - 1); if (p >= 0) readers[p]++; }
+        for (int d = 0; d < l->depend_num; d++) { const int p = producer_of(net, l->depend_list[d]); if (p >= 0) readers[p]++; }
+    }
+    return readers;
+}
+
+/* Block fusion: find every  1x1 conv -> 3x3 depthwise conv -> 1x1 conv [-> dropout -> shortcut from the block
+ * input]  chain whose intermediate tensors have no other reader, and plan one fused kernel for it (block_mma.cu). */
+static int engine_find_blocks(ffb_engine *e)
+{
+    NET *net = &e->net->pub; const int L = net->layer_num;
+    for (ffb_engine::Block &b : e->blocks) blk_plan_destroy(b.plan);
+    e->blocks.clear(); e->blk_at.assign(L, -1); e->in_block.assign(L, 0);
+    if (!e->fuse_block) return 0;
+    const std::vector<int> readers = count_readers(net);
+    auto is_pw = [](const LAYER *l) { return l->type == LAYER_TYPE_CONV && l->fs == 1 && l->stride == 1 && l->groups == 1 && l->pad == 0; };
+    for (int i = 0; i + 2 < L; i++) {
+        const LAYER *a = net->layer_list + i, *d = a + 1, *p = a + 2;
+        if (!is_pw(a) || !is_pw(p) || d->type != LAYER_TYPE_CONV) continue;
+        if (!(d->fs == 3 && d->pad == 1 && d->groups == d->c && d->fn == d->c && (d->stride == 1 || d->stride == 2))) continue;
+        if (readers[i] != 1 || readers[i + 1] != 1) continue;
+        int sc = -1, act_res = 0;
+        for (int j = i + 3; j < L && j <= i + 4; j++) {
+            const LAYER *sl = net->layer_list + j;
+            if (sl->type == LAYER_TYPE_DROPOUT) continue;
+            if (sl->type == LAYER_TYPE_SHORTCUT && i > 0 && readers[i + 2] == 1 && producer_of(net, j - 1) == i + 2 &&
+                producer_of(net, sl->depend_list[0]) == producer_of(net, i - 1) && d->stride == 1 && a->c == p->fn) { sc = j; act_res = sl->activation; }
+            break;
+        }
+        /* fuse_block 1 (default): only the block shapes where the fused kernel beats the three separate layers on a B200
+           (measured, profiles/r1j_block_fusion.txt): the shared-memory-staged design loses on the 160x160 blocks (8-24
+           expanded channels: too little work per staged byte) and on 136 expanded channels; 2: every supported block */
+        const bool wanted = e->fuse_block >= 2 || a->fn == 32 || a->fn == 48 || (a->fn == 96 && d->stride == 1) || a->fn == 224;
+        if (!wanted) continue;
+        BlkPlan *plan = blk_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res);
+        if (!plan) continue;
+        if (blk_prepare(plan, e->convs[i]->d_packed, e->convs[i + 1]->d_packed, e->convs[i + 2]->d_packed, e->stream) != 0) { blk_plan_destroy(plan); return -1; }
+        e->blk_at[i] = (int)e->blocks.size(); e->in_block[i + 1] = e->in_block[i + 2] = 1;
+        if (sc >= 0) e->in_block[sc] = 1;
+        e->blocks.push_back({ i, sc, plan });
+        if (getenv("FFCNN_BLK_VERBOSE")) fprintf(stderr, "ffcnn_b200: block L%d-L%d: %s\n", i, sc >= 0 ? sc : i + 2, blk_describe(plan));
+        i += 2;
+    }
+    return 0;
 }
 
 /* ---- activation arena: one buffer per produced tensor, reused once its last reader has run ---- */
@@ -426,32 +497,38 @@ static int engine_plan(ffb_engine *e)
        shortcut layer adds the skip tensor in its own epilogue and writes the shortcut's output; the conv's own output and
        the separate add kernel disappear (2 of the 4 tensor passes).  Off under keep_all (every layer output must exist). */
     e->fuse_sc.assign(L, -1); e->fused_away.assign(L, 0);
-    if (e->fuse_shortcut && !e->keep_all) {
-        std::vector<int> readers(L, 0);                         /* how many non-alias layers read layer k's output */
-        auto producer_of = [&](int k) { while (k >= 0 && (net->layer_list[k].type == LAYER_TYPE_DROPOUT ||
-                                                       (net->layer_list[k].type == LAYER_TYPE_ROUTE && net->layer_list[k].depend_num == 1)))
-                                            k = net->layer_list[k].type == LAYER_TYPE_DROPOUT ? k - 1 : net->layer_list[k].depend_list[0];
-                                        return k; };
-        for (int k = 0; k < L; k++) {
-            const LAYER *l = net->layer_list + k;
-            if (l->type == LAYER_TYPE_DROPOUT || (l->type == LAYER_TYPE_ROUTE && l->depend_num == 1)) continue;
-            if (l->type != LAYER_TYPE_ROUTE && k > 0) { const int p = producer_of(k - 1); if (p >= 0) readers[p]++; }
-            for (int d = 0; d < l->depend_num; d++) { const int p = producer_of(l->depend_list[d]); if (p >= 0) readers[p]++; }
-        }
+    const bool fuse = e->keep_all != 1;                         /* keep_all 1: every layer materialised by its own kernel; 2: fused plan, no buffer reuse */
+    const bool use_blocks = fuse && e->fuse_block && (int)e->blk_at.size() == L;
+    if (e->fuse_shortcut && fuse) {
+        const std::vector<int> readers = count_readers(net);
         for (int j = 1; j < L; j++) {
             const LAYER *sl = net->layer_list + j;
-            if (sl->type != LAYER_TYPE_SHORTCUT) continue;
-            const int p = producer_of(j - 1), d = sl->depend_list[0];
-            if (p < 0 || producer_of(d) == p) continue;
+            if (sl->type != LAYER_TYPE_SHORTCUT || (use_blocks && e->in_block[j])) continue;
+            const int p = producer_of(net, j - 1), d = sl->depend_list[0];
+            if (p < 0 || producer_of(net, d) == p || (use_blocks && (e->in_block[p] || e->blk_at[p] >= 0))) continue;
             const ffb_conv *op = net->layer_list[p].type == LAYER_TYPE_CONV ? e->convs[p] : nullptr;
             if (!op || (op->kind != CK_PW_FFMA && op->kind != CK_PW_TC) || readers[p] != 1 || net->layer_list[p + 1].c % 4) continue;
             e->fuse_sc[p] = j; e->fused_away[j] = 1;
         }
     }
+    int blk_buf = -1;                                           /* output buffer of the block being walked through */
     for (int i = 0; i < L; i++) {
         const LAYER *il = net->layer_list + i, *ol = il + 1;
         Tens &o = e->outs[i];
         o.h = ol->h; o.w = ol->w; o.c = ol->c; o.ld = FFB_ALIGN(ol->c, 4);
+        if (use_blocks && e->blk_at[i] >= 0) {
+            /* the fused kernel runs in this layer's slot: it reads the block input and writes the projection's
+               (or the shortcut's) tensor; the two expanded tensors are never materialised */
+            const LAYER *pl = net->layer_list + i + 3;           /* geometry of the projection's output */
+            blk_buf = new_buf((size_t)pl->h * pl->w * FFB_ALIGN(pl->c, 4), i);
+            touch(in_of(i), i);
+            continue;                                            /* o stays without a buffer */
+        }
+        if (use_blocks && e->in_block[i]) {
+            if (il->type == LAYER_TYPE_CONV && net->layer_list[i].fs == 1) { o.buf = blk_buf; touch(o, i); }   /* projection: the block's output */
+            else if (il->type == LAYER_TYPE_SHORTCUT) { o = in_of(i); touch(o, i); }                           /* fused shortcut: same tensor */
+            continue;                                            /* depthwise: no buffer */
+        }
         if (il->type == LAYER_TYPE_CONV && e->fuse_sc[i] >= 0) {
             /* the conv writes the shortcut's tensor: one buffer, created now, named by both layers */
             o.buf = new_buf(o.frame_floats(), i); touch(in_of(i), i); touch(e->outs[net->layer_list[e->fuse_sc[i]].depend_list[0]], i); touch(o, i);
@@ -527,6 +604,8 @@ static int engine_prepare_weights(ffb_engine *e)
         if (op->tc) { pw_tc_plan_destroy(op->tc); op->tc = NULL; }
         if (conv_prepare(op, e->stream) != 0) return -1;
     }
+    if (engine_find_blocks(e) != 0) return -1;
+    e->plan_dirty = true;
     return 0;
 }
 
@@ -560,6 +639,7 @@ int ffb_net_attach(NET *net, int device, int max_batch)
     if ((env = getenv("FFCNN_GRAPH")))     e->use_graph = atoi(env);
     if ((env = getenv("FFCNN_DW_MODE")))   e->dw_mode = atoi(env);
     if ((env = getenv("FFCNN_PDL")))       sm100::g_ffb_pdl = atoi(env);
+    if ((env = getenv("FFCNN_FUSE_BLOCK"))) e->fuse_block = atoi(env);
     CK(cudaMalloc(&e->d_packed, std::max(1, net->weight_size) * sizeof(float)));
     CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     if (engine_prepare_weights(e) != 0) return -1;
@@ -616,6 +696,7 @@ int ffb_set_option(NET *net, const char *name, int value)
     else if (!strcmp(name, "fuse_input")) { e->fuse_input = value; }
     else if (!strcmp(name, "fuse_shortcut")) { if (e->fuse_shortcut != value) e->plan_dirty = true; e->fuse_shortcut = value; }
     else if (!strcmp(name, "keep_all"))  { if (e->keep_all != value) e->plan_dirty = true; e->keep_all = value; }
+    else if (!strcmp(name, "fuse_block")) { reweight = e->fuse_block != value; e->fuse_block = value; }
     else { ffb_set_error("unknown option '%s'", name); return -1; }
     if (reweight) {
         CK(cudaSetDevice(e->device));
@@ -638,6 +719,8 @@ int ffb_get_option(NET *net, const char *name)
     if (!strcmp(name, "input_fused")) return e->input_fused ? 1 : 0;
     if (!strcmp(name, "fuse_shortcut")) return e->fuse_shortcut;
     if (!strcmp(name, "keep_all")) return e->keep_all;
+    if (!strcmp(name, "fuse_block")) return e->fuse_block;
+    if (!strcmp(name, "blocks")) return (int)e->blocks.size();
     if (!strcmp(name, "max_batch")) return e->max_batch;
     if (!strcmp(name, "batch")) return e->batch;
     if (!strcmp(name, "device")) return e->device;
@@ -702,7 +785,7 @@ int ffb_input_u8(NET *net, const unsigned char *frames, int n, int w, int h, int
     net->s1 = s1; net->s2 = s2;
     for (int i = 0; i < 3; i++) { e->in_mean[i] = mean[i]; e->in_norm[i] = norm[i]; }
     /* no resize (frame == net size): the stem reads the u8 frames itself and the fp32 input tensor is never materialised */
-    e->input_fused = e->fuse_input && !e->keep_all && w == e->input.w && h == e->input.h && net->layer_num > 0 &&
+    e->input_fused = e->fuse_input && e->keep_all != 1 && w == e->input.w && h == e->input.h && net->layer_num > 0 &&
                      net->layer_list[0].type == LAYER_TYPE_CONV && e->convs[0] && e->convs[0]->kind == CK_STEM && e->outs[0].ld == 8;
     e->u8_src = src; e->u8_pitch = pitch;
     if (e->input_fused) return 0;
@@ -739,6 +822,15 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
     NET *net = &e->net->pub; const LAYER *il = net->layer_list + i;
     const Tens &in = i == 0 ? e->input : e->outs[i - 1]; const Tens &o = e->outs[i];
     const int n = e->batch;
+    if (e->keep_all != 1 && e->fuse_block && (int)e->blk_at.size() > i) {
+        if (e->in_block[i]) return 0;                          /* computed by the block kernel launched in an earlier slot */
+        if (e->blk_at[i] >= 0) {
+            const ffb_engine::Block &b = e->blocks[e->blk_at[i]]; const Tens &y = e->outs[i + 2];
+            if (blk_run(b.plan, in.p, in.ld, y.p, y.ld, n, st) != 0) return -1;
+            (*launches)++;
+            return 0;
+        }
+    }
     switch (il->type) {
     case LAYER_TYPE_CONV:
         if (i == 0 && e->input_fused) {
@@ -1024,6 +1116,7 @@ long ffb_layer_output(NET *net, int layer, int frame, float *chw, long capacity)
     return count;
 }
 
+static thread_local bool g_cost_recursing = false;
 int ffb_layer_cost(NET *net, int i, double *bytes, double *flops, char *kname, int cap)
 {
     if (!net || i < 0 || i >= net->layer_num) { ffb_set_error("ffb_layer_cost: bad layer"); return -1; }
@@ -1043,6 +1136,18 @@ int ffb_layer_cost(NET *net, int i, double *bytes, double *flops, char *kname, i
     }
     ffb_net *fn = ffb_from_pub(net);
     if (a->type == LAYER_TYPE_CONV && fn->engine && fn->engine->convs[i]) nm = fn->engine->convs[i]->name;
+    if (fn->engine && fn->engine->keep_all != 1 && fn->engine->fuse_block && (int)fn->engine->blk_at.size() > i && !g_cost_recursing) {
+        /* a fused block is reported in its first layer's slot with the summed (unfused) algorithmic cost of its layers */
+        ffb_engine *e = fn->engine;
+        if (e->in_block[i]) { by = 0; fl = 0; nm = "in_block"; }
+        else if (e->blk_at[i] >= 0) {
+            const ffb_engine::Block &b = e->blocks[e->blk_at[i]];
+            g_cost_recursing = true;
+            for (int k = i + 1; k <= (b.sc >= 0 ? b.sc : i + 2); k++) { double b2 = 0, f2 = 0; ffb_layer_cost(net, k, &b2, &f2, NULL, 0); by += b2; fl += f2; }
+            g_cost_recursing = false;
+            nm = "block_mma_3xtf32";
+        }
+    }
     if (bytes) *bytes = by;
     if (flops) *flops = fl;
     if (kname && cap > 0) snprintf(kname, (size_t)cap, "%s", nm);

@@ -211,12 +211,13 @@ def test_full_batch_256_properties(assets, golden):
 
 
 def test_liveness_arena_gives_same_heads_as_keep_all(assets):
-    """The reused-buffer plan (ffcnn.c:511-517's free-when-unreferenced, done statically) must not change results."""
+    """The reused-buffer plan (ffcnn.c:511-517's free-when-unreferenced, done statically) must not change results:
+    keep_all=2 runs the same (fused) kernels with one private buffer per tensor, so the boxes must be bit-identical."""
     cfg, wts, bmp = assets
     img, w, h = ref.load_bmp(bmp)
     s2f = synth.shifted_frames_from(img, w, h, 8)
     res = []
-    for keep in (1, 0):
+    for keep in (2, 0):
         net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=8)
         net.set_option("keep_all", keep)
         net.detect_batch_u8(s2f, 8, 320, 320, 960)
@@ -272,3 +273,50 @@ def test_ragged_and_odd_shapes_through_generic_kernel():
         x = rng.standard_normal((ic, ih, iw)).astype(np.float32)
         got = fb.groupconv(x, f, iw, ih, ic, grp, pad, st, fs, fn, act)
         assert rel_err(got, orc.conv_raw(x, f, iw, ih, ic, grp, pad, st, fs, fn, act, False)) < FEAT_TOL
+
+
+@pytest.mark.parametrize("fuse_block", [1, 2])
+def test_fused_blocks_against_oracle(assets, oracle_layers, fuse_block):
+    """Block fusion (1x1 expand -> 3x3 depthwise -> 1x1 project [+ shortcut] as one kernel, block_mma.cu): every tensor the
+    fused plan still materialises (block outputs, tail layers, heads) against the oracle, boxes against the oracle's, and
+    the fused plan must give the same boxes on a batch as the layer-by-layer plan.  fuse_block 1 = default policy,
+    2 = every supported block (all 24 chains of the graph, both strides, every channel configuration)."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=8)
+    net.set_option("fuse_block", fuse_block)
+    net.set_option("keep_all", 2)                       # fused plan, but no buffer reuse: surviving tensors stay readable
+    nblocks = net.get_option("blocks")
+    assert nblocks == 24 if fuse_block == 2 else 0 < nblocks < 24
+    net.net_input(img, w, h)
+    x = net.input_tensor().copy()
+    got = net.net_forward()
+    outs, raw, fin = orc.forward(oracle_layers, x, net.net.s1, net.net.s2, v6_quirk=True)
+    checked = 0
+    for i, o in enumerate(outs):
+        _, _, kn = net.layer_cost(i)
+        if o is None or kn == "in_block":
+            continue
+        # a projection conv followed by dropout + shortcut shares its buffer with the shortcut: only the shortcut's values live there
+        nxt = [oracle_layers[j].type for j in range(i + 1, min(i + 3, len(oracle_layers)))]
+        if orc.SHORTCUT in nxt and oracle_layers[i].type in (orc.CONV, orc.DROPOUT):
+            continue
+        a = net.layer_output(i, 0)
+        if a is None:
+            continue
+        assert rel_err(a, o) < FEAT_TOL, (i, kn, rel_err(a, o))
+        checked += 1
+    assert checked >= 20
+    graw = net.boxes(0, raw=True)
+    assert len(graw) == len(raw) and [int(t) for t in graw["type"]] == [int(t) for t in raw["type"]]
+    boxes_close(got, fin, px=BOX_TOL, score=SCORE_TOL)
+    s2f = synth.shifted_frames_from(img, w, h, 8)
+    net.set_option("keep_all", 0)
+    net.detect_batch_u8(s2f, 8, 320, 320, 960)
+    fused = [net.boxes(f) for f in range(8)]
+    net.set_option("fuse_block", 0)
+    assert net.get_option("blocks") == 0
+    net.detect_batch_u8(s2f, 8, 320, 320, 960)
+    for f in range(8):
+        boxes_close(fused[f], net.boxes(f), px=BOX_TOL, score=SCORE_TOL)
+    net.close()
