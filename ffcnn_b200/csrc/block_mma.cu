@@ -59,12 +59,12 @@ static float slope_of(int act) { return act == 2 ? 0.1f : act == 1 ? 0.f : 1.f; 
 
 /* Tile search: minimise an estimate of SM cycles per output pixel (tensor pipe: 2.14 clk per m16n8k8 on the SM, measured
  * with tools/micro/mma_sync.cu; FFMA/issue work of the depthwise stage; barrier and tile-start latencies), subject to
- * the shared-memory budget.  FFCNN_BLK_TILE_<OH>="TH,TW,GC" overrides the choice for blocks with that output height. */
+ * the shared-memory budget.  FFCNN_BLK_TILE_<OH>_<CEXP>="TH,TW,GC" overrides the choice for blocks with that output height / expanded width. */
 static bool plan_tile(BlkPlan *p)
 {
     const int S = p->S, KS1 = p->KS1, NT3 = p->NT3, G = p->G, SXs = 8 * KS1 + 4;
     int fTH = 0, fTW = 0, fGC = 0;
-    char key[48]; snprintf(key, sizeof key, "FFCNN_BLK_TILE_%d", p->OH);
+    char key[64]; snprintf(key, sizeof key, "FFCNN_BLK_TILE_%d_%d", p->OH, p->cexp);      /* developer override for tile sweeps (tools/blk_sweep.py) */
     if (const char *ov = getenv(key)) sscanf(ov, "%d,%d,%d", &fTH, &fTW, &fGC);
     double best = 1e30; bool ok = false;
     for (int GC = 1; GC <= G && GC <= 4; GC++) {
@@ -75,7 +75,11 @@ static bool plan_tile(BlkPlan *p)
             if (fTW && TW != fTW) continue;
             for (int TH = 1; TH <= p->OH && TH <= 80; TH++) {
                 if (fTH && TH != fTH) continue;
-                const int M3 = (TH * TW + 15) / 16, MTW = (M3 + BLK_WARPS - 1) / BLK_WARPS;
+                /* stage-B units: single m-tiles (MTW 1) or 2x2-pixel quads over row pairs (MTW 2, 4) */
+                const int M3 = (TH * TW + 15) / 16;
+                int MTW = (M3 + BLK_WARPS - 1) / BLK_WARPS;
+                if (MTW > 1 && (TH & 1)) continue;                     /* quads need whole row pairs */
+                if (MTW > 1) { const int nquads = ((TH + 1) / 2 * TW + 15) / 16; MTW = 2 * ((nquads + BLK_WARPS - 1) / BLK_WARPS); }
                 const BlkInst *inst = find_inst(KS1, NT3, S, MTW, GC);
                 if (!inst) continue;
                 const int HH = (TH - 1) * S + 3, HW = (TW - 1) * S + 3;
@@ -83,14 +87,22 @@ static bool plan_tile(BlkPlan *p)
                 const int XH = frame ? p->H : HH, XW = frame ? p->W : HW;
                 if (XH > 256 || XW > 256) continue;
                 const int M1 = (XH * XW + 15) / 16, xrows = 32 * ((M1 + 1) / 2);
-                const size_t smem = 4 * (size_t)(128 + 2 * xrows + 2 * off.total + 3 * xrows * SXs + HH * HW * SEs) + 128;
+                const size_t smem = 4 * (size_t)(128 + 2 * xrows + 2 * off.total + 2 * xrows * SXs + HH * HW * SEs) + 128;
                 if (smem > 225 * 1024) continue;
                 int occ = (int)((228 * 1024) / (smem + 1024)); if (occ > inst->MINB) occ = inst->MINB; if (occ < 1) occ = 1;
-                const double rounds_e = (double)(((M1 + 1) / 2 * GC + BLK_WARPS - 1) / BLK_WARPS) / GC;   /* work item = (m-tile pair, group) */
-                const double t_mma = 2.14 * (rounds_e * BLK_WARPS * 2 * G * KS1 * 6 + (double)MTW * BLK_WARPS * G * 6 * NT3);
-                const double t_alu = ((double)MTW * BLK_WARPS * G * (S == 1 ? 190 : 205) + rounds_e * BLK_WARPS * G * (30 + 28 * KS1)) / 4;
-                const double t_fix = NC * 2 * 160.0 + 2500.0;
-                const double t_tile = occ >= 2 ? std::max(t_mma, t_alu) + 0.35 * std::min(t_mma, t_alu) + 0.5 * t_fix : t_mma + t_alu + t_fix;
+                /* per-tile cost on one SM, three candidate limiters (profiles/r1j: shared-memory wavefronts bind first):
+                   wf  = shared-memory wavefronts (1 per clk), mma = m16n8k8 tensor ops (2.14 clk each), ins = issue slots / 4 */
+                const int MT = KS1 * GC > 6 ? 1 : 2, items = (M1 + MT - 1) / MT, rounds = (items + BLK_WARPS - 1) / BLK_WARPS;
+                const int units = MTW > 1 ? ((TH + 1) / 2 * TW + 15) / 16 : M3, urounds = (units + BLK_WARPS - 1) / BLK_WARPS;
+                const int taps = MTW > 1 ? (S + 3) * (S + 3) : 3 * (S + 3), mper = MTW > 1 ? 2 : 1;
+                const double wfA = (double)items * NC * (4 * MT * KS1 + 8 * KS1 * GC + 4 * MT + 8 * MT * GC);
+                const double wfB = (double)units * G * 4 * taps + (double)BLK_WARPS * G * (8 * NT3 + 11);
+                const double mmaA = (double)rounds * BLK_WARPS * MT * G * KS1 * 6, mmaB = (double)urounds * BLK_WARPS * mper * G * 6 * NT3;
+                const double insA = (double)rounds * BLK_WARPS * NC * (KS1 * (14 * MT + GC * (2 + 6 * MT)) + MT * 2 * (8 + 14 * GC));
+                const double insB = (double)urounds * BLK_WARPS * G * (taps + mper * (72 + 16 + 24) + 2 * NT3 * (1 + 3 * mper) + 14);
+                const double t_wf = (wfA + wfB) / 0.85, t_mma = 2.14 * (mmaA + mmaB), t_ins = (insA + insB) / 4 / 0.8;
+                const double t_fix = (NC * 2 * 200.0 + 1500.0) * (occ >= 2 ? 0.5 : 1.0);
+                const double t_tile = std::max(t_wf, std::max(t_mma, t_ins)) * (occ >= 2 ? 1.15 : 1.4) + t_fix;
                 const double waste = (double)((p->OH + TH - 1) / TH * TH) * ((p->OW + TW - 1) / TW * TW) / ((double)p->OH * p->OW);
                 /* tiles per SM: few, big tiles quantise badly when a frame is one or two tiles */
                 const double score = t_tile / (TH * TW) * waste;

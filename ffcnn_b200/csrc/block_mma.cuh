@@ -122,16 +122,23 @@ __device__ __forceinline__ BlkTile blk_tile(const BlkArgs &a, long tile)
  * channel lanes beyond the tensor's (box wider than the tensor) arrive as zeros, which gives the padded, bank-conflict-free
  * pixel stride SXs = 8*KS1 + 4 for free.  Normally the box is the whole halo (xo = yo = 0); when one tile covers the whole
  * image ("frame mode") the halo ring lies entirely outside the image, the box is just the image (xo = yo = 1) and the ring
- * rows of E are cleared once per kernel.  Once landed, the tile is split in place into tf32 hi (same buffer) and lo (sXl).
+ * rows of E are cleared once per kernel.
+ *
+ * Output-pixel <-> fragment-row map of stage B.  MTW == 1: m-tile mt = 16 consecutive pixels of the row-major tile, lane
+ * (g) owns pixels 2g, 2g+1.  MTW >= 2: the tile is walked in ROW PAIRS -- m-tiles 2k and 2k+1 cover the same 16 positions
+ * of the (row pair, x) sequence in the upper and the lower row -- so a lane owns a 2x2 pixel quad and its 3x3 stencils
+ * share loads: (S+3)^2 shared-memory reads per quad instead of 2 * 3 * (S+3).
  */
 template <int KS1, int NT3, int S, int MTW, int GC, int MINB>
 __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_constant__ CUtensorMap tmX, const BlkArgs a)
 {
     extern __shared__ __align__(128) float4 blk_smem4[];
     float *smem = reinterpret_cast<float *>(blk_smem4);
-    constexpr int CIN_P = 8 * KS1, SXs = CIN_P + 4, COUT_P = 8 * NT3, XV = CIN_P / 4;
+    constexpr int CIN_P = 8 * KS1, SXs = CIN_P + 4, COUT_P = 8 * NT3;
     constexpr int SEs = 16 * GC + (S == 1 ? 8 : 4);       /* E pixel stride (floats): conflict-free 128-bit stencil loads */
-    constexpr int MH = MTW > 2 ? 2 : MTW;                 /* m-tiles whose A fragments are live at once in stage B */
+    constexpr int MT = (KS1 * GC > 6) ? 1 : 2;            /* m-tiles per stage-A work item (bounds the accumulator registers) */
+    constexpr bool QUAD = MTW >= 2;
+    constexpr int NQ = QUAD ? MTW / 2 : 1;                /* quads (or single m-tiles) per warp */
     constexpr BlkChunk off(GC, KS1, NT3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int HW = a.HW;
@@ -139,14 +146,13 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 96);       /* full_x[2], full_w[2] */
     int2     *sMap = reinterpret_cast<int2 *>(smem + 128);          /* [xrows]: x-tile pixel -> { byte offset of its E row or -1, hy | hx << 16 } */
     float    *sW = smem + 128 + 2 * a.xrows;
-    float    *sXB = sW + 2 * off.total;                             /* [2][xrows * SXs]: hi after the split pass */
-    float    *sXl = sXB + 2 * a.xrows * SXs;                        /* [xrows * SXs]: lo of the current tile */
-    float    *sE = sXl + a.xrows * SXs;
+    float    *sXB = sW + 2 * off.total;                             /* [2][xrows * SXs] */
+    float    *sE = sXB + 2 * a.xrows * SXs;
     uint64_t *full_x = bars, *full_w = bars + 2;
     const uint32_t sE_addr = sm100::smem_u32(sE), sW_addr = sm100::smem_u32(sW);
     const uint32_t x_bytes = (uint32_t)a.XH * a.XW * SXs * 4;
     constexpr uint32_t w_bytes = (uint32_t)off.total * 4;
-    const int XP = a.XH * a.XW, npairs = (((XP + 15) >> 4) + 1) >> 1, M3 = (a.TH * a.TW + 15) >> 4;
+    const int XP = a.XH * a.XW, nitems = (((XP + 15) >> 4) + MT - 1) / MT;
 
     if (tid == 0) {
         sm100::tma_prefetch_desc(&tmX);
@@ -159,24 +165,26 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
         sMap[xp] = make_int2(xp < XP ? (hy * HW + hx) * SEs * 4 : -1, hy | (hx << 16));
     }
     for (int i = tid; i < a.HH * HW * SEs / 4; i += BLK_THREADS) reinterpret_cast<float4 *>(sE)[i] = blk_zero4();
-    /* tile-independent lane geometry: this lane's two output pixels (ty, tx), (ty, tx+1) of every m-tile its warp owns */
-    uint32_t dwrow[MTW][3]; int tyx[MTW];
+    /* tile-independent lane geometry: top-left output pixel (ty, tx) of this lane's quad (or pixel pair) per owned unit */
+    uint32_t dwbase[NQ]; int tyx[NQ];
 #pragma unroll
-    for (int mi = 0; mi < MTW; mi++) {
-        const int qq = (warp + BLK_WARPS * mi) * 16 + 2 * g, qc = min(qq, a.TH * a.TW - 2);
-        const int ty = qc / a.TW, tx = qc - ty * a.TW;
-#pragma unroll
-        for (int dy = 0; dy < 3; dy++) dwrow[mi][dy] = sE_addr + (uint32_t)(((ty * S + dy) * HW + tx * S) * SEs + 4 * t) * 4;
-        tyx[mi] = qq < a.TH * a.TW ? (ty << 16 | tx) : (0x7fff << 16);          /* invalid rows fail the ty < th test */
+    for (int qi = 0; qi < NQ; qi++) {
+        const int unit = warp + BLK_WARPS * qi;                                  /* quad index (QUAD) or m-tile index */
+        const int p = unit * 16 + 2 * g;
+        int ty, tx; bool valid;
+        if (QUAD) { const int np = (a.TH + 1) / 2 * a.TW, pc = min(p, np - 2); const int rp = pc / a.TW; tx = pc - rp * a.TW; ty = 2 * rp; valid = p < np; }
+        else      { const int np = a.TH * a.TW, pc = min(p, np - 2); ty = pc / a.TW; tx = pc - ty * a.TW; valid = p < np; }
+        dwbase[qi] = sE_addr + (uint32_t)(((ty * S) * HW + tx * S) * SEs + 4 * t) * 4;
+        tyx[qi] = valid ? (ty << 16 | tx) : (0x7fff << 16);                      /* invalid units fail the ty < th test */
     }
-    const int nmi = warp < M3 ? (M3 - warp + BLK_WARPS - 1) / BLK_WARPS : 0;    /* m-tiles this warp owns (warp-uniform) */
-    constexpr int step_pair = BLK_WARPS / GC, step_grp = BLK_WARPS - step_pair * GC;
+    const int nunits = QUAD ? ((a.TH + 1) / 2 * a.TW + 15) >> 4 : (a.TH * a.TW + 15) >> 4;
+    const int nq = warp < nunits ? (nunits - warp + BLK_WARPS - 1) / BLK_WARPS : 0;     /* units this warp owns (warp-uniform) */
+    const uint32_t rowpitch = (uint32_t)HW * SEs * 4;
     __syncthreads();
     pdl_trigger(); pdl_wait();
 
     auto load_x = [&](long tile, int b) {                                       /* one thread */
         const BlkTile q = blk_tile<S>(a, tile);
-        sm100::fence_proxy_async_smem();                  /* the split pass wrote this buffer through the generic proxy */
         sm100::mbar_arrive_expect_tx(full_x + b, x_bytes);
         sm100::tma_load_4d(sXB + b * a.xrows * SXs, &tmX, 0, q.ix0 + a.xo, q.iy0 + a.yo, q.n, full_x + b);
     };
@@ -192,10 +200,10 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
         const BlkTile q = blk_tile<S>(a, tile);
         const int xb = it & 1;
-        float *sX = sXB + xb * a.xrows * SXs;
+        const float *sX = sXB + xb * a.xrows * SXs;
         const bool border = !a.frame && (q.iy0 < 0 || q.ix0 < 0 || q.iy0 + a.HH > a.H || q.ix0 + HW > a.W);
 
-        __syncthreads();                                  /* the previous tile no longer reads sW / sE / sXl / the other x buffer */
+        __syncthreads();                                  /* the previous tile no longer reads sW / sE / the other x buffer */
         const bool last_tile = tile + gridDim.x >= a.ntiles;
         if (tid == 0 && !last_tile) load_x(tile + gridDim.x, xb ^ 1);
         float pacc[MTW][NT3][4];
@@ -206,90 +214,83 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 4; j++) pacc[mi][nt][j] = 0.f;
         sm100::mbar_wait(full_x + xb, (it >> 1) & 1);
-        /* split pass: x -> hi (in place) + lo, once per tile instead of once per use */
-        for (int i = tid; i < XP * XV; i += BLK_THREADS) {
-            const int xp = i / XV, c4 = i - xp * XV;
-            float4 *ph = reinterpret_cast<float4 *>(sX + xp * SXs + c4 * 4), *pl = reinterpret_cast<float4 *>(sXl + xp * SXs + c4 * 4);
-            const float4 v = *ph; float4 h, l; uint32_t hh, ll;
-            split_tf32(v.x, hh, ll); h.x = __uint_as_float(hh); l.x = __uint_as_float(ll);
-            split_tf32(v.y, hh, ll); h.y = __uint_as_float(hh); l.y = __uint_as_float(ll);
-            split_tf32(v.z, hh, ll); h.z = __uint_as_float(hh); l.z = __uint_as_float(ll);
-            split_tf32(v.w, hh, ll); h.w = __uint_as_float(hh); l.w = __uint_as_float(ll);
-            *ph = h; *pl = l;
-        }
 
         for (int c = 0; c < a.NC; c++, cs++) {
             const int wb = w_resident ? 0 : cs & 1;
             sm100::mbar_wait(full_w + wb, w_resident ? 0 : (cs >> 1) & 1);
-            __syncthreads();                              /* split pass visible (c == 0) / every warp done with chunk c-1: E and the other weight buffer are free */
+            if (c > 0) __syncthreads();                   /* every warp is done with chunk c-1: E and the other weight buffer are free */
             if (tid == 0 && !w_resident && !(last_tile && c + 1 == a.NC)) load_chunk(c + 1 < a.NC ? c + 1 : 0, wb ^ 1);
             const float *wc = sW + wb * off.total;
             const float *wl4 = wc + lane * 4, *wt4 = wc + 4 * t;
 
-            /* ---------------- stage A: expand GEMM; work item = (pair of m-tiles, 16-channel group) ---------------- */
-            {
-                int pair = warp / GC, grp = warp - pair * GC;
-                while (pair < npairs) {
-                    const int mt0 = pair * 2;
-                    float acc[2][2][4];
+            /* ---------------- stage A: expand GEMM; work item = MT m-tiles x all GC groups of the chunk ----------------
+               the A fragments (x, split hi/lo on the fly) are loaded once per k-step and reused by every group */
+            for (int item = warp; item < nitems; item += BLK_WARPS) {
+                const int mt0 = item * MT;
+                float acc[GC][MT][2][4];
 #pragma unroll
-                    for (int m = 0; m < 2; m++)
+                for (int gr = 0; gr < GC; gr++)
+#pragma unroll
+                    for (int m = 0; m < MT; m++)
 #pragma unroll
                         for (int ntl = 0; ntl < 2; ntl++)
 #pragma unroll
-                            for (int j = 0; j < 4; j++) acc[m][ntl][j] = 0.f;
-                    const int xoff = (mt0 * 16 + 2 * g) * SXs + 2 * t;
+                            for (int j = 0; j < 4; j++) acc[gr][m][ntl][j] = 0.f;
+                const float *xr = sX + (mt0 * 16 + 2 * g) * SXs + 2 * t;
 #pragma unroll
-                    for (int ks = 0; ks < KS1; ks++) {
-                        uint32_t ah[2][4], al[2][4];
+                for (int ks = 0; ks < KS1; ks++) {
+                    uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
-                        for (int m = 0; m < 2; m++) {
-                            const float2 h0 = *reinterpret_cast<const float2 *>(sX + xoff + m * 16 * SXs + 8 * ks), h1 = *reinterpret_cast<const float2 *>(sX + xoff + m * 16 * SXs + SXs + 8 * ks);
-                            const float2 l0 = *reinterpret_cast<const float2 *>(sXl + xoff + m * 16 * SXs + 8 * ks), l1 = *reinterpret_cast<const float2 *>(sXl + xoff + m * 16 * SXs + SXs + 8 * ks);
-                            ah[m][0] = __float_as_uint(h0.x); ah[m][1] = __float_as_uint(h1.x); ah[m][2] = __float_as_uint(h0.y); ah[m][3] = __float_as_uint(h1.y);
-                            al[m][0] = __float_as_uint(l0.x); al[m][1] = __float_as_uint(l1.x); al[m][2] = __float_as_uint(l0.y); al[m][3] = __float_as_uint(l1.y);
-                        }
+                    for (int m = 0; m < MT; m++) {
+                        const float2 x0 = *reinterpret_cast<const float2 *>(xr + m * 16 * SXs + 8 * ks), x1 = *reinterpret_cast<const float2 *>(xr + m * 16 * SXs + SXs + 8 * ks);
+                        split_tf32(x0.x, ah[m][0], al[m][0]); split_tf32(x1.x, ah[m][1], al[m][1]);
+                        split_tf32(x0.y, ah[m][2], al[m][2]); split_tf32(x1.y, ah[m][3], al[m][3]);
+                    }
+#pragma unroll
+                    for (int gr = 0; gr < GC; gr++) {
                         uint32_t bh[2][2], bl[2][2];
 #pragma unroll
                         for (int ntl = 0; ntl < 2; ntl++) {
-                            const float4 b = *reinterpret_cast<const float4 *>(wl4 + off.w1 + ((grp * 2 + ntl) * KS1 + ks) * 128);   /* hi0 hi1 lo0 lo1 */
+                            const float4 b = *reinterpret_cast<const float4 *>(wl4 + off.w1 + ((gr * 2 + ntl) * KS1 + ks) * 128);   /* hi0 hi1 lo0 lo1 */
                             bh[ntl][0] = __float_as_uint(b.x); bh[ntl][1] = __float_as_uint(b.y); bl[ntl][0] = __float_as_uint(b.z); bl[ntl][1] = __float_as_uint(b.w);
                         }
-                        /* the three 3xTF32 terms of one accumulator are dependent: issue each term across the four
+                        /* the three 3xTF32 terms of one accumulator are dependent: each term is issued across the
                            independent accumulators so the tensor pipe always has independent work in flight */
 #pragma unroll
-                        for (int m = 0; m < 2; m++)
+                        for (int m = 0; m < MT; m++)
 #pragma unroll
-                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[m][ntl], al[m], bh[ntl][0], bh[ntl][1]);
+                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[gr][m][ntl], al[m], bh[ntl][0], bh[ntl][1]);
 #pragma unroll
-                        for (int m = 0; m < 2; m++)
+                        for (int m = 0; m < MT; m++)
 #pragma unroll
-                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[m][ntl], ah[m], bl[ntl][0], bl[ntl][1]);
+                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[gr][m][ntl], ah[m], bl[ntl][0], bl[ntl][1]);
 #pragma unroll
-                        for (int m = 0; m < 2; m++)
+                        for (int m = 0; m < MT; m++)
 #pragma unroll
-                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[m][ntl], ah[m], bh[ntl][0], bh[ntl][1]);
+                            for (int ntl = 0; ntl < 2; ntl++) mma_tf32(acc[gr][m][ntl], ah[m], bh[ntl][0], bh[ntl][1]);
                     }
-                    const float4 s1 = *reinterpret_cast<const float4 *>(wt4 + off.s1 + grp * 16);
-                    const float4 b1 = *reinterpret_cast<const float4 *>(wt4 + off.b1 + grp * 16);
+                }
 #pragma unroll
-                    for (int m = 0; m < 2; m++)
+                for (int m = 0; m < MT; m++)
 #pragma unroll
-                        for (int r = 0; r < 2; r++) {
-                            const int2 mp = sMap[(mt0 + m) * 16 + 2 * g + r];
-                            if (mp.x >= 0) {
-                                float4 v = make_float4(acc[m][0][2 * r], acc[m][0][2 * r + 1], acc[m][1][2 * r], acc[m][1][2 * r + 1]);
-                                v = bn_act4(v, s1, b1, a.slope1);
-                                if (border) {             /* halo pixels outside the image are the depthwise conv's zero padding */
-                                    const int iy = q.iy0 + (mp.y & 0xffff), ix = q.ix0 + (mp.y >> 16);
-                                    if ((unsigned)iy >= (unsigned)a.H || (unsigned)ix >= (unsigned)a.W) v = blk_zero4();
-                                }
-                                sm100::sts128(sE_addr + mp.x + (grp * 16 + 4 * t) * 4, v);
+                    for (int r = 0; r < 2; r++) {
+                        const int2 mp = sMap[(mt0 + m) * 16 + 2 * g + r];
+                        if (mp.x >= 0) {
+                            bool inside = true;
+                            if (border) {                 /* halo pixels outside the image are the depthwise conv's zero padding */
+                                const int iy = q.iy0 + (mp.y & 0xffff), ix = q.ix0 + (mp.y >> 16);
+                                inside = (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W;
+                            }
+#pragma unroll
+                            for (int gr = 0; gr < GC; gr++) {
+                                const float4 s1 = *reinterpret_cast<const float4 *>(wt4 + off.s1 + gr * 16);
+                                const float4 b1 = *reinterpret_cast<const float4 *>(wt4 + off.b1 + gr * 16);
+                                float4 v = make_float4(acc[gr][m][0][2 * r], acc[gr][m][0][2 * r + 1], acc[gr][m][1][2 * r], acc[gr][m][1][2 * r + 1]);
+                                v = inside ? bn_act4(v, s1, b1, a.slope1) : blk_zero4();
+                                sm100::sts128(sE_addr + mp.x + (gr * 16 + 4 * t) * 4, v);
                             }
                         }
-                    pair += step_pair; grp += step_grp;
-                    if (GC > 1 && grp >= GC) { grp -= GC; pair++; }
-                }
+                    }
             }
             __syncthreads();
 
@@ -301,56 +302,62 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                 for (int k = 0; k < 9; k++) wd[k] = *reinterpret_cast<const float4 *>(wt4 + off.wd + (grp * 9 + k) * 16);
                 const float4 sd = *reinterpret_cast<const float4 *>(wt4 + off.sd + grp * 16);
                 const float4 bd = *reinterpret_cast<const float4 *>(wt4 + off.bd + grp * 16);
+                uint32_t ah[MTW][2][4], al[MTW][2][4];
 #pragma unroll
-                for (int mh = 0; mh < MTW; mh += MH) {
-                    if (mh < nmi) {
-                        uint32_t ah[MH][2][4], al[MH][2][4];
+                for (int qi = 0; qi < NQ; qi++) {
+                    constexpr uint32_t px = SEs * 4;
+                    constexpr int NR = QUAD ? S + 3 : 3, NCOL = S + 3;             /* input rows / columns the unit touches */
+                    float4 d[2][2];                                                /* [row of the quad][pixel] */
 #pragma unroll
-                        for (int mj = 0; mj < MH; mj++) {
-                            const int mi = mh + mj;
-                            float4 d0 = blk_zero4(), d1 = blk_zero4();
+                    for (int h = 0; h < 2; h++) { d[h][0] = blk_zero4(); d[h][1] = blk_zero4(); }
+                    if (qi < nq) {
 #pragma unroll
-                            for (int dy = 0; dy < 3; dy++) {
-                                const uint32_t row = dwrow[mi][dy] + grp * 64;
-                                constexpr uint32_t px = SEs * 4;
-                                if (S == 1) {
-                                    const float4 e0 = sm100::lds128(row), e1 = sm100::lds128(row + px), e2 = sm100::lds128(row + 2 * px), e3 = sm100::lds128(row + 3 * px);
-                                    blk_fma4(d0, e0, wd[dy * 3]); blk_fma4(d0, e1, wd[dy * 3 + 1]); blk_fma4(d0, e2, wd[dy * 3 + 2]);
-                                    blk_fma4(d1, e1, wd[dy * 3]); blk_fma4(d1, e2, wd[dy * 3 + 1]); blk_fma4(d1, e3, wd[dy * 3 + 2]);
-                                } else {
-                                    const float4 e0 = sm100::lds128(row), e1 = sm100::lds128(row + px), e2 = sm100::lds128(row + 2 * px),
-                                                 e3 = sm100::lds128(row + 3 * px), e4 = sm100::lds128(row + 4 * px);
-                                    blk_fma4(d0, e0, wd[dy * 3]); blk_fma4(d0, e1, wd[dy * 3 + 1]); blk_fma4(d0, e2, wd[dy * 3 + 2]);
-                                    blk_fma4(d1, e2, wd[dy * 3]); blk_fma4(d1, e3, wd[dy * 3 + 1]); blk_fma4(d1, e4, wd[dy * 3 + 2]);
+                        for (int r = 0; r < NR; r++) {
+                            const uint32_t row = dwbase[qi] + grp * 64 + r * rowpitch;
+                            float4 e[NCOL];
+#pragma unroll
+                            for (int k = 0; k < NCOL; k++) e[k] = sm100::lds128(row + k * px);
+#pragma unroll
+                            for (int h = 0; h < (QUAD ? 2 : 1); h++) {
+                                const int dy = r - h * S;                              /* tap row of this input row for quad row h */
+                                if (dy >= 0 && dy < 3) {
+                                    blk_fma4(d[h][0], e[0], wd[dy * 3]); blk_fma4(d[h][0], e[1], wd[dy * 3 + 1]); blk_fma4(d[h][0], e[2], wd[dy * 3 + 2]);
+                                    blk_fma4(d[h][1], e[S], wd[dy * 3]); blk_fma4(d[h][1], e[S + 1], wd[dy * 3 + 1]); blk_fma4(d[h][1], e[S + 2], wd[dy * 3 + 2]);
                                 }
                             }
-                            d0 = bn_act4(d0, sd, bd, a.sloped); d1 = bn_act4(d1, sd, bd, a.sloped);
-                            split_tf32(d0.x, ah[mj][0][0], al[mj][0][0]); split_tf32(d1.x, ah[mj][0][1], al[mj][0][1]);
-                            split_tf32(d0.y, ah[mj][0][2], al[mj][0][2]); split_tf32(d1.y, ah[mj][0][3], al[mj][0][3]);
-                            split_tf32(d0.z, ah[mj][1][0], al[mj][1][0]); split_tf32(d1.z, ah[mj][1][1], al[mj][1][1]);
-                            split_tf32(d0.w, ah[mj][1][2], al[mj][1][2]); split_tf32(d1.w, ah[mj][1][3], al[mj][1][3]);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < (QUAD ? 2 : 1); h++) {
+                        const int mi = QUAD ? 2 * qi + h : qi;
+                        const float4 d0 = bn_act4(d[h][0], sd, bd, a.sloped), d1 = bn_act4(d[h][1], sd, bd, a.sloped);
+                        split_tf32(d0.x, ah[mi][0][0], al[mi][0][0]); split_tf32(d1.x, ah[mi][0][1], al[mi][0][1]);
+                        split_tf32(d0.y, ah[mi][0][2], al[mi][0][2]); split_tf32(d1.y, ah[mi][0][3], al[mi][0][3]);
+                        split_tf32(d0.z, ah[mi][1][0], al[mi][1][0]); split_tf32(d1.z, ah[mi][1][1], al[mi][1][1]);
+                        split_tf32(d0.w, ah[mi][1][2], al[mi][1][2]); split_tf32(d1.w, ah[mi][1][3], al[mi][1][3]);
+                    }
+                }
+                if (nq > 0) {
+#pragma unroll
+                    for (int kk = 0; kk < 2; kk++) {
+                        uint32_t bh[NT3][2], bl[NT3][2];
+#pragma unroll
+                        for (int nt = 0; nt < NT3; nt++) {
+                            const float4 b = *reinterpret_cast<const float4 *>(wl4 + off.w2 + ((grp * 2 + kk) * NT3 + nt) * 128);
+                            bh[nt][0] = __float_as_uint(b.x); bh[nt][1] = __float_as_uint(b.y); bl[nt][0] = __float_as_uint(b.z); bl[nt][1] = __float_as_uint(b.w);
                         }
 #pragma unroll
-                        for (int kk = 0; kk < 2; kk++) {
-                            uint32_t bh[NT3][2], bl[NT3][2];
+                        for (int mi = 0; mi < MTW; mi++)
 #pragma unroll
-                            for (int nt = 0; nt < NT3; nt++) {
-                                const float4 b = *reinterpret_cast<const float4 *>(wl4 + off.w2 + ((grp * 2 + kk) * NT3 + nt) * 128);
-                                bh[nt][0] = __float_as_uint(b.x); bh[nt][1] = __float_as_uint(b.y); bl[nt][0] = __float_as_uint(b.z); bl[nt][1] = __float_as_uint(b.w);
-                            }
+                            for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mi][nt], al[mi][kk], bh[nt][0], bh[nt][1]);
 #pragma unroll
-                            for (int mj = 0; mj < MH; mj++)
+                        for (int mi = 0; mi < MTW; mi++)
 #pragma unroll
-                                for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mh + mj][nt], al[mj][kk], bh[nt][0], bh[nt][1]);
+                            for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mi][nt], ah[mi][kk], bl[nt][0], bl[nt][1]);
 #pragma unroll
-                            for (int mj = 0; mj < MH; mj++)
+                        for (int mi = 0; mi < MTW; mi++)
 #pragma unroll
-                                for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mh + mj][nt], ah[mj][kk], bl[nt][0], bl[nt][1]);
-#pragma unroll
-                            for (int mj = 0; mj < MH; mj++)
-#pragma unroll
-                                for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mh + mj][nt], ah[mj][kk], bh[nt][0], bh[nt][1]);
-                        }
+                            for (int nt = 0; nt < NT3; nt++) mma_tf32(pacc[mi][nt], ah[mi][kk], bh[nt][0], bh[nt][1]);
                     }
                 }
             }
@@ -359,10 +366,11 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
         /* ---------------- block epilogue: BN + act [+ shortcut from the resident x tile] -> y ---------------- */
 #pragma unroll
         for (int mi = 0; mi < MTW; mi++) {
-            const int ty = tyx[mi] >> 16, tx = tyx[mi] & 0xffff;
+            const int qi = QUAD ? mi >> 1 : mi;
+            const int ty = (tyx[qi] >> 16) + (QUAD ? (mi & 1) : 0), tx = tyx[qi] & 0xffff;
             if (ty < q.th && tx < q.tw) {
                 float *yp = a.y + (((long)q.n * a.OH + q.oy0 + ty) * a.OW + q.ox0 + tx) * a.ldy;
-                const int xc = ((ty + 1 - a.yo) * a.XW + tx + 1 - a.xo) * SXs;           /* centre pixel; S == 1 whenever res is set */
+                const float *xc = sX + ((ty + 1 - a.yo) * a.XW + tx + 1 - a.xo) * SXs;   /* centre pixel; S == 1 whenever res is set */
 #pragma unroll
                 for (int nt = 0; nt < NT3; nt++) {
                     const int co = 8 * nt + 2 * t;
@@ -371,11 +379,10 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                         float2 v0, v1;
                         v0.x = slope_act(fmaf(pacc[mi][nt][0], s3.x, b3.x), a.slope3); v0.y = slope_act(fmaf(pacc[mi][nt][1], s3.y, b3.y), a.slope3);
                         v1.x = slope_act(fmaf(pacc[mi][nt][2], s3.x, b3.x), a.slope3); v1.y = slope_act(fmaf(pacc[mi][nt][3], s3.y, b3.y), a.slope3);
-                        if (a.res) {                      /* x = hi + lo exactly */
-                            const float2 h0 = *reinterpret_cast<const float2 *>(sX + xc + co), h1 = *reinterpret_cast<const float2 *>(sX + xc + SXs + co);
-                            const float2 l0 = *reinterpret_cast<const float2 *>(sXl + xc + co), l1 = *reinterpret_cast<const float2 *>(sXl + xc + SXs + co);
-                            v0.x = slope_act(v0.x + (h0.x + l0.x), a.slope_res); v0.y = slope_act(v0.y + (h0.y + l0.y), a.slope_res);
-                            v1.x = slope_act(v1.x + (h1.x + l1.x), a.slope_res); v1.y = slope_act(v1.y + (h1.y + l1.y), a.slope_res);
+                        if (a.res) {
+                            const float2 r0 = *reinterpret_cast<const float2 *>(xc + co), r1 = *reinterpret_cast<const float2 *>(xc + SXs + co);
+                            v0.x = slope_act(v0.x + r0.x, a.slope_res); v0.y = slope_act(v0.y + r0.y, a.slope_res);
+                            v1.x = slope_act(v1.x + r1.x, a.slope_res); v1.y = slope_act(v1.y + r1.y, a.slope_res);
                         }
                         *reinterpret_cast<float2 *>(yp + co) = v0;
                         *reinterpret_cast<float2 *>(yp + a.ldy + co) = v1;               /* tw is even: pixel tx+1 is inside the tile */

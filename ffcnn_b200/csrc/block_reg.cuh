@@ -1,0 +1,269 @@
+/*
+ * block_reg.cuh -- fused inverted-residual block for the high-resolution, low-channel layers (expanded width <= 24):
+ *
+ *     x --1x1 expand, BN, act--> e --3x3 depthwise (stride 1|2), BN, act--> d --1x1 project, BN, act--> [+ x] --> y
+ *
+ * (conv-v6.c:46-91 pointwise, 96-287 depthwise, ffcnn.c:412-423 dropout/shortcut -- the layers L1-L3, L4-L8, L9-L11 of
+ * yolo-fastest-1.1.)  At 160x160 these layers have so few channels that one pixel's whole expanded vector fits in a
+ * lane's registers, so nothing is staged anywhere: a warp owns a strip of 64 input columns and sweeps it top to bottom.
+ * Per input row each lane loads its two pixels of x, expands them with FFMAs whose weight operands come straight from
+ * the constant bank (the block's ~170-620 weights travel as a __grid_constant__ kernel parameter), fetches the
+ * expanded vectors of the two neighbouring columns with warp shuffles, and adds the row's taps to three rolling
+ * depthwise accumulators (the output rows above, at and below it).  The output row that just became complete is
+ * BN+activated, projected, optionally added to x (still in registers), and stored.  HBM sees x once and y once.
+ *
+ * Arithmetic is plain fp32 FFMA in the reference's tap order (ky, then kx: conv-v0.c:16-25).  Lanes 0 and 31 (lane 0
+ * only for stride 2) are halo lanes: they expand pixels for their neighbours but produce no output.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+#include "sm100.cuh"
+
+namespace ffb {
+
+template <int CIN, int CEXP, int COUT>
+struct RegBlockW {
+    /* every matrix is stored with the OUTPUT channel innermost: consecutive FFMAs of the unrolled loops then use
+       consecutive constants (one 128-bit uniform load feeds four) and independent accumulators (no dependent chains) */
+    float w1[CIN][CEXP], s1[CEXP], b1[CEXP];
+    float wd[9][CEXP], sd[CEXP], bd[CEXP];
+    float w2[CEXP][COUT], s3[COUT], b3[COUT];
+};
+
+struct RegBlockArgs {
+    const float *x; float *y;
+    int N, H, W, OH, OW, R, nsx, nsy;       /* R output rows per warp strip; nsx x nsy strips per frame */
+    float slope1, sloped, slope3, slope_res;
+};
+
+constexpr int REG_WARPS = 4;
+
+__device__ __forceinline__ float rb_act(float v, float slope) { return fmaxf(v, v * slope); }
+
+constexpr int RB_CH = 8;            /* expanded channels processed at a time: bounds the transient registers of a row step */
+
+/* expand channels [C0, C0 + RB_CH) of one pixel: e[c] = act(s1[c] * sum_k x[k] * w1[c][k] + b1[c]), or 0 outside the image
+ * (the depthwise conv's zero padding) */
+template <int C0, int CIN, int CEXP, int COUT>
+__device__ __forceinline__ void rb_expand(const RegBlockW<CIN, CEXP, COUT> &w, const float (&x)[CIN], bool inside, float slope, float (&e)[RB_CH])
+{
+#pragma unroll
+    for (int c = 0; c < RB_CH; c++) e[c] = x[0] * w.w1[0][C0 + c];
+#pragma unroll
+    for (int k = 1; k < CIN; k++)
+#pragma unroll
+        for (int c = 0; c < RB_CH; c++) e[c] = fmaf(x[k], w.w1[k][C0 + c], e[c]);
+#pragma unroll
+    for (int c = 0; c < RB_CH; c++) e[c] = inside ? rb_act(fmaf(e[c], w.s1[C0 + c], w.b1[C0 + c]), slope) : 0.f;
+}
+
+template <int CIN>
+__device__ __forceinline__ void rb_load(const float *p, bool ok, float (&x)[CIN])
+{
+#pragma unroll
+    for (int v = 0; v < CIN / 4; v++) {
+        const float4 t = ok ? __ldg(reinterpret_cast<const float4 *>(p) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * v] = t.x; x[4 * v + 1] = t.y; x[4 * v + 2] = t.z; x[4 * v + 3] = t.w;
+    }
+}
+
+/* d[C0 ..] (+)= taps of kernel row DY applied to the three horizontally adjacent expanded pixels l, m, r (channel chunk C0) */
+template <int DY, bool SET, int C0, int CIN, int CEXP, int COUT>
+__device__ __forceinline__ void rb_taps(const RegBlockW<CIN, CEXP, COUT> &w, float (&d)[CEXP], const float (&l)[RB_CH], const float (&m)[RB_CH], const float (&r)[RB_CH])
+{
+#pragma unroll
+    for (int c = 0; c < RB_CH; c++) d[C0 + c] = SET ? l[c] * w.wd[DY * 3][C0 + c] : fmaf(l[c], w.wd[DY * 3][C0 + c], d[C0 + c]);
+#pragma unroll
+    for (int c = 0; c < RB_CH; c++) d[C0 + c] = fmaf(m[c], w.wd[DY * 3 + 1][C0 + c], d[C0 + c]);
+#pragma unroll
+    for (int c = 0; c < RB_CH; c++) d[C0 + c] = fmaf(r[c], w.wd[DY * 3 + 2][C0 + c], d[C0 + c]);
+}
+
+/* finish one output pixel: BN + act of the depthwise sum, projection, BN + act, optional shortcut, store.
+ * PART splits a wide block into channel slices run as consecutive launches (the projection is a sum over expanded channels):
+ * 0 = whole block; 1 = first slice, store the raw partial sums; 2 = middle slice, add to them; 3 = last slice, add, BN + act. */
+template <bool RES, int PART, int CIN, int CEXP, int COUT>
+__device__ __forceinline__ void rb_finish(const RegBlockW<CIN, CEXP, COUT> &w, const RegBlockArgs &a, const float (&d)[CEXP], const float (&xc)[CIN], float *yp)
+{
+    float dd[CEXP];
+#pragma unroll
+    for (int c = 0; c < CEXP; c++) dd[c] = rb_act(fmaf(d[c], w.sd[c], w.bd[c]), a.sloped);
+    float o[COUT];
+    if (PART >= 2) {
+#pragma unroll
+        for (int v = 0; v < COUT / 4; v++) { const float4 t = reinterpret_cast<const float4 *>(yp)[v]; o[4 * v] = t.x; o[4 * v + 1] = t.y; o[4 * v + 2] = t.z; o[4 * v + 3] = t.w; }
+    }
+    if (PART < 2) {
+#pragma unroll
+        for (int co = 0; co < COUT; co++) o[co] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < CEXP; c++)
+#pragma unroll
+        for (int co = 0; co < COUT; co++) o[co] = fmaf(dd[c], w.w2[c][co], o[co]);
+#pragma unroll
+    for (int co = 0; co < COUT; co++) {
+        float s = o[co];
+        if (PART == 0 || PART == 3) s = rb_act(fmaf(s, w.s3[co], w.b3[co]), a.slope3);
+        if (RES) s = rb_act(s + xc[co < CIN ? co : 0], a.slope_res);
+        o[co] = s;
+    }
+#pragma unroll
+    for (int v = 0; v < COUT / 4; v++) reinterpret_cast<float4 *>(yp)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+}
+
+/* ------------------------------------------------------------------ stride 1: two output pixels per lane, 60 per warp */
+template <int CIN, int CEXP, int COUT, bool RES>
+__global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid_constant__ RegBlockW<CIN, CEXP, COUT> w, const RegBlockArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const long strip = (long)blockIdx.x * REG_WARPS + (threadIdx.x >> 5);
+    const int per_frame = a.nsx * a.nsy;
+    if (strip >= (long)a.N * per_frame) return;
+    const int n = (int)(strip / per_frame), sr = (int)(strip - (long)n * per_frame), sy = sr / a.nsx, sx = sr - sy * a.nsx;
+    const int ox_lo = sx * 60, oy0 = sy * a.R, oy1 = min(oy0 + a.R, a.OH);
+    const int ix0 = ox_lo - 2 + 2 * lane, ix1 = ix0 + 1;                       /* this lane's two columns */
+    const bool in0 = ix0 >= 0 && ix0 < a.W, in1 = ix1 >= 0 && ix1 < a.W;
+    const bool writes = lane >= 1 && lane <= 30 && ix0 < a.W;                   /* W is even: ix1 is inside whenever ix0 is */
+    const float *xf = a.x + (long)n * a.H * a.W * CIN;
+    float *yf = a.y + (long)n * a.OH * a.OW * COUT;
+    sm100::pdl_trigger(); sm100::pdl_wait();
+
+    float A0[CEXP], A1[CEXP], B0[CEXP], B1[CEXP], C0[CEXP], C1[CEXP];           /* three rolling output rows x two pixels */
+    float xc0[CIN], xc1[CIN], xn0[CIN], xn1[CIN], xp0[CIN], xp1[CIN];           /* x of the row in flight / the next row / the previous row */
+#pragma unroll
+    for (int c = 0; c < CEXP; c++) { A0[c] = A1[c] = B0[c] = B1[c] = C0[c] = C1[c] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < CIN; k++) xp0[k] = xp1[k] = 0.f;
+    {
+        const int r = oy0 - 1; const bool rok = r >= 0;
+        rb_load<CIN>(xf + ((long)max(r, 0) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
+        rb_load<CIN>(xf + ((long)max(r, 0) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
+    }
+    /* one input row: dm = output row r-1 (gets kernel row 2 and is finished), d0 = row r (kernel row 1), dp = row r+1 (kernel row 0, first contribution) */
+    auto step = [&](int r, float (&dm0)[CEXP], float (&dm1)[CEXP], float (&d00)[CEXP], float (&d01)[CEXP], float (&dp0)[CEXP], float (&dp1)[CEXP]) {
+        /* expand -> neighbour exchange -> taps, RB_CH channels at a time */
+        auto chunk = [&](auto c0, bool rin) {
+            constexpr int C0 = decltype(c0)::value;
+            float e0[RB_CH], e1[RB_CH], el[RB_CH], er[RB_CH];
+            rb_expand<C0>(w, xc0, rin && in0, a.slope1, e0);
+            rb_expand<C0>(w, xc1, rin && in1, a.slope1, e1);
+#pragma unroll
+            for (int c = 0; c < RB_CH; c++) { el[c] = __shfl_up_sync(0xffffffffu, e1[c], 1); er[c] = __shfl_down_sync(0xffffffffu, e0[c], 1); }
+            rb_taps<2, false, C0>(w, dm0, el, e0, e1); rb_taps<2, false, C0>(w, dm1, e0, e1, er);
+            rb_taps<1, false, C0>(w, d00, el, e0, e1); rb_taps<1, false, C0>(w, d01, e0, e1, er);
+            rb_taps<0, true, C0>(w, dp0, el, e0, e1);  rb_taps<0, true, C0>(w, dp1, e0, e1, er);
+        };
+#pragma unroll
+        for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; }
+        {   /* prefetch the next row's x while this one is being expanded */
+            const int rn = r + 1; const bool rok = rn < a.H && rn <= oy1;
+            rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
+            rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
+        }
+        const bool rin = r >= 0 && r < a.H;
+        chunk(std::integral_constant<int, 0>(), rin);
+        if constexpr (CEXP > 8)  chunk(std::integral_constant<int, 8>(), rin);
+        if constexpr (CEXP > 16) chunk(std::integral_constant<int, 16>(), rin);
+        const int oy = r - 1;
+        if (writes && oy >= oy0 && oy < oy1) {
+            float *yp = yf + ((long)oy * a.OW + ix0) * COUT;
+            rb_finish<RES, 0>(w, a, dm0, xp0, yp);
+            rb_finish<RES, 0>(w, a, dm1, xp1, yp + COUT);
+        }
+#pragma unroll
+        for (int k = 0; k < CIN; k++) { xp0[k] = xc0[k]; xp1[k] = xc1[k]; }
+    };
+    /* rows are taken three at a time with no branch around the steps (a warp shuffle under a branch the compiler cannot
+       prove uniform costs four extra synchronisation instructions each); rows past the strip load zeros and write nothing */
+    for (int r = oy0 - 1; r <= oy1; r += 3) {
+        step(r, A0, A1, B0, B1, C0, C1);
+        step(r + 1, B0, B1, C0, C1, A0, A1);
+        step(r + 2, C0, C1, A0, A1, B0, B1);
+    }
+}
+
+/* ------------------------------------------------------------------ stride 2: one output pixel per lane, 31 per warp */
+template <int CIN, int CEXP, int COUT, int PART>
+__global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid_constant__ RegBlockW<CIN, CEXP, COUT> w, const RegBlockArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const long strip = (long)blockIdx.x * REG_WARPS + (threadIdx.x >> 5);
+    const int per_frame = a.nsx * a.nsy;
+    if (strip >= (long)a.N * per_frame) return;
+    const int n = (int)(strip / per_frame), sr = (int)(strip - (long)n * per_frame), sy = sr / a.nsx, sx = sr - sy * a.nsx;
+    const int ox = sx * 31 + lane - 1, oy0 = sy * a.R, oy1 = min(oy0 + a.R, a.OH);
+    const int ix0 = 2 * ox, ix1 = ix0 + 1;                                      /* centre and right tap columns; the left tap comes from lane - 1 */
+    const bool in0 = ix0 >= 0 && ix0 < a.W, in1 = ix1 >= 0 && ix1 < a.W;
+    const bool writes = lane >= 1 && ox < a.OW;
+    const float *xf = a.x + (long)n * a.H * a.W * CIN;
+    float *yf = a.y + (long)n * a.OH * a.OW * COUT;
+    sm100::pdl_trigger(); sm100::pdl_wait();
+
+    float A[CEXP], B[CEXP];                                                     /* output rows oy and oy + 1 */
+    float xc0[CIN], xc1[CIN], xn0[CIN], xn1[CIN];
+#pragma unroll
+    for (int c = 0; c < CEXP; c++) A[c] = B[c] = 0.f;
+    const int r_first = 2 * oy0 - 1, r_last = 2 * (oy1 - 1) + 1;
+    {
+        const bool rok = r_first >= 0;
+        rb_load<CIN>(xf + ((long)max(r_first, 0) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
+        rb_load<CIN>(xf + ((long)max(r_first, 0) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
+    }
+    const float dummy[CIN] = {};
+    auto fetch_row = [&](int r) {                                               /* xc <- row r, prefetch row r + 1 */
+#pragma unroll
+        for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; }
+        const int rn = r + 1; const bool rok = rn < a.H && rn <= r_last;
+        rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
+        rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
+    };
+    /* odd input row 2oy-1: kernel row 2 of output row oy-1 (cur) and kernel row 0 of output row oy (nxt), RB_CH channels at a time */
+    auto odd_chunk = [&](auto c0, bool rin, float (&cur)[CEXP], float (&nxt)[CEXP]) {
+        constexpr int C0 = decltype(c0)::value;
+        float e0[RB_CH], e1[RB_CH], el[RB_CH];
+        rb_expand<C0>(w, xc0, rin && in0, a.slope1, e0);
+        rb_expand<C0>(w, xc1, rin && in1, a.slope1, e1);
+#pragma unroll
+        for (int c = 0; c < RB_CH; c++) el[c] = __shfl_up_sync(0xffffffffu, e1[c], 1);
+        rb_taps<2, false, C0>(w, cur, el, e0, e1);
+        rb_taps<0, true, C0>(w, nxt, el, e0, e1);
+    };
+    auto even_chunk = [&](auto c0, bool rin, float (&nxt)[CEXP]) {              /* even input row 2oy: kernel row 1 of output row oy */
+        constexpr int C0 = decltype(c0)::value;
+        float e0[RB_CH], e1[RB_CH], el[RB_CH];
+        rb_expand<C0>(w, xc0, rin && in0, a.slope1, e0);
+        rb_expand<C0>(w, xc1, rin && in1, a.slope1, e1);
+#pragma unroll
+        for (int c = 0; c < RB_CH; c++) el[c] = __shfl_up_sync(0xffffffffu, e1[c], 1);
+        rb_taps<1, false, C0>(w, nxt, el, e0, e1);
+    };
+    /* rows come in (odd, even) pairs: odd row 2oy-1 closes output row oy-1 and opens row oy; even row 2oy is row oy's centre */
+    auto pair = [&](int oy, float (&cur)[CEXP], float (&nxt)[CEXP]) {
+        {
+            const int r = 2 * oy - 1; const bool rin = r >= 0 && r < a.H;
+            fetch_row(r);
+            /* the closing taps of `cur` must be complete before it is finished, the opening taps of `nxt` are independent:
+               chunks are run for both, then `cur` is finished */
+            odd_chunk(std::integral_constant<int, 0>(), rin, cur, nxt);
+            if constexpr (CEXP > 8)  odd_chunk(std::integral_constant<int, 8>(), rin, cur, nxt);
+            if constexpr (CEXP > 16) odd_chunk(std::integral_constant<int, 16>(), rin, cur, nxt);
+            if (writes && oy - 1 >= oy0 && oy - 1 < oy1) rb_finish<false, PART>(w, a, cur, dummy, yf + ((long)(oy - 1) * a.OW + ox) * COUT);
+        }
+        {
+            const int r = 2 * oy; const bool rin = r < a.H && oy < oy1;
+            fetch_row(r);
+            even_chunk(std::integral_constant<int, 0>(), rin, nxt);
+            if constexpr (CEXP > 8)  even_chunk(std::integral_constant<int, 8>(), rin, nxt);
+            if constexpr (CEXP > 16) even_chunk(std::integral_constant<int, 16>(), rin, nxt);
+        }
+    };
+    for (int oy = oy0; oy <= oy1; oy += 2) {                                   /* no branch around the pairs: see k_block_reg_s1 */
+        pair(oy, A, B);
+        pair(oy + 1, B, A);
+    }
+}
+
+} // namespace ffb

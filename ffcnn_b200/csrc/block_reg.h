@@ -1,0 +1,13 @@
+/* block_reg.h -- host interface of the register-resident fused block kernel (block_reg.cuh / block_reg.cu). */
+#pragma once
+#include <cuda_runtime.h>
+
+struct RegPlan;
+/* Same contract as blk_plan_create (block_mma.h) for the low-channel blocks (expanded width <= 24).  h1 / hd / h3: HOST
+ * pointers to the packed reference rows (ffcnn.c:218-234) of the expand, depthwise and projection convs: the weights
+ * travel as a kernel parameter.  Returns NULL when the shape has no instantiated kernel. */
+RegPlan *reg_plan_create(int cin, int cexp, int cout, int stride, int h, int w, int act1, int actd, int act3, int res, int act_res,
+                         const float *h1, const float *hd, const float *h3);
+void     reg_plan_destroy(RegPlan *p);
+int      reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st);
+const char *reg_describe(const RegPlan *p);

@@ -31,6 +31,7 @@
 #include "dw_tma.cuh"
 #include "pw_tc.h"
 #include "block_mma.h"
+#include "block_reg.h"
 
 using namespace ffb;
 
@@ -345,7 +346,7 @@ struct ffb_engine {
     int fuse_shortcut = 1;
     /* fused inverted-residual blocks (block_mma.cu): expand conv `first`, depthwise first+1, projection first+2 and, when
        sc >= 0, the shortcut layer sc run as ONE kernel launched in the slot of layer `first` */
-    struct Block { int first, sc; BlkPlan *plan; };
+    struct Block { int first, sc; BlkPlan *plan; RegPlan *reg; };      /* exactly one of plan (block_mma.cu) / reg (block_reg.cu) is set */
     std::vector<Block> blocks;
     std::vector<int> blk_at;                /* per layer: index into blocks if the layer is a block's first conv, else -1 */
     std::vector<char> in_block;             /* per layer: computed inside a block (its own launch slot is empty) */
@@ -406,7 +407,7 @@ void ffb_engine_destroy(ffb_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     engine_free_plan(e);
     for (ffb_conv *c : e->convs) conv_release(c);
-    for (ffb_engine::Block &b : e->blocks) blk_plan_destroy(b.plan);
+    for (ffb_engine::Block &b : e->blocks) { blk_plan_destroy(b.plan); reg_plan_destroy(b.reg); }
     cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_cand); cudaFree(e->d_count); cudaFree(e->d_flush);
     cudaFreeHost(e->h_stage); cudaFreeHost(e->h_cand); cudaFreeHost(e->h_count);
     for (int i = 0; i < 2; i++) { cudaFree(e->d_slot[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]); }
@@ -442,7 +443,7 @@ static std::vector<int> count_readers(const NET *net)
 static int engine_find_blocks(ffb_engine *e)
 {
     NET *net = &e->net->pub; const int L = net->layer_num;
-    for (ffb_engine::Block &b : e->blocks) blk_plan_destroy(b.plan);
+    for (ffb_engine::Block &b : e->blocks) { blk_plan_destroy(b.plan); reg_plan_destroy(b.reg); }
     e->blocks.clear(); e->blk_at.assign(L, -1); e->in_block.assign(L, 0);
     if (!e->fuse_block) return 0;
     const std::vector<int> readers = count_readers(net);
@@ -460,18 +461,25 @@ static int engine_find_blocks(ffb_engine *e)
                 producer_of(net, sl->depend_list[0]) == producer_of(net, i - 1) && d->stride == 1 && a->c == p->fn) { sc = j; act_res = sl->activation; }
             break;
         }
-        /* fuse_block 1 (default): only the block shapes where the fused kernel beats the three separate layers on a B200
-           (measured, profiles/r1j_block_fusion.txt): the shared-memory-staged design loses on the 160x160 blocks (8-24
-           expanded channels: too little work per staged byte) and on 136 expanded channels; 2: every supported block */
-        const bool wanted = e->fuse_block >= 2 || a->fn == 32 || a->fn == 48 || (a->fn == 96 && d->stride == 1) || a->fn == 224;
-        if (!wanted) continue;
-        BlkPlan *plan = blk_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res);
-        if (!plan) continue;
-        if (blk_prepare(plan, e->convs[i]->d_packed, e->convs[i + 1]->d_packed, e->convs[i + 2]->d_packed, e->stream) != 0) { blk_plan_destroy(plan); return -1; }
+        /* two fused kernels: the register-resident one (block_reg.cu) for the 160x160 blocks with <= 24 expanded channels,
+           the shared-memory / tensor-core one (block_mma.cu) for the rest.  fuse_block 1 (default) uses the latter only for
+           the block shapes where it beats the three separate layers on a B200 (measured, profiles/r1k_block_fusion.txt: it
+           loses at 136 expanded channels and on the stride-2 96-channel block); 2: every supported block; 3: block_mma only */
+        BlkPlan *plan = nullptr; RegPlan *reg = nullptr;
+        if (e->fuse_block != 3)
+            reg = reg_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res,
+                                  a->filter, d->filter, p->filter);
+        if (!reg) {
+            const bool wanted = e->fuse_block >= 2 || a->fn == 32 || a->fn == 48 || (a->fn == 96 && d->stride == 1) || a->fn == 224;
+            if (!wanted) continue;
+            plan = blk_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res);
+            if (!plan) continue;
+            if (blk_prepare(plan, e->convs[i]->d_packed, e->convs[i + 1]->d_packed, e->convs[i + 2]->d_packed, e->stream) != 0) { blk_plan_destroy(plan); return -1; }
+        }
         e->blk_at[i] = (int)e->blocks.size(); e->in_block[i + 1] = e->in_block[i + 2] = 1;
         if (sc >= 0) e->in_block[sc] = 1;
-        e->blocks.push_back({ i, sc, plan });
-        if (getenv("FFCNN_BLK_VERBOSE")) fprintf(stderr, "ffcnn_b200: block L%d-L%d: %s\n", i, sc >= 0 ? sc : i + 2, blk_describe(plan));
+        e->blocks.push_back({ i, sc, plan, reg });
+        if (getenv("FFCNN_BLK_VERBOSE")) fprintf(stderr, "ffcnn_b200: block L%d-L%d: %s\n", i, sc >= 0 ? sc : i + 2, plan ? blk_describe(plan) : reg_describe(reg));
         i += 2;
     }
     return 0;
@@ -826,7 +834,7 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         if (e->in_block[i]) return 0;                          /* computed by the block kernel launched in an earlier slot */
         if (e->blk_at[i] >= 0) {
             const ffb_engine::Block &b = e->blocks[e->blk_at[i]]; const Tens &y = e->outs[i + 2];
-            if (blk_run(b.plan, in.p, in.ld, y.p, y.ld, n, st) != 0) return -1;
+            if ((b.plan ? blk_run(b.plan, in.p, in.ld, y.p, y.ld, n, st) : reg_run(b.reg, in.p, in.ld, y.p, y.ld, n, st)) != 0) return -1;
             (*launches)++;
             return 0;
         }
@@ -1145,7 +1153,7 @@ int ffb_layer_cost(NET *net, int i, double *bytes, double *flops, char *kname, i
             g_cost_recursing = true;
             for (int k = i + 1; k <= (b.sc >= 0 ? b.sc : i + 2); k++) { double b2 = 0, f2 = 0; ffb_layer_cost(net, k, &b2, &f2, NULL, 0); by += b2; fl += f2; }
             g_cost_recursing = false;
-            nm = "block_mma_3xtf32";
+            nm = b.plan ? "block_mma_3xtf32" : "block_reg_fp32";
         }
     }
     if (bytes) *bytes = by;
