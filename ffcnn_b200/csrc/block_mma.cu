@@ -66,6 +66,16 @@ static bool plan_tile(BlkPlan *p)
     int fTH = 0, fTW = 0, fGC = 0;
     char key[64]; snprintf(key, sizeof key, "FFCNN_BLK_TILE_%d_%d", p->OH, p->cexp);      /* developer override for tile sweeps (tools/blk_sweep.py) */
     if (const char *ov = getenv(key)) sscanf(ov, "%d,%d,%d", &fTH, &fTW, &fGC);
+    else {
+        /* tiles measured best on a B200 at batch 256 (tools/blk_sweep.py, profiles/r1k_block_tile_sweep.txt); the cost
+           model below covers every other shape */
+        static const struct { int oh, ow, cexp, s, th, tw, gc; } best_tiles[] = {
+            { 80, 80, 32, 1, 16, 16, 2 }, { 40, 40, 32, 2, 4, 20, 2 }, { 40, 40, 48, 1, 8, 20, 3 }, { 40, 40, 96, 1, 8, 20, 2 },
+            { 20, 20, 96, 2, 10, 10, 3 }, { 20, 20, 136, 1, 10, 20, 3 },
+        };
+        for (const auto &b : best_tiles)
+            if (b.oh == p->OH && b.ow == p->OW && b.cexp == p->cexp && b.s == S) { fTH = b.th; fTW = b.tw; fGC = b.gc; }
+    }
     double best = 1e30; bool ok = false;
     for (int GC = 1; GC <= G && GC <= 4; GC++) {
         if (G % GC || (fGC && GC != fGC)) continue;

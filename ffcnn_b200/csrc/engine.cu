@@ -330,7 +330,8 @@ static int stem_run_u8(ffb_conv *op, const unsigned char *frames, int pitch, flo
 
 /* =================================================================================== engine */
 
-struct Tens { int buf = -1; float *p = nullptr; int h = 0, w = 0, c = 0, ld = 0; size_t frame_floats() const { return (size_t)h * w * ld; } };
+struct Tens { int buf = -1; float *p = nullptr; int h = 0, w = 0, c = 0, ld = 0, coff = 0;   /* coff: channel offset inside a wider (concat) buffer */
+              size_t frame_floats() const { return (size_t)h * w * ld; } };
 
 struct Buf { size_t floats = 0, offset = 0; int first = 0, last = 0; };
 
@@ -351,6 +352,13 @@ struct ffb_engine {
     std::vector<int> blk_at;                /* per layer: index into blocks if the layer is a block's first conv, else -1 */
     std::vector<char> in_block;             /* per layer: computed inside a block (its own launch slot is empty) */
     int fuse_block = 1;
+    /* tail fusions: the SPP block (three max pools of one tensor + their route) as one kernel launched in the route's
+       slot, and upsample layers that write straight into the concat tensor of the route that reads them */
+    struct Spp { int route, x, r[3], off[3], offx; };
+    std::vector<Spp> spps;
+    std::vector<int> spp_at, up_into;       /* per layer: index into spps (route layers) / the route an upsample writes into, else -1 */
+    std::vector<char> in_spp;               /* pool layers computed by the SPP kernel */
+    int fuse_tail = 1;
     Tens input;
     std::vector<Buf> bufs;
     float *d_arena = nullptr; size_t arena_floats = 0;
@@ -464,13 +472,13 @@ static int engine_find_blocks(ffb_engine *e)
         /* two fused kernels: the register-resident one (block_reg.cu) for the 160x160 blocks with <= 24 expanded channels,
            the shared-memory / tensor-core one (block_mma.cu) for the rest.  fuse_block 1 (default) uses the latter only for
            the block shapes where it beats the three separate layers on a B200 (measured, profiles/r1k_block_fusion.txt: it
-           loses at 136 expanded channels and on the stride-2 96-channel block); 2: every supported block; 3: block_mma only */
+           loses on the stride-2 136-channel block); 2: every supported block; 3: block_mma only */
         BlkPlan *plan = nullptr; RegPlan *reg = nullptr;
         if (e->fuse_block != 3)
             reg = reg_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res,
                                   a->filter, d->filter, p->filter);
         if (!reg) {
-            const bool wanted = e->fuse_block >= 2 || a->fn == 32 || a->fn == 48 || (a->fn == 96 && d->stride == 1) || a->fn == 224;
+            const bool wanted = e->fuse_block >= 2 || a->fn == 32 || a->fn == 48 || a->fn == 96 || (a->fn == 136 && d->stride == 1) || a->fn == 224;
             if (!wanted) continue;
             plan = blk_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res);
             if (!plan) continue;
@@ -519,6 +527,45 @@ static int engine_plan(ffb_engine *e)
             e->fuse_sc[p] = j; e->fused_away[j] = 1;
         }
     }
+    e->spps.clear(); e->spp_at.assign(L, -1); e->up_into.assign(L, -1); e->in_spp.assign(L, 0);
+    std::vector<int> up_coff(L, 0), route_buf(L, -1);
+    if (fuse && e->fuse_tail) {
+        const std::vector<int> readers = count_readers(net);
+        for (int j = 1; j < L; j++) {
+            const LAYER *rl = net->layer_list + j;
+            if (rl->type != LAYER_TYPE_ROUTE || rl->depend_num < 2) continue;
+            /* SPP: exactly three stride-1 odd max pools of X plus X itself, each pool read by nothing else */
+            int pools[4], npool = 0, xdep = -1, coff[4], acc = 0; bool ok = rl->depend_num == 4;
+            for (int d = 0; d < rl->depend_num && ok; d++) {
+                const int q = producer_of(net, rl->depend_list[d]); const LAYER *ql = net->layer_list + q;
+                coff[d] = acc; acc += net->layer_list[q + 1].c;
+                if (ql->type == LAYER_TYPE_MAXPOOL && ql->stride == 1 && (ql->fs & 1) && readers[q] == 1 && ql->c % 4 == 0) pools[npool++] = d;
+                else if (xdep < 0) xdep = d; else ok = false;
+            }
+            if (ok && npool == 3 && xdep >= 0) {
+                const int X = producer_of(net, rl->depend_list[xdep]);
+                ffb_engine::Spp sp; sp.route = j; sp.x = X; sp.offx = coff[xdep];
+                for (int a = 0; a < 3 && ok; a++) {
+                    const int q = producer_of(net, rl->depend_list[pools[a]]);
+                    if (q < 1 || producer_of(net, q - 1) != X) ok = false;
+                    sp.r[a] = (net->layer_list[q].fs - 1) / 2; sp.off[a] = coff[pools[a]];
+                }
+                for (int a = 0; a < 3; a++) for (int b = a + 1; b < 3; b++) if (sp.r[b] < sp.r[a]) { std::swap(sp.r[a], sp.r[b]); std::swap(sp.off[a], sp.off[b]); }
+                if (ok && sp.r[0] < sp.r[1] && sp.r[1] < sp.r[2]) {
+                    e->spp_at[j] = (int)e->spps.size(); e->spps.push_back(sp);
+                    for (int a = 0; a < 3; a++) e->in_spp[producer_of(net, rl->depend_list[pools[a]])] = 1;
+                    continue;
+                }
+            }
+            /* an upsample read only by this route writes its pixels straight into the concat tensor */
+            acc = 0;
+            for (int d = 0; d < rl->depend_num; d++) {
+                const int q = producer_of(net, rl->depend_list[d]); const LAYER *ql = net->layer_list + q;
+                if (ql->type == LAYER_TYPE_UPSAMPLE && readers[q] == 1 && acc % 4 == 0 && ql->c % 4 == 0 && e->up_into[q] < 0) { e->up_into[q] = j; up_coff[q] = acc; }
+                acc += net->layer_list[q + 1].c;
+            }
+        }
+    }
     int blk_buf = -1;                                           /* output buffer of the block being walked through */
     for (int i = 0; i < L; i++) {
         const LAYER *il = net->layer_list + i, *ol = il + 1;
@@ -537,6 +584,15 @@ static int engine_plan(ffb_engine *e)
             else if (il->type == LAYER_TYPE_SHORTCUT) { o = in_of(i); touch(o, i); }                           /* fused shortcut: same tensor */
             continue;                                            /* depthwise: no buffer */
         }
+        if (e->in_spp[i]) { touch(in_of(i), i); continue; }      /* pool inside the SPP kernel: never materialised */
+        if (e->up_into[i] >= 0) {
+            /* the route's concat buffer is created here, at its first writer; this layer's tensor is a channel window of it */
+            const int j = e->up_into[i]; const LAYER *jo = net->layer_list + j + 1;
+            if (route_buf[j] < 0) route_buf[j] = new_buf((size_t)jo->h * jo->w * FFB_ALIGN(jo->c, 4), i);
+            o.buf = route_buf[j]; o.ld = FFB_ALIGN(jo->c, 4); o.coff = up_coff[i];
+            touch(in_of(i), i); touch(o, i);
+            continue;
+        }
         if (il->type == LAYER_TYPE_CONV && e->fuse_sc[i] >= 0) {
             /* the conv writes the shortcut's tensor: one buffer, created now, named by both layers */
             o.buf = new_buf(o.frame_floats(), i); touch(in_of(i), i); touch(e->outs[net->layer_list[e->fuse_sc[i]].depend_list[0]], i); touch(o, i);
@@ -547,8 +603,9 @@ static int engine_plan(ffb_engine *e)
         case LAYER_TYPE_DROPOUT: o = in_of(i); break;                               /* alias */
         case LAYER_TYPE_ROUTE:
             if (il->depend_num == 1) { o = e->outs[il->depend_list[0]]; break; }   /* alias */
-            o.buf = new_buf(o.frame_floats(), i);
+            o.buf = route_buf[i] >= 0 ? route_buf[i] : new_buf(o.frame_floats(), i);
             for (int d = 0; d < il->depend_num; d++) touch(e->outs[il->depend_list[d]], i);
+            if (e->spp_at[i] >= 0) touch(e->outs[e->spps[e->spp_at[i]].x], i);
             break;
         case LAYER_TYPE_YOLO: o = Tens(); touch(in_of(i), 1 << 30); break;          /* heads stay alive for ffb_detect */
         case LAYER_TYPE_SHORTCUT:
@@ -589,7 +646,7 @@ static int engine_plan(ffb_engine *e)
     CK(cudaMalloc(&e->d_arena, top * sizeof(float)));
     CK(cudaMemsetAsync(e->d_arena, 0, top * sizeof(float), e->stream));
     e->input.p = e->d_arena + bufs[e->input.buf].offset;
-    for (Tens &t : e->outs) if (t.buf >= 0) t.p = e->d_arena + bufs[t.buf].offset;
+    for (Tens &t : e->outs) if (t.buf >= 0) t.p = e->d_arena + bufs[t.buf].offset + t.coff;
     e->plan_dirty = false;
     return 0;
 }
@@ -705,6 +762,7 @@ int ffb_set_option(NET *net, const char *name, int value)
     else if (!strcmp(name, "fuse_shortcut")) { if (e->fuse_shortcut != value) e->plan_dirty = true; e->fuse_shortcut = value; }
     else if (!strcmp(name, "keep_all"))  { if (e->keep_all != value) e->plan_dirty = true; e->keep_all = value; }
     else if (!strcmp(name, "fuse_block")) { reweight = e->fuse_block != value; e->fuse_block = value; }
+    else if (!strcmp(name, "fuse_tail")) { if (e->fuse_tail != value) e->plan_dirty = true; e->fuse_tail = value; }
     else { ffb_set_error("unknown option '%s'", name); return -1; }
     if (reweight) {
         CK(cudaSetDevice(e->device));
@@ -728,6 +786,7 @@ int ffb_get_option(NET *net, const char *name)
     if (!strcmp(name, "fuse_shortcut")) return e->fuse_shortcut;
     if (!strcmp(name, "keep_all")) return e->keep_all;
     if (!strcmp(name, "fuse_block")) return e->fuse_block;
+    if (!strcmp(name, "fuse_tail")) return e->fuse_tail;
     if (!strcmp(name, "blocks")) return (int)e->blocks.size();
     if (!strcmp(name, "max_batch")) return e->max_batch;
     if (!strcmp(name, "batch")) return e->batch;
@@ -850,6 +909,7 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         (*launches)++;
         break;
     case LAYER_TYPE_MAXPOOL: case LAYER_TYPE_AVGPOOL:
+        if (e->keep_all != 1 && (int)e->in_spp.size() > i && e->in_spp[i]) break;      /* computed by the SPP kernel in the route's slot */
         if (in.c % 4) { ffb_set_error("pool layer %d: channels %d not a multiple of 4", i, in.c); return -1; }
         CK(launch_pdl(k_pool, dim3(grid_for((long)n * o.h * o.w * (o.c / 4), 128)), dim3(128), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.h, o.w, o.ld, 0,
                       il->fs, il->stride, (int)(il->type == LAYER_TYPE_MAXPOOL)));
@@ -869,10 +929,23 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         (*launches)++;
         break; }
     case LAYER_TYPE_ROUTE:
-        if (il->depend_num > 1) {
+        if (il->depend_num > 1 && e->keep_all != 1 && (int)e->spp_at.size() > i && e->spp_at[i] >= 0) {
+            const ffb_engine::Spp &sp = e->spps[e->spp_at[i]]; const Tens &x = e->outs[sp.x];
+            const size_t spp_bytes = (size_t)4 * x.h * x.w * x.c * sizeof(float);
+            static size_t spp_configured = 0;
+            if (spp_bytes <= 200 * 1024) {                     /* frame fits in shared memory: separable version, one CTA per frame */
+                if (spp_bytes > spp_configured) { CK(cudaFuncSetAttribute(k_spp_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spp_bytes)); spp_configured = spp_bytes; }
+                CK(launch_pdl(k_spp_smem, dim3(n), dim3(256), spp_bytes, st, (const float *)x.p, o.p, x.h, x.w, x.c, x.ld, o.ld,
+                              sp.r[0], sp.r[1], sp.r[2], sp.off[0], sp.off[1], sp.off[2], sp.offx));
+            } else
+                CK(launch_pdl(k_spp, dim3(grid_for((long)n * x.h * x.w * (x.c / 4), 128, 16)), dim3(128), 0, st, (const float *)x.p, o.p, n, x.h, x.w, x.c, x.ld, o.ld,
+                              sp.r[0], sp.r[1], sp.r[2], sp.off[0], sp.off[1], sp.off[2], sp.offx));
+            (*launches)++;
+        } else if (il->depend_num > 1) {
             int coff = 0;
             for (int d = 0; d < il->depend_num; d++) {
                 const Tens &s = e->outs[il->depend_list[d]];
+                if (s.buf == o.buf && s.buf >= 0) { coff += s.c; continue; }          /* written in place by its producer (upsample into concat) */
                 const long px = (long)n * s.h * s.w;
                 if (s.c % 4 == 0 && coff % 4 == 0) CK(launch_pdl(k_concat, dim3(grid_for(px * (s.c / 4), 256)), dim3(256), 0, st, (const float *)s.p, o.p, px, s.c, s.ld, o.ld, coff));
                 else CK(launch_pdl(k_copy_strided, dim3(grid_for(px * s.c, 256)), dim3(256), 0, st, (const float *)s.p, o.p, px, s.c, s.ld, o.ld, coff));
@@ -1118,7 +1191,7 @@ long ffb_layer_output(NET *net, int layer, int frame, float *chw, long capacity)
     CK(cudaSetDevice(e->device));
     std::vector<float> tmp(t.frame_floats());
     CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(tmp.data(), t.p + (size_t)frame * t.frame_floats(), tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tmp.data(), t.p + (size_t)frame * t.frame_floats(), (tmp.size() - t.coff) * sizeof(float), cudaMemcpyDeviceToHost));
     const size_t plane = (size_t)t.h * t.w;
     for (int c = 0; c < t.c; c++) for (size_t p = 0; p < plane; p++) chw[c * plane + p] = tmp[p * t.ld + c];
     return count;
@@ -1144,6 +1217,16 @@ int ffb_layer_cost(NET *net, int i, double *bytes, double *flops, char *kname, i
     }
     ffb_net *fn = ffb_from_pub(net);
     if (a->type == LAYER_TYPE_CONV && fn->engine && fn->engine->convs[i]) nm = fn->engine->convs[i]->name;
+    if (fn->engine && fn->engine->keep_all != 1 && (int)fn->engine->spp_at.size() > i && !g_cost_recursing) {
+        ffb_engine *e = fn->engine;
+        if (e->in_spp[i]) { by = 0; fl = 0; nm = "in_spp"; }
+        else if (e->spp_at[i] >= 0) {                          /* the SPP kernel: its three pools + the route, reported in the route's slot */
+            g_cost_recursing = true;
+            for (int k = 0; k < net->layer_num; k++) if (e->in_spp[k]) { double b2 = 0, f2 = 0; ffb_layer_cost(net, k, &b2, &f2, NULL, 0); by += b2; fl += f2; }
+            g_cost_recursing = false;
+            nm = "spp_fused";
+        }
+    }
     if (fn->engine && fn->engine->keep_all != 1 && fn->engine->fuse_block && (int)fn->engine->blk_at.size() > i && !g_cost_recursing) {
         /* a fused block is reported in its first layer's slot with the summed (unfused) algorithmic cost of its layers */
         ffb_engine *e = fn->engine;

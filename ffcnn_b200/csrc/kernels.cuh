@@ -355,6 +355,83 @@ __global__ void k_pool(const float *__restrict__ in, float *__restrict__ out, in
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * SPP block in one pass: three stride-1 max pools of the SAME tensor (radii r1 < r2 < r3, reference windows
+ * [x-(fs-1)/2, +fs) cut to the image, ffcnn.c:354-394) plus the route that concatenates them with the tensor itself
+ * (ffcnn.c:425-434) -- layers L109-L114 of yolo-fastest-1.1.  One thread per (pixel, 4 channels): the (2*r3+1)^2 window
+ * is read once (L1-resident: a 10x10x48 frame is 19 KB) and feeds the three nested maxima; the four results go straight
+ * to their channel offsets of the concat tensor.  max is exact, so nesting the windows changes nothing.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void k_spp(const float *__restrict__ in, float *__restrict__ out, int n, int H, int W, int C, int ldi, int ldo,
+                      int r1, int r2, int r3, int off1, int off2, int off3, int offx)
+{
+    pdl_trigger(); pdl_wait();
+    const int c4n = C / 4;
+    const long total = (long)n * H * W * c4n;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4; long p = i / c4n;
+        const int x = (int)(p % W); p /= W;
+        const int y = (int)(p % H); const long f = p / H;
+        const float *img = in + f * (long)H * W * ldi + c;
+        const float4 ctr = ldg4(img + ((long)y * W + x) * ldi);
+        float4 m1 = ctr, m2 = ctr, m3 = ctr;
+        const int ya = max(y - r3, 0), yb = min(y + r3, H - 1), xa = max(x - r3, 0), xb = min(x + r3, W - 1);
+        for (int yy = ya; yy <= yb; yy++) {
+            const int ady = abs(yy - y);
+            for (int xx = xa; xx <= xb; xx++) {
+                const float4 v = ldg4(img + ((long)yy * W + xx) * ldi);
+                const int d = max(ady, abs(xx - x));
+                m3.x = fmaxf(m3.x, v.x); m3.y = fmaxf(m3.y, v.y); m3.z = fmaxf(m3.z, v.z); m3.w = fmaxf(m3.w, v.w);
+                if (d <= r2) { m2.x = fmaxf(m2.x, v.x); m2.y = fmaxf(m2.y, v.y); m2.z = fmaxf(m2.z, v.z); m2.w = fmaxf(m2.w, v.w); }
+                if (d <= r1) { m1.x = fmaxf(m1.x, v.x); m1.y = fmaxf(m1.y, v.y); m1.z = fmaxf(m1.z, v.z); m1.w = fmaxf(m1.w, v.w); }
+            }
+        }
+        float *o = out + (f * (long)H * W + (long)y * W + x) * ldo + c;
+        *reinterpret_cast<float4 *>(o + off1) = m1; *reinterpret_cast<float4 *>(o + off2) = m2;
+        *reinterpret_cast<float4 *>(o + off3) = m3; *reinterpret_cast<float4 *>(o + offx) = ctr;
+    }
+}
+
+/* Same operation, one CTA per frame, separable: the frame is staged in shared memory, a horizontal pass leaves the three
+ * row maxima (radii r1 < r2 < r3), a vertical pass finishes them -- 9 + 17 shared-memory reads per (pixel, 4 channels)
+ * instead of 81 global ones.  Needs 4 * H*W*C floats of shared memory (77 KB for the 10x10x48 SPP input). */
+__global__ void __launch_bounds__(256) k_spp_smem(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C, int ldi, int ldo,
+                                                  int r1, int r2, int r3, int off1, int off2, int off3, int offx)
+{
+    extern __shared__ float4 spp_smem[];
+    pdl_trigger(); pdl_wait();
+    const int c4n = C / 4, items = H * W * c4n;
+    float4 *sIn = spp_smem, *sH1 = sIn + items, *sH2 = sH1 + items, *sH3 = sH2 + items;
+    const float *img = in + (long)blockIdx.x * H * W * ldi;
+    float *o = out + (long)blockIdx.x * H * W * ldo;
+    auto mx = [](float4 a, const float4 b) { a.x = fmaxf(a.x, b.x); a.y = fmaxf(a.y, b.y); a.z = fmaxf(a.z, b.z); a.w = fmaxf(a.w, b.w); return a; };
+    for (int i = threadIdx.x; i < items; i += blockDim.x) { const int c = i % c4n, p = i / c4n; sIn[i] = ldg4(img + (long)p * ldi + 4 * c); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int c = i % c4n, p = i / c4n, x = p % W, rowbase = (p - x) * c4n + c;
+        float4 m = sIn[i];
+        for (int d = 1; d <= r3; d++) {
+            if (x - d >= 0) m = mx(m, sIn[rowbase + (x - d) * c4n]);
+            if (x + d < W)  m = mx(m, sIn[rowbase + (x + d) * c4n]);
+            if (d == r1) sH1[i] = m;
+            if (d == r2) sH2[i] = m;
+        }
+        sH3[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int c = i % c4n, p = i / c4n, x = p % W, y = p / W, colbase = x * c4n + c, rs = W * c4n;
+        float4 m1 = sH1[i], m2 = sH2[i], m3 = sH3[i];
+        for (int d = 1; d <= r3; d++) {
+            if (y - d >= 0) { const int j = colbase + (y - d) * rs; m3 = mx(m3, sH3[j]); if (d <= r2) m2 = mx(m2, sH2[j]); if (d <= r1) m1 = mx(m1, sH1[j]); }
+            if (y + d < H)  { const int j = colbase + (y + d) * rs; m3 = mx(m3, sH3[j]); if (d <= r2) m2 = mx(m2, sH2[j]); if (d <= r1) m1 = mx(m1, sH1[j]); }
+        }
+        float *op = o + (long)p * ldo + 4 * c;
+        *reinterpret_cast<float4 *>(op + off1) = m1; *reinterpret_cast<float4 *>(op + off2) = m2;
+        *reinterpret_cast<float4 *>(op + off3) = m3; *reinterpret_cast<float4 *>(op + offx) = sIn[i];
+    }
+}
+
 /* nearest upsample (ffcnn.c:396-410): out[y][x] = in[y/s][x/s] */
 __global__ void k_upsample(const float *__restrict__ in, float *__restrict__ out, int n, int H, int W, int C, int ldi,
                            int ldo, int coff, int s)
