@@ -129,6 +129,10 @@ def main():
         print(json.dumps(line))
         return
 
+    # stdout carries exactly one JSON line: whatever libraries print while the job runs (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -213,6 +217,7 @@ def main():
     nboxes = sum(len(net.boxes(f)) for f in range(B))
     clocks = sampler.summary() if rank == 0 else None
 
+    print("bench.py rank %d/%d: resident %.3f ms/step, e2e %.3f ms/step (wall %.3f ms/step)" % (rank, world, ms / K, ms_e2e / KE, 1e3 * (time.time() - t_wall) / KE), file=sys.stderr)
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -273,7 +278,10 @@ def main():
                 line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": desc}
             except Exception as ex:                      # the baseline is a reported number, never a reason to lose the GPU line
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "failed: %s" % ex}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     net.close()
     if world > 1:
         dist.barrier()
