@@ -372,7 +372,12 @@ struct ffb_engine {
     unsigned char *d_frames = nullptr; size_t d_frames_cap = 0;
     float *h_stage = nullptr; size_t h_stage_cap = 0;
     /* detection */
-    Candidate *d_cand = nullptr, *h_cand = nullptr; int *d_count = nullptr, *h_count = nullptr; int cand_cap = 0;
+    /* two candidate sets: while the host decodes batch i from one, the GPU may already be filtering batch i+1 into the other */
+    struct DetSet { Candidate *d_cand = nullptr, *h_cand = nullptr; int *d_count = nullptr, *h_count = nullptr; int cap = 0, n = 0, s1 = 1, s2 = 1;
+                    cudaEvent_t done = nullptr; } det[2];
+    int det_cur = 0;
+    cudaStream_t d2h_stream = nullptr;      /* candidate read-back must not queue behind the next batch's forward pass */
+    bool slot_enqueued[2] = { false, false };
     std::vector<std::vector<BBOX>> boxes, raw;
     int s1 = 1, s2 = 1; size_t d2h_bytes = 0;
     /* submit/collect pipeline: two device frame slots filled on a copy stream while the previous batch computes */
@@ -416,8 +421,10 @@ void ffb_engine_destroy(ffb_engine *e)
     engine_free_plan(e);
     for (ffb_conv *c : e->convs) conv_release(c);
     for (ffb_engine::Block &b : e->blocks) { blk_plan_destroy(b.plan); reg_plan_destroy(b.reg); }
-    cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_cand); cudaFree(e->d_count); cudaFree(e->d_flush);
-    cudaFreeHost(e->h_stage); cudaFreeHost(e->h_cand); cudaFreeHost(e->h_count);
+    cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_flush);
+    cudaFreeHost(e->h_stage);
+    for (ffb_engine::DetSet &d : e->det) { cudaFree(d.d_cand); cudaFree(d.d_count); cudaFreeHost(d.h_cand); cudaFreeHost(d.h_count); if (d.done) cudaEventDestroy(d.done); }
+    if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
     for (int i = 0; i < 2; i++) { cudaFree(e->d_slot[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]); }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -708,8 +715,12 @@ int ffb_net_attach(NET *net, int device, int max_batch)
     CK(cudaMalloc(&e->d_packed, std::max(1, net->weight_size) * sizeof(float)));
     CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     if (engine_prepare_weights(e) != 0) return -1;
-    CK(cudaMalloc(&e->d_count, sizeof(int)));
-    CK(cudaMallocHost(&e->h_count, sizeof(int)));
+    for (ffb_engine::DetSet &d : e->det) {
+        CK(cudaMalloc(&d.d_count, sizeof(int)));
+        CK(cudaMallocHost(&d.h_count, sizeof(int)));
+        CK(cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming));
+    }
+    CK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -1025,22 +1036,25 @@ int ffb_detect_enqueue(NET *net)
     if (n < 1) { ffb_set_error("ffb_detect: no batch"); return -1; }
     int key = 0; std::vector<Head> heads = yolo_heads(e, &key);
     const int cap = std::max(4096, std::min(key, 2048) * n);
-    if (cap > e->cand_cap) {
+    ffb_engine::DetSet &d = e->det[e->det_cur];
+    if (cap > d.cap) {
         CK(cudaStreamSynchronize(e->stream));
-        cudaFree(e->d_cand); cudaFreeHost(e->h_cand); e->d_cand = nullptr; e->h_cand = nullptr;
-        CK(cudaMalloc(&e->d_cand, (size_t)cap * sizeof(Candidate)));
-        CK(cudaMallocHost(&e->h_cand, (size_t)cap * sizeof(Candidate)));
-        e->cand_cap = cap;
+        cudaFree(d.d_cand); cudaFreeHost(d.h_cand); d.d_cand = nullptr; d.h_cand = nullptr;
+        CK(cudaMalloc(&d.d_cand, (size_t)cap * sizeof(Candidate)));
+        CK(cudaMallocHost(&d.h_cand, (size_t)cap * sizeof(Candidate)));
+        d.cap = cap;
     }
-    CK(cudaMemsetAsync(e->d_count, 0, sizeof(int), e->stream));
+    d.n = n; d.s1 = e->s1; d.s2 = e->s2;
+    CK(cudaMemsetAsync(d.d_count, 0, sizeof(int), e->stream));
     for (const Head &h : heads) {
         const LAYER *yl = net->layer_list + h.layer; const Tens &t = e->outs[h.layer - 1];
         if (t.c != 3 * (5 + yl->class_num)) { ffb_set_error("yolo layer %d: %d channels, expected %d", h.layer, t.c, 3 * (5 + yl->class_num)); return -1; }
         const long warps = (long)n * h.cells;
         CK(launch_pdl(k_yolo_filter, dim3((int)((warps * 32 + 255) / 256)), dim3(256), 0, e->stream, (const float *)t.p, n, h.cells, t.ld, yl->class_num, 0, h.key_base,
-                      yl->ignore_thres, e->d_cand, e->d_count, e->cand_cap));
+                      yl->ignore_thres, d.d_cand, d.d_count, d.cap));
     }
-    CK(cudaMemcpyAsync(e->h_count, e->d_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(d.h_count, d.d_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaEventRecord(d.done, e->stream));
     return (int)heads.size();
 }
 
@@ -1050,20 +1064,22 @@ int ffb_detect_finish(NET *net)
     ffb_engine *e = engine_of(net);
     if (!e) return -1;
     CK(cudaSetDevice(e->device));
-    const int n = e->batch;
+    ffb_engine::DetSet &d = e->det[e->det_cur];
+    const int n = d.n;
     std::vector<Head> heads = yolo_heads(e, nullptr);
-    CK(cudaStreamSynchronize(e->stream));
-    int cnt = std::min(*e->h_count, e->cand_cap);
+    CK(cudaEventSynchronize(d.done));                      /* this batch only: a look-ahead batch may already be queued behind it */
+    int cnt = std::min(*d.h_count, d.cap);
     e->d2h_bytes = sizeof(int) + (size_t)cnt * sizeof(Candidate);
     if (cnt > 0) {
-        CK(cudaMemcpyAsync(e->h_cand, e->d_cand, (size_t)cnt * sizeof(Candidate), cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaMemcpyAsync(d.h_cand, d.d_cand, (size_t)cnt * sizeof(Candidate), cudaMemcpyDeviceToHost, e->d2h_stream));
+        CK(cudaStreamSynchronize(e->d2h_stream));
     }
-    std::sort(e->h_cand, e->h_cand + cnt, [](const Candidate &a, const Candidate &b) { return a.frame != b.frame ? a.frame < b.frame : a.key < b.key; });
+    Candidate *h_cand = d.h_cand;
+    std::sort(h_cand, h_cand + cnt, [](const Candidate &a, const Candidate &b) { return a.frame != b.frame ? a.frame < b.frame : a.key < b.key; });
     e->boxes.assign(n, std::vector<BBOX>()); e->raw.assign(n, std::vector<BBOX>());
     const int netw = net->layer_list[0].w, neth = net->layer_list[0].h;
     for (int k = 0; k < cnt; k++) {
-        const Candidate &c = e->h_cand[k];
+        const Candidate &c = h_cand[k];
         if (c.frame < 0 || c.frame >= n) continue;
         const Head *hd = nullptr;
         for (const Head &h : heads) if (c.key >= h.key_base && c.key < h.key_base + h.cells * 3) hd = &h;
@@ -1075,7 +1091,7 @@ int ffb_detect_finish(NET *net)
     }
     for (int f = 0; f < n; f++) {
         e->boxes[f] = e->raw[f];
-        const int m = ffb_nms(e->boxes[f].data(), (int)e->boxes[f].size(), 0.5f, 1, e->s1, e->s2);
+        const int m = ffb_nms(e->boxes[f].data(), (int)e->boxes[f].size(), 0.5f, 1, d.s1, d.s2);
         e->boxes[f].resize(m);
     }
     return 0;
@@ -1142,6 +1158,20 @@ int ffb_submit_u8(NET *net, const unsigned char *frames_host, int n, int w, int 
     return 0;
 }
 
+/* enqueue everything batch `slot` needs on the GPU: wait for its copy, net_input + layer loop, candidate filter */
+static int collect_enqueue(NET *net, ffb_engine *e, int slot)
+{
+    const ffb_engine::SlotMeta &m = e->slot_meta[slot];
+    CK(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
+    if (ffb_input_u8(net, e->d_slot[slot], m.n, m.w, m.h, m.pitch, m.has_mean ? m.mean : nullptr, m.has_norm ? m.norm : nullptr, 1) != 0) return -1;
+    if (ffb_forward(net) != 0) return -1;
+    CK(cudaEventRecord(e->ev_free[slot], e->stream));
+    e->det_cur = slot;
+    if (ffb_detect_enqueue(net) < 0) return -1;
+    e->slot_enqueued[slot] = true;
+    return 0;
+}
+
 int ffb_collect(NET *net)
 {
     ffb_engine *e = engine_of(net);
@@ -1149,12 +1179,12 @@ int ffb_collect(NET *net)
     if (e->collected >= e->submitted) { ffb_set_error("ffb_collect: nothing submitted"); return -1; }
     CK(cudaSetDevice(e->device));
     const int slot = (int)(e->collected & 1);
-    const ffb_engine::SlotMeta &m = e->slot_meta[slot];
-    CK(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
-    if (ffb_input_u8(net, e->d_slot[slot], m.n, m.w, m.h, m.pitch, m.has_mean ? m.mean : nullptr, m.has_norm ? m.norm : nullptr, 1) != 0) return -1;
-    if (ffb_forward(net) != 0) return -1;
-    CK(cudaEventRecord(e->ev_free[slot], e->stream));
-    if (ffb_detect_enqueue(net) < 0) return -1;
+    if (!e->slot_enqueued[slot] && collect_enqueue(net, e, slot) != 0) return -1;
+    /* look-ahead: the next submitted batch is queued behind this one before the host blocks, so the GPU goes straight from
+       batch i to batch i+1 while the host decodes batch i (its candidates sit in the other detection set) */
+    if (e->submitted - e->collected >= 2 && !e->slot_enqueued[slot ^ 1] && collect_enqueue(net, e, slot ^ 1) != 0) return -1;
+    e->det_cur = slot;
+    e->slot_enqueued[slot] = false;
     e->collected++;
     return ffb_detect_finish(net);
 }
