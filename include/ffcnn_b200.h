@@ -46,7 +46,10 @@ int   ffb_commit_weights(NET *net);
  * (conv-v0); "pw_mode" 0 = auto, 1 = fp32 FFMA everywhere, 2 = tcgen05 3xTF32 where eligible,
  * 3 = tcgen05 1xTF32; "dw_mode" 0 = TMA-fed shared-memory stencil for the depthwise layers (default), 1 = the
  * register-window kernel fed by plain loads; "graph" 1 = replay a captured CUDA graph (default), 0 = plain launches;
- * "keep_all" 1 = every layer output gets its own buffer (needed by ffb_layer_output); "fuse_input" 1 (default) = when
+ * "keep_all" 1 = layer-by-layer plan, every layer output gets its own buffer (ffb_layer_output works for every layer),
+ * 2 = the fused plan with one private buffer per surviving tensor; "fuse_block" 1 (default) = run the expand -> depthwise ->
+ * project [-> shortcut] chains where it pays as ONE kernel each, 2 = every supported chain, 0 = off;
+ * "fuse_tail" 1 (default) = SPP pools + route as one kernel, upsample writes into its concat tensor; "fuse_input" 1 (default) = when
  * the frames already have the net's size, the stem kernel reads the u8 frames itself (net_input fused, no fp32 input
  * tensor) -- the frame buffer handed to ffb_input_u8 must then stay valid until ffb_forward's work has completed. */
 int  ffb_set_option(NET *net, const char *name, int value);
@@ -101,7 +104,8 @@ int  ffb_collect(NET *net);
 /* ---- inspection / measurement ------------------------------------------------------------ */
 
 /* Copy the output of layer `layer` for frame `frame` to host as CHW fp32 (the reference layout).
- * Needs option keep_all=1 set before ffb_forward.  Returns the number of floats. */
+ * Needs option keep_all=1 (or 2: then only tensors the fused plan materialises exist, others return 0) set before
+ * ffb_forward.  Returns the number of floats. */
 long ffb_layer_output(NET *net, int layer, int frame, float *chw_host, long capacity);
 
 /* Time every layer of the current batch with CUDA events: ms[i] = mean over `reps` launches of
