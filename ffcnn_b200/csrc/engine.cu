@@ -1049,8 +1049,8 @@ int ffb_detect_enqueue(NET *net)
     for (const Head &h : heads) {
         const LAYER *yl = net->layer_list + h.layer; const Tens &t = e->outs[h.layer - 1];
         if (t.c != 3 * (5 + yl->class_num)) { ffb_set_error("yolo layer %d: %d channels, expected %d", h.layer, t.c, 3 * (5 + yl->class_num)); return -1; }
-        const long warps = (long)n * h.cells;
-        CK(launch_pdl(k_yolo_filter, dim3((int)((warps * 32 + 255) / 256)), dim3(256), 0, e->stream, (const float *)t.p, n, h.cells, t.ld, yl->class_num, 0, h.key_base,
+        const long threads = (long)n * h.cells;                 /* one thread per grid cell */
+        CK(launch_pdl(k_yolo_filter, dim3((int)((threads + 255) / 256)), dim3(256), 0, e->stream, (const float *)t.p, n, h.cells, t.ld, yl->class_num, 0, h.key_base,
                       yl->ignore_thres, d.d_cand, d.d_count, d.cap));
     }
     CK(cudaMemcpyAsync(d.h_count, d.d_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));

@@ -525,47 +525,64 @@ __global__ void k_prep_weights(const float *__restrict__ flt, int row, int fn, i
 }
 
 /* ------------------------------------------------------------------------------------------------
- * yolo candidate filter (first half of ffcnn.c:438-452 on the GPU).  One warp per grid cell: the 255
- * head values of the cell are read coalesced, each anchor's first arg-max over the class logits is
- * found with a shuffle reduction (ties -> lowest class index, like the sequential `cs < val` scan), and
- * lane 0 tests a float estimate of the reference confidence against thresh - margin.  Survivors are
- * appended (atomic counter) as raw logits; the host re-does the exact double-precision decode.
+ * yolo candidate filter (first half of ffcnn.c:438-452 on the GPU).  Each anchor's first arg-max over the
+ * class logits is found with a shuffle reduction (ties -> lowest class index, like the sequential
+ * `cs < val` scan), and lane 0 tests a float estimate of the reference confidence against thresh - margin.
+ * Survivors are appended (atomic counter) as raw logits; the host re-does the exact double-precision decode.
  * ---------------------------------------------------------------------------------------------- */
 struct Candidate { int frame, key, cls; float bs, cs, tx, ty, tw, th; };
 
+/* Two levels.  (1) One THREAD per grid cell reads only the three objectness logits: the reference confidence
+ * 1 / (1 + e^-bs (1 + e^-cs)) can never exceed sigmoid(bs), so an anchor whose sigmoid(bs) is below thresh - margin is out
+ * without its 80 class logits ever being read (almost every anchor of almost every cell: the heads are then read at ~1/10
+ * of their size).  (2) The survivors of the 32 cells of a warp are taken one by one by the WHOLE warp: coalesced read of
+ * the class logits, shuffle arg-max, exact-form float confidence test by lane 0, append. */
 __global__ void k_yolo_filter(const float *__restrict__ head, int n, int cells, int ld, int classes, int head_index,
                               int key_base, float thresh, Candidate *__restrict__ list, int *__restrict__ counter, int cap)
 {
     pdl_trigger(); pdl_wait();
     const int lane = threadIdx.x & 31;
-    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-    if (warp >= (long)n * cells) return;
-    const int cell = (int)(warp % cells); const int f = (int)(warp / cells);
-    const float *v = head + warp * ld;
+    const long cell_id = blockIdx.x * (long)blockDim.x + threadIdx.x;         /* frame * cells + cell */
+    const long total = (long)n * cells;
     const int per = 5 + classes;
-    for (int a = 0; a < 3; a++) {
-        const float *pv = v + a * per;
-        float best = -INFINITY; int bi = 0x7fffffff;
-        for (int l = lane; l < classes; l += 32) {
-            const float s = __ldg(pv + 5 + l);
-            if (s > best) { best = s; bi = l; }
-        }
+    unsigned pass = 0;
+    if (cell_id < total) {
+        const float *v = head + cell_id * ld;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
-            const int   oi = __shfl_xor_sync(0xffffffffu, bi, d);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        for (int a = 0; a < 3; a++) {
+            const float bs = __ldg(v + a * per + 4);
+            const float ub = 1.0f / (1.0f + expf(-bs));                        /* upper bound of the confidence */
+            if (ub >= thresh - 1e-3f || !(ub == ub)) pass |= 1u << a;
         }
-        if (lane == 0) {
-            const float bs = __ldg(pv + 4);
-            const float conf = 1.0f / (1.0f + expf(-bs) * (1.0f + expf(-best)));
-            if (conf >= thresh - 1e-3f || !(conf == conf)) {
-                const int slot = atomicAdd(counter, 1);
-                if (slot < cap) {
-                    Candidate c;
-                    c.frame = f; c.key = key_base + cell * 3 + a; c.cls = bi == 0x7fffffff ? 0 : bi;
-                    c.bs = bs; c.cs = best; c.tx = __ldg(pv); c.ty = __ldg(pv + 1); c.tw = __ldg(pv + 2); c.th = __ldg(pv + 3);
-                    list[slot] = c;
+    }
+    for (int a = 0; a < 3; a++) {
+        unsigned todo = __ballot_sync(0xffffffffu, (pass >> a) & 1u);
+        while (todo) {
+            const int src = __ffs(todo) - 1; todo &= todo - 1;
+            const long cid = __shfl_sync(0xffffffffu, cell_id, src);
+            const float *pv = head + cid * ld + a * per;
+            float best = -INFINITY; int bi = 0x7fffffff;
+            for (int l = lane; l < classes; l += 32) {
+                const float s = __ldg(pv + 5 + l);
+                if (s > best) { best = s; bi = l; }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+                const int   oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (lane == 0) {
+                const float bs = __ldg(pv + 4);
+                const float conf = 1.0f / (1.0f + expf(-bs) * (1.0f + expf(-best)));
+                if (conf >= thresh - 1e-3f || !(conf == conf)) {
+                    const int slot = atomicAdd(counter, 1);
+                    if (slot < cap) {
+                        Candidate c;
+                        c.frame = (int)(cid / cells); c.key = key_base + (int)(cid % cells) * 3 + a; c.cls = bi == 0x7fffffff ? 0 : bi;
+                        c.bs = bs; c.cs = best; c.tx = __ldg(pv); c.ty = __ldg(pv + 1); c.tw = __ldg(pv + 2); c.th = __ldg(pv + 3);
+                        list[slot] = c;
+                    }
                 }
             }
         }
