@@ -102,7 +102,7 @@ static bool plan_tile(BlkPlan *p)
                 int occ = (int)((228 * 1024) / (smem + 1024)); if (occ > inst->MINB) occ = inst->MINB; if (occ < 1) occ = 1;
                 /* per-tile cost on one SM, three candidate limiters (profiles/r1j: shared-memory wavefronts bind first):
                    wf  = shared-memory wavefronts (1 per clk), mma = m16n8k8 tensor ops (2.14 clk each), ins = issue slots / 4 */
-                const int MT = KS1 * GC > 6 ? 1 : 2, items = (M1 + MT - 1) / MT, rounds = (items + BLK_WARPS - 1) / BLK_WARPS;
+                const int MT = KS1 * GC >= 6 ? 1 : 2, items = (M1 + MT - 1) / MT, rounds = (items + BLK_WARPS - 1) / BLK_WARPS;
                 const int units = MTW > 1 ? ((TH + 1) / 2 * TW + 15) / 16 : M3, urounds = (units + BLK_WARPS - 1) / BLK_WARPS;
                 const int taps = MTW > 1 ? (S + 3) * (S + 3) : 3 * (S + 3), mper = MTW > 1 ? 2 : 1;
                 const double wfA = (double)items * NC * (4 * MT * KS1 + 8 * KS1 * GC + 4 * MT + 8 * MT * GC);

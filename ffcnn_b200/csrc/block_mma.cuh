@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     float *smem = reinterpret_cast<float *>(blk_smem4);
     constexpr int CIN_P = 8 * KS1, SXs = CIN_P + 4, COUT_P = 8 * NT3;
     constexpr int SEs = 16 * GC + (S == 1 ? 8 : 4);       /* E pixel stride (floats): conflict-free 128-bit stencil loads */
-    constexpr int MT = (KS1 * GC > 6) ? 1 : 2;            /* m-tiles per stage-A work item (bounds the accumulator registers) */
+    constexpr int MT = (KS1 * GC >= 6) ? 1 : 2;           /* m-tiles per stage-A work item (bounds the accumulator registers; 1 also spreads the 7 m-tiles of a 10x10 frame over 7 warps) */
     constexpr bool QUAD = MTW >= 2;
     constexpr int NQ = QUAD ? MTW / 2 : 1;                /* quads (or single m-tiles) per warp */
     constexpr BlkChunk off(GC, KS1, NT3);
