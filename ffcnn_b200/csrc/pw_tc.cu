@@ -5,8 +5,9 @@
  * in[px][ic] + b[oc]).  In batched NHWC this is one GEMM  D[M x N] = A[M x K] * W[N x K]^T  with M = n*h*w pixels,
  * K = ic, N = oc, both operands K-major -- a genuine dense contraction, so it goes to the tensor pipe:
  *
- *   warp 0  TMA producer : A tiles [128 px x 32 ch] (128-byte rows, SWIZZLE_128B) through a S-stage mbarrier ring;
- *                          the layer's weights once per CTA (resident for the whole persistent loop)
+ *   warp 0  TMA producer : A sub-tiles [128 px x 32 ch] (128-byte rows, SWIZZLE_128B) through an S-slot mbarrier ring --
+ *                          the ring is K-CHUNK granular (16 KB slots), so even K = 192 next to 150 KB of resident weights
+ *                          keeps several loads in flight; the layer's weights once per CTA (resident for the whole loop)
  *   warp 1  MMA issuer   : one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=NS, K=8 per instruction),
  *                          accumulators live in TMEM (double buffered), completion via tcgen05.commit -> mbarrier
  *   warps 2-5            : (a) 3xTF32 split of the landed activation tile, (b) epilogue: tcgen05.ld -> act(fma(acc, s, b))
@@ -29,6 +30,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "pw_tc.h"
@@ -93,7 +95,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     uint8_t *sBh = smem;
     uint8_t *sBl = sBh + (size_t)Kc * b_sub;
     uint8_t *sA  = sBl + (a.split ? (size_t)Kc * b_sub : 0);
-    uint8_t *sO  = sA + (size_t)S * Kc * A_SUB;
+    uint8_t *sO  = sA + (size_t)S * A_SUB;
     float   *sSc = reinterpret_cast<float *>(sO + (size_t)a.G * 8 * 4096);
     float   *sBi = sSc + NS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBi + NS);
@@ -131,13 +133,16 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     if (warp == 0) {
         /* ===================== TMA producer ===================== */
         if (elect_one()) {
+            uint32_t cq = 0;                                 /* K chunks issued so far: slot = cq % S */
             int it = 0;
             for (int t = group; t < a.tiles; t += ngroups, it++) {
-                const int s = it % S; const uint32_t ph = (it / S) & 1;
-                mbar_wait(empty + s, ph ^ 1);
-                TRACE(0, it, 0);
-                mbar_arrive_expect_tx(full + s, (uint32_t)Kc * A_SUB);
-                for (int kc = 0; kc < Kc; kc++) tma_load_2d(sA + ((size_t)s * Kc + kc) * A_SUB, &tmA, kc * 32, t * BM, full + s);
+                for (int kc = 0; kc < Kc; kc++, cq++) {
+                    const int s = cq % S; const uint32_t ph = (cq / S) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    if (kc == 0) TRACE(0, it, 0);
+                    mbar_arrive_expect_tx(full + s, (uint32_t)A_SUB);
+                    tma_load_2d(sA + (size_t)s * A_SUB, &tmA, kc * 32, t * BM, full + s);
+                }
             }
         }
     } else if (warp == 1) {
@@ -145,35 +150,33 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_tf32(BM, NS);
             mbar_wait(bfull, 0);
+            uint32_t cq = 0;
             int it = 0;
             for (int t = group; t < a.tiles; t += ngroups, it++) {
-                const int s = it % S; const uint32_t ph = (it / S) & 1;
                 const int ab = it & 1; const uint32_t aph = (it >> 1) & 1;
-                mbar_wait(a.split ? conv + s : full + s, ph);
-                TRACE(1, it, 0);
-                mbar_wait(tempty + ab, aph ^ 1);
-                TRACE(1, it, 1);
-                tc_fence_after_sync();
                 const uint32_t d = tmem_base + acc_col0 + ab * NS;
-                const uint32_t a_base = smem_u32(sA + (size_t)s * Kc * A_SUB);
                 const uint32_t bh_base = smem_u32(sBh), bl_base = smem_u32(sBl);
                 uint32_t accum = 0;
-                if (a.split) {
-                    const uint32_t alo = tmem_base + alo_col0 + s * Kc * 32;
-                    for (int ks = 0; ks < a.ksteps_total; ks++) {           /* A_lo (TMEM) x W_hi */
-                        const int kc = ks >> 2, kk = ks & 3;
-                        mma_tf32_ts(d, alo + ks * 8, umma_desc_sw128(bh_base + kc * b_sub + kk * 32), idesc, accum); accum = 1;
+                for (int kc = 0; kc < Kc; kc++, cq++) {
+                    const int s = cq % S; const uint32_t ph = (cq / S) & 1;
+                    mbar_wait(a.split ? conv + s : full + s, ph);
+                    if (kc == 0) { TRACE(1, it, 0); mbar_wait(tempty + ab, aph ^ 1); TRACE(1, it, 1); }
+                    tc_fence_after_sync();
+                    const uint32_t a_base = smem_u32(sA + (size_t)s * A_SUB);
+                    const int nk = min(4, a.ksteps_total - kc * 4);            /* k-steps (of 8) in this chunk */
+                    if (a.split) {
+                        const uint32_t alo = tmem_base + alo_col0 + s * 32;
+                        for (int kk = 0; kk < nk; kk++) {                       /* A_lo (TMEM) x W_hi */
+                            mma_tf32_ts(d, alo + kk * 8, umma_desc_sw128(bh_base + kc * b_sub + kk * 32), idesc, accum); accum = 1;
+                        }
+                        for (int kk = 0; kk < nk; kk++)                         /* A_hi x W_lo */
+                            mma_tf32_ss(d, umma_desc_sw128(a_base + kk * 32), umma_desc_sw128(bl_base + kc * b_sub + kk * 32), idesc, 1);
                     }
-                    for (int ks = 0; ks < a.ksteps_total; ks++) {           /* A_hi x W_lo */
-                        const int kc = ks >> 2, kk = ks & 3;
-                        mma_tf32_ss(d, umma_desc_sw128(a_base + kc * A_SUB + kk * 32), umma_desc_sw128(bl_base + kc * b_sub + kk * 32), idesc, 1);
+                    for (int kk = 0; kk < nk; kk++) {                           /* A_hi x W_hi (or raw x raw in 1xTF32 mode) */
+                        mma_tf32_ss(d, umma_desc_sw128(a_base + kk * 32), umma_desc_sw128(bh_base + kc * b_sub + kk * 32), idesc, accum); accum = 1;
                     }
+                    tc_commit(empty + s);        /* ring slot (and its A_lo columns) reusable once these MMAs retire */
                 }
-                for (int ks = 0; ks < a.ksteps_total; ks++) {               /* A_hi x W_hi (or raw x raw in 1xTF32 mode) */
-                    const int kc = ks >> 2, kk = ks & 3;
-                    mma_tf32_ss(d, umma_desc_sw128(a_base + kc * A_SUB + kk * 32), umma_desc_sw128(bh_base + kc * b_sub + kk * 32), idesc, accum); accum = 1;
-                }
-                tc_commit(empty + s);            /* smem stage (and its A_lo columns) reusable once these MMAs retire */
                 tc_commit(tfull + ab);           /* accumulator ready for the epilogue */
                 TRACE(1, it, 2);
             }
@@ -251,25 +254,28 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         for (int t = group; t < a.tiles; t += ngroups, it++) {
             if (it % a.G != grp) continue;
             if (a.split) {
-                const int s = it % S; const uint32_t ph = (it / S) & 1;
-                if (et == 0) TRACE(2, it, 0);
-                mbar_wait(full + s, ph);
-                if (et == 0) TRACE(2, it, 1);
-                const uint32_t arow = smem_u32(sA + (size_t)s * Kc * A_SUB + row * 128);
-                const uint32_t alo = tmem_base + lane_addr + alo_col0 + s * Kc * 32;
-                for (int ub = half; ub < Kc * 4; ub += 4) {  /* 2 units (of 8 consecutive k each) per pass, all loads issued first */
+                for (int kc = 0; kc < Kc; kc++) {
+                    const uint32_t cq = (uint32_t)it * Kc + kc;
+                    const int s = cq % S; const uint32_t ph = (cq / S) & 1;
+                    if (et == 0 && kc == 0) TRACE(2, it, 0);
+                    mbar_wait(full + s, ph);
+                    if (et == 0 && kc == 0) TRACE(2, it, 1);
+                    const uint32_t arow = smem_u32(sA + (size_t)s * A_SUB + row * 128);
+                    const uint32_t alo = tmem_base + lane_addr + alo_col0 + s * 32;
+                    const int nu = min(4, (a.K - kc * 32 + 7) / 8);             /* valid units (8 consecutive k each) in this chunk */
+                    /* this warp half's two units of the chunk (half, half + 2), all loads issued first */
                     float4 x[2][2]; uint32_t pp[2][2];
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        const int u = ub + 2 * i, kc = u >> 2, c2 = u & 3;
-                        pp[i][0] = arow + kc * A_SUB + (((2 * c2) ^ (row & 7)) << 4);
-                        pp[i][1] = arow + kc * A_SUB + (((2 * c2 + 1) ^ (row & 7)) << 4);
-                        if (u < Kc * 4) { x[i][0] = lds128(pp[i][0]); x[i][1] = lds128(pp[i][1]); }
+                        const int c2 = half + 2 * i;
+                        pp[i][0] = arow + (((2 * c2) ^ (row & 7)) << 4);
+                        pp[i][1] = arow + (((2 * c2 + 1) ^ (row & 7)) << 4);
+                        if (c2 < nu) { x[i][0] = lds128(pp[i][0]); x[i][1] = lds128(pp[i][1]); }
                     }
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        const int u = ub + 2 * i;
-                        if (u < Kc * 4) {
+                        const int c2 = half + 2 * i;
+                        if (c2 < nu) {
                             const float4 x0 = x[i][0], x1 = x[i][1];
                             float4 h0, h1; uint32_t lo[8];
                             h0.x = tf32_round(x0.x); h0.y = tf32_round(x0.y); h0.z = tf32_round(x0.z); h0.w = tf32_round(x0.w);
@@ -280,14 +286,14 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                             lo[4] = __float_as_uint(x1.x - h1.x); lo[5] = __float_as_uint(x1.y - h1.y);
                             lo[6] = __float_as_uint(x1.z - h1.z); lo[7] = __float_as_uint(x1.w - h1.w);
                             sts128(pp[i][0], h0); sts128(pp[i][1], h1);
-                            tmem_st8(alo + u * 8, lo);
+                            tmem_st8(alo + c2 * 8, lo);
                         }
                     }
+                    fence_proxy_async_smem();                /* in-place A_hi writes -> visible to the tensor core (async proxy) */
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    mbar_arrive(conv + s);
                 }
-                fence_proxy_async_smem();                    /* in-place A_hi writes -> visible to the tensor core (async proxy) */
-                tmem_st_wait();
-                tc_fence_before_sync();
-                mbar_arrive(conv + s);
                 if (et == 0) TRACE(2, it, 2);
             }
             if (prev_t >= 0) epilogue(prev_t, prev_it);
@@ -381,16 +387,23 @@ static bool plan_tiling(PwTcPlan *p)
 {
     const int N16 = (p->N + 15) & ~15;
     const size_t limit = 227 * 1024 - 2048;          /* dynamic smem ceiling minus alignment slack */
+    /* fewest N slices first (every slice re-reads and re-splits the activation tile), then as many 16 KB ring slots as fit
+       (at least 2 -- one K chunk in flight while another is being consumed -- and no more than 2 tiles' worth or 8) */
     for (int minS = 2; minS >= 1; minS--)
         for (int nsl = 1; nsl <= 8; nsl++) {
             int NS = (N16 + nsl - 1) / nsl;
             NS = nsl > 1 ? (NS + 31) & ~31 : (NS + 15) & ~15;
             if (NS > 256) continue;
             const size_t B = (size_t)(p->split ? 2 : 1) * p->Kc * NS * 128;
-            for (int S = (minS == 2 ? 4 : 1); S >= minS; S--)
+            const int maxS = std::min(8, std::max(2, 2 * p->Kc));
+            for (int S = maxS; S >= minS; S--)
                 for (int OB = (p->Kc <= 3 ? MAX_GROUPS : 1); OB >= 1; OB--) {   /* OB = warp groups (a second one pays off when tiles are small); staging = 8 warps x 4 KB each */
-                    const size_t smem = B + (size_t)S * p->Kc * A_SUB + (size_t)OB * 8 * 4096 + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
-                    const int tmem = 2 * NS + (p->split ? S * p->Kc * 32 : 0);
+                    /* two groups take alternate tiles and each waits only on its own tiles' ring slots: a slot must then
+                       always serve the same group (S a multiple of 2 * Kc), or a group would skip mbarrier phases and its
+                       parity wait would alias (found as a hang on 48 -> 224 with S = 2, Kc = 2) */
+                    if (OB == 2 && S % (2 * p->Kc) != 0) continue;
+                    const size_t smem = B + (size_t)S * A_SUB + (size_t)OB * 8 * 4096 + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
+                    const int tmem = 2 * NS + (p->split ? S * 32 : 0);
                     if (smem <= limit && tmem <= 512) {
                         p->NS = NS; p->nsl = nsl; p->S = S; p->OB = OB; p->NP = nsl * NS;
                         p->smem = smem + 1024;

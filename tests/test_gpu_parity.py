@@ -320,3 +320,31 @@ def test_fused_blocks_against_oracle(assets, oracle_layers, fuse_block):
     for f in range(8):
         boxes_close(fused[f], net.boxes(f), px=BOX_TOL, score=SCORE_TOL)
     net.close()
+
+
+def test_fused_plan_odd_batches_and_geometries(assets):
+    """Ragged cases for the fused plan: batch sizes that do not fill the tile grid, non-square nets (640x448 = the reference
+    main()'s geometry, 416x256) and a net whose deepest maps are 11x11 (odd width: those chains must fall back to the
+    per-layer kernels).  The fused plan must give the layer-by-layer plan's boxes (both are within tolerance of the oracle)."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    pix = img[:, :w * 3].reshape(h, w, 3)
+    for (nw, nh, n) in ((0, 0, 1), (0, 0, 7), (640, 448, 2), (416, 256, 3), (352, 352, 2)):
+        W, H = nw or 320, nh or 320
+        base = pix[np.arange(H) * h // H][:, np.arange(W) * w // W]
+        pitch = (W * 3 + 3) & ~3
+        frames = np.zeros((n, H, pitch), np.uint8)
+        for f in range(n):
+            frames[f, :, :W * 3] = np.roll(base, (f * 3, f * 5), (0, 1)).reshape(H, W * 3)
+        res = []
+        for fuse in (1, 0):
+            net = fb.Net(cfg, wts, nw, nh, device=0, max_batch=n)
+            net.set_option("fuse_block", fuse); net.set_option("fuse_tail", fuse)
+            for _ in range(2):                                              # second pass replays the CUDA graph
+                net.detect_batch_u8(frames, n, W, H, pitch)
+            res.append([net.boxes(f) for f in range(n)])
+            assert (net.get_option("blocks") > 0) == bool(fuse)
+            net.close()
+        assert sum(len(b) for b in res[0]) > 0
+        for a, b in zip(*res):
+            boxes_close(a, b, px=BOX_TOL, score=SCORE_TOL)
