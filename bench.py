@@ -4,11 +4,13 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference ...                      times the reference's own CPU path (oracle/_ref)
 
-One "step" = one pass of the hot path over one batch of 256 synthetic frames per GPU: batched net_input kernel,
-the 112-launch layer loop (CUDA graph replay) and the yolo candidate-filter kernels.  `value` is measured with the
-u8 frames already resident in HBM (4 distinct batches rotated, 314 MB > L2); `e2e` goes through the public C-ABI
-call ffb_detect_batch_u8 with pinned HOST frames in and decoded boxes out (H2D + kernels + D2H + host decode/NMS
-inside the timed region).  Multi-GPU: frames are independent -> contiguous shards per rank, no data-path collective;
+One "step" = one pass of the hot path over one batch of 256 synthetic frames per GPU: net_input fused into the stem
+kernel, the 131-layer loop as 43 kernel launches (CUDA graph replay; 23 expand->depthwise->project chains and the SPP
+block run as one fused kernel each) and the yolo candidate-filter kernels.  `value` is measured with the u8 frames
+already resident in HBM (4 distinct batches rotated, 314 MB > L2); `e2e` goes through the public C-ABI calls
+ffb_submit_u8 / ffb_collect with pinned HOST frames in and decoded boxes out (H2D + kernels + D2H + host decode/NMS
+inside the timed region).  `roofline` charges a fused kernel the summed algorithmic bytes of the layers it replaces
+(SURVEY 8d defines bytes per layer), so a fraction above 1 means faster than those layers could run unfused.  Multi-GPU: frames are independent -> contiguous shards per rank, no data-path collective;
 the only traffic is one NCCL broadcast of the packed weights at load (weak scaling, 256 frames per GPU).
 Prints ONE JSON line on rank 0.
 """
