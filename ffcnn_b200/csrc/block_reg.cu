@@ -63,6 +63,7 @@ RegPlan *reg_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
 
 void reg_plan_destroy(RegPlan *p) { delete p; }
 const char *reg_describe(const RegPlan *p) { return p ? p->desc : ""; }
+int reg_launches(const RegPlan *p) { return p && p->kind == 2 ? 3 : 1; }
 
 int reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st)
 {

@@ -11,3 +11,4 @@ RegPlan *reg_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
 void     reg_plan_destroy(RegPlan *p);
 int      reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st);
 const char *reg_describe(const RegPlan *p);
+int      reg_launches(const RegPlan *p);          /* kernels one reg_run enqueues (3 for the sliced 24-channel block) */

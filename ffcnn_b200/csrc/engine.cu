@@ -905,7 +905,7 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         if (e->blk_at[i] >= 0) {
             const ffb_engine::Block &b = e->blocks[e->blk_at[i]]; const Tens &y = e->outs[i + 2];
             if ((b.plan ? blk_run(b.plan, in.p, in.ld, y.p, y.ld, n, st) : reg_run(b.reg, in.p, in.ld, y.p, y.ld, n, st)) != 0) return -1;
-            (*launches)++;
+            *launches += b.plan ? 1 : reg_launches(b.reg);
             return 0;
         }
     }
