@@ -928,7 +928,7 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         break;
     case LAYER_TYPE_UPSAMPLE:
         if (in.c % 4) { ffb_set_error("upsample layer %d: channels %d not a multiple of 4", i, in.c); return -1; }
-        CK(launch_pdl(k_upsample, dim3(grid_for((long)n * o.h * o.w * (o.c / 4), 128)), dim3(128), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride));
+        CK(launch_pdl(k_upsample, dim3(grid_for((long)n * o.h * o.w * (o.c / 4), 128, 64)), dim3(128), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride));
         (*launches)++;
         break;
     case LAYER_TYPE_SHORTCUT: {
