@@ -51,7 +51,7 @@ class NET(C.Structure):
 
 def build(verbose: bool = False) -> str:
     """Compile libffcnn_b200.so in-tree (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)."""
-    r = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j4", "-C", os.path.join(HERE, "csrc")], capture_output=True, text=True)
     if r.returncode != 0:
         raise FfcnnError("building libffcnn_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
     if verbose:
