@@ -348,3 +348,36 @@ def test_fused_plan_odd_batches_and_geometries(assets):
         assert sum(len(b) for b in res[0]) > 0
         for a, b in zip(*res):
             boxes_close(a, b, px=BOX_TOL, score=SCORE_TOL)
+
+
+def test_second_darknet_graph_against_oracle(tmp_path):
+    """Widening: the yolov3-tiny-like graph of ffcnn_b200/tinygraph.py through the same loader and engine --
+    dense 3x3 and grouped convs (generic kernel), stride-2 max pools, avgpool, relu, upsample into a route, a tcgen05
+    pointwise layer, 2-class yolo heads -- every layer and the boxes of three frames against the oracle (which is bit-exact
+    against the compiled reference on this graph)."""
+    from ffcnn_b200 import tinygraph as tg
+    cfg, wts = tg.write(str(tmp_path))
+    layers = orc.load_net(cfg, wts, 0, 0)
+    fr = tg.frames(3)
+    for keep in (1, 0):
+        net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=3)
+        net.set_option("keep_all", keep)
+        net.detect_batch_u8(fr, 3, tg.W, tg.H, fr.shape[2])
+        for f in range(3):
+            x, s1, s2 = orc.net_input(fr[f], tg.W, tg.H, tg.W, tg.H)
+            outs, raw, fin = orc.forward(layers, x, s1, s2, True)
+            if keep:
+                for i, o in enumerate(outs):
+                    if o is not None:
+                        assert rel_err(net.layer_output(i, f), o) < FEAT_TOL, (f, i, rel_err(net.layer_output(i, f), o))
+            graw = net.boxes(f, raw=True)
+            assert len(graw) == len(raw) and [int(t) for t in graw["type"]] == [int(t) for t in raw["type"]]
+            # random weights give boxes up to 200 px wide: w = exp(tw) * anchor turns a logit error d into w * d pixels, so the
+            # pixel tolerance grows with the box (2e-5 absolute on the logit, the feature-map tolerance at |head| = 1)
+            got = net.boxes(f)
+            assert len(got) == len(fin)
+            for g, e in zip(got, fin):
+                assert int(g["type"]) == int(e["type"]) and abs(float(g["score"]) - float(e["score"])) <= SCORE_TOL
+                tol = BOX_TOL + 2e-5 * max(float(e["x2"]) - float(e["x1"]), float(e["y2"]) - float(e["y1"]))
+                assert max(abs(float(g[k]) - float(e[k])) for k in ("x1", "y1", "x2", "y2")) <= tol, (g, e, tol)
+        net.close()

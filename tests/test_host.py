@@ -192,3 +192,30 @@ def test_net_dump_prints_the_reference_table(assets):
             "else:\n    r = ref.RefNet(%r, %r, 0, 0, 'v6_O2'); r.L.net_dump.argtypes=[__import__('ctypes').c_void_p]; r.L.net_dump(r.net)\n") % (REPO, cfg, cfg, wts)
     outs = [subprocess.run([sys.executable, "-c", code, w], capture_output=True, text=True, check=True).stdout for w in ("mine", "ref")]
     assert outs[0] == outs[1] and outs[0].count("\n") == 132
+
+
+def test_parse_second_graph_matches_oracle_loader(tmp_path):
+    """The host C loader on the yolov3-tiny-like widening graph (ffcnn_b200/tinygraph.py): pools, avgpool, relu, grouped conv,
+    absolute + relative routes, 2-class heads -- same layer table and bit-identical packed weights as the oracle's loader
+    (itself bit-exact against the compiled reference on this graph, tests/test_oracle.py)."""
+    from ffcnn_b200 import tinygraph as tg
+    cfg, wts = tg.write(str(tmp_path))
+    layers = orc.load_net(cfg, wts, 0, 0)
+    net = fb.Net(cfg, wts, 0, 0, device=None)
+    assert net.layer_num == len(layers) == 17
+    for i, L in enumerate(layers):
+        a, b = net.layer(i), net.layer(i + 1)
+        assert (a.type, a.w, a.h, a.c) == (L.type, L.w, L.h, L.c), i
+        if L.type != orc.YOLO:
+            assert (b.w, b.h, b.c) == (L.ow, L.oh, L.oc), i
+        if L.type == orc.CONV:
+            assert (a.fn, a.fs, a.stride, a.groups, a.pad, a.batchnorm, a.activation) == (L.fn, L.fs, L.stride, L.groups, L.pad, L.batchnorm, L.activation), i
+        if L.type in (orc.MAXPOOL, orc.AVGPOOL, orc.UPSAMPLE):
+            assert a.stride == L.stride and (L.type == orc.UPSAMPLE or a.fs == L.fs), i
+        if L.type in (orc.SHORTCUT, orc.ROUTE):
+            assert list(a.depend_list)[:a.depend_num] == L.deps, i
+        if L.type == orc.YOLO:
+            assert a.class_num == 2 and [tuple(p) for p in a.anchor_list] == L.anchors and a.ignore_thres == np.float32(0.3)
+    want = np.concatenate([L.filt.reshape(-1) for L in layers if L.type == orc.CONV])
+    assert np.array_equal(net.packed_weights().view(np.uint32), want.view(np.uint32))
+    net.close()

@@ -144,3 +144,23 @@ def test_live_reference_bit_exact(assets):
     for i in (0, 57, 116, 129):
         assert np.array_equal(bits(outs[i]), bits(routs[i])), i
     assert raw.tobytes() == rraw.tobytes() and fin.tobytes() == rfin.tobytes()
+
+
+def test_second_graph_matches_reference_goldens(tmp_path):
+    """Widening case: a yolov3-tiny-like graph (dense 3x3, stride-2 max pools, avgpool, relu, grouped conv,
+    relative + absolute routes, two heads) -- the restatement must reproduce the compiled reference bit for bit."""
+    from ffcnn_b200 import tinygraph as tg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tinygraph.npz"))
+    cfg, wts = tg.write(str(tmp_path))
+    layers = orc.load_net(cfg, wts, 0, 0)
+    assert [L.type for L in layers].count(orc.YOLO) == 2 and [L.type for L in layers].count(orc.AVGPOOL) == 1
+    fr = tg.frames(3)
+    for f in range(3):
+        x, s1, s2 = orc.net_input(fr[f], tg.W, tg.H, tg.W, tg.H)
+        outs, raw, fin = orc.forward(layers, x, s1, s2, True)
+        if f == 0:
+            for i, o in enumerate(outs):
+                if o is not None:
+                    assert np.array_equal(bits(o), bits(g[f"v0_L{i}"])), i
+        assert raw.tobytes() == g[f"v0_f{f}_raw"].tobytes() and fin.tobytes() == g[f"v0_f{f}_final"].tobytes()
+        assert fin.tobytes() == g[f"v6_O2_f{f}_final"].tobytes() and len(fin) > 50
