@@ -268,7 +268,9 @@ def main():
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic["traffic"] if traffic else None, "traffic_of": traffic, "peak_source": peak_src, "kernel_share_of_step": tg["ms"] / total_ms, "layers_in_kernel": tg["layers"],
+                         "traffic": traffic["traffic"] if traffic else None, "traffic_of": traffic, "peak_source": peak_src,
+                         "accounting": "achieved = algorithmic bytes (SURVEY 8d, per layer, unfused) of the layers the kernel runs / its time; a fused block kernel is "
+                                       "charged the sum over the layers it replaces, its real DRAM traffic (traffic_of) is far lower -- the expanded tensors never reach HBM", "kernel_share_of_step": tg["ms"] / total_ms, "layers_in_kernel": tg["layers"],
                          "whole_graph": {"achieved": ALG_BYTES_PER_FRAME * B * K / (ms * 1e-3) / 1e9 / 1, "frac": ALG_BYTES_PER_FRAME * B * K / (ms * 1e-3) / 1e9 / peak,
                                          "alg_bytes_per_frame": ALG_BYTES_PER_FRAME},
                          "by_kernel": {k: {"ms": round(v["ms"], 4), "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
