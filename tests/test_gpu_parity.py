@@ -381,3 +381,36 @@ def test_second_darknet_graph_against_oracle(tmp_path):
                 tol = BOX_TOL + 2e-5 * max(float(e["x2"]) - float(e["x1"]), float(e["y2"]) - float(e["y1"]))
                 assert max(abs(float(g[k]) - float(e[k])) for k in ("x1", "y1", "x2", "y2")) <= tol, (g, e, tol)
         net.close()
+
+
+def test_cli_prints_the_reference_lines_and_draws_boxes(assets, golden, tmp_path):
+    """tools/ffcnn_cli.c on test.bmp: the stdout of the reference's `./ffcnn 2 test.bmp cfg weights` (ffcnn.c:552-593) --
+    banner, net_dump table, timing, net_profile, one line per box -- and out.bmp with the boxes drawn; the batched mode
+    gives the same lines per frame."""
+    import subprocess
+    cfg, wts, bmp = assets
+    fb.build()
+    exe = os.path.join(REPO, "ffcnn_b200", "ffcnn_cli")
+    want = ["score: %.2f, category: %2d, rect: (%3d %3d %3d %3d)" % (b["score"], b["type"], int(b["x1"]), int(b["y1"]), int(b["x2"]), int(b["y2"]))
+            for b in golden["testbmp_640x448"]["v6_O2_final"]]
+    r = subprocess.run([exe, "2", bmp, cfg, wts], capture_output=True, text=True, cwd=tmp_path, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "file_bmp    : " + bmp and "2 times inference:" in r.stdout
+    assert lines[-len(want):] == want
+    assert sum(l.lstrip().startswith(("conv", "avgpool", "maxpool", "upsample", "dropout", "shortcut", "route", "yolo")) for l in lines) >= 131 + 8
+    src, w, h = ref.load_bmp(bmp)
+    out, w2, h2 = ref.load_bmp(str(tmp_path / "out.bmp"))
+    assert (w2, h2) == (w, h)
+    b = golden["testbmp_640x448"]["v6_O2_final"][0]
+    x1, y1, y2 = int(b["x1"]), int(b["y1"]), int(b["y2"])
+    ym = min(max((y1 + y2) // 2, 0), h - 1)
+    assert tuple(out[ym, 3 * x1:3 * x1 + 3]) == (0, 255, 0)                          # B,G,R of the left edge
+    assert (out != src).any() and (out != src).mean() < 0.05
+    r = subprocess.run([exe, "--batch", cfg, wts, bmp, bmp, bmp, "--out", "det"], capture_output=True, text=True, cwd=tmp_path, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    for f in range(3):
+        at = lines.index("frame %d: %s" % (f, bmp))
+        assert lines[at + 1:at + 1 + len(want)] == want
+        assert np.array_equal(ref.load_bmp(str(tmp_path / ("det%d.bmp" % f)))[0], out)

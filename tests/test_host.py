@@ -219,3 +219,28 @@ def test_parse_second_graph_matches_oracle_loader(tmp_path):
     want = np.concatenate([L.filt.reshape(-1) for L in layers if L.type == orc.CONV])
     assert np.array_equal(net.packed_weights().view(np.uint32), want.view(np.uint32))
     net.close()
+
+
+def _cli():
+    fb.build()
+    exe = os.path.join(REPO, "ffcnn_b200", "ffcnn_cli")
+    assert os.path.exists(exe)
+    return exe
+
+
+def test_cli_argument_and_error_behaviour(assets, tmp_path):
+    """tools/ffcnn_cli.c = the reference's test driver (ffcnn.c:552-593): same banner, same message and status for an
+    unreadable picture; without a GPU it reports the refused net_load instead of dereferencing NULL like the reference."""
+    cfg, wts, bmp = assets
+    exe = _cli()
+    r = subprocess.run([exe, "1", "/nonexistent.bmp"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.stdout.splitlines() == ["file_bmp    : /nonexistent.bmp", "file_cfg    : yolo-fastest-1.1.cfg",
+                                     "file_weights: yolo-fastest-1.1.weights", "failed to load bmp file: /nonexistent.bmp !"]
+    assert r.returncode == 255                                                       # main() returns -1
+    r = subprocess.run([exe, "--batch", cfg], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "usage" in r.stderr
+    if fb.device_count() <= 0:
+        for args in (["1", bmp, cfg, wts], ["--batch", cfg, wts, bmp]):
+            r = subprocess.run([exe] + args, capture_output=True, text=True, cwd=tmp_path)
+            assert r.returncode == 2 and "no CPU fallback" in r.stderr
+        assert not os.path.exists(tmp_path / "out.bmp")
