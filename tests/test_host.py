@@ -244,3 +244,24 @@ def test_cli_argument_and_error_behaviour(assets, tmp_path):
             r = subprocess.run([exe] + args, capture_output=True, text=True, cwd=tmp_path)
             assert r.returncode == 2 and "no CPU fallback" in r.stderr
         assert not os.path.exists(tmp_path / "out.bmp")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REPO, "oracle", "_ref", "ffcnn_ref_bench")), reason="oracle/_ref not built")
+def test_bench_reference_arm_prints_the_contract_line(assets):
+    """`bench.py --impl reference`: the compiled reference (conv-v6) on the host cores, one JSON line with the keys the
+    driver reads; under torchrun only rank 0 works."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=REPO)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "frames/s" and j["higher_is_better"] is True and j["value"] > 0
+    assert j["metric"].startswith("frames/sec yolo-fastest-1.1 320x320")
+    assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert j["e2e"] == {"value": j["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=60, cwd=REPO, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
