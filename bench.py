@@ -44,36 +44,78 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md: clocks.sm, clocks.max.sm and the
+    clocks_event_reasons nvidia-smi prints).  Read in-process through NVML -- the library nvidia-smi itself is a client of --
+    every 100 ms: a forked `nvidia-smi` per sample, and also one background `nvidia-smi -lms` process, held driver locks
+    long enough to slow the host-driven e2e loop by 8-16 % (profiles/r1n_notes.txt).  BENCH_CLOCKS=smi uses the recipe's
+    background `nvidia-smi -lms 200` process instead, BENCH_CLOCKS=off samples once before and once after."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.uuid, self.stop_flag = index, uuid, threading.Event()
+        self.mode = os.environ.get("BENCH_CLOCKS", "nvml")
+        self.sm, self.mask, self.max_mhz, self.proc, self.log, self.nv, self.h = [], 0, None, None, None, None, None
+
+    def begin(self):
+        if self.mode == "smi":
+            import tempfile
+            self.log = tempfile.TemporaryFile(mode="w+")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "200"],
+                                         stdout=self.log, stderr=subprocess.DEVNULL)
+            return
+        import pynvml as nv
+        nv.nvmlInit()
+        self.nv = nv
+        try:
+            self.h = nv.nvmlDeviceGetHandleByUUID(self.uuid) if self.uuid else nv.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        self.sample()
+        if self.mode != "off":
+            self.start()
+
+    def sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
 
     def run(self):
-        while not self.stop_flag.is_set():
+        while not self.stop_flag.wait(0.1):
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.sample()
             except Exception:
                 pass
-            self.stop_flag.wait(0.05)
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.log.seek(0)
+            rows = [[c.strip() for c in line.split(",")] for line in self.log.read().splitlines() if line.count(",") >= 7]
+            self.log.close()
+            self.sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+            mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+            self.max_mhz = mx[0] if mx else None
+            reasons = sorted({name for r in rows for (name, _), v in zip(self.REASONS, r[4:8]) if v.lower().startswith("active")})
+        else:
+            self.stop_flag.set()
+            if self.is_alive():
+                self.join(timeout=2)
+            if self.nv is not None:
+                try:
+                    self.sample()
+                except Exception:
+                    pass
+            reasons = sorted(name for name, bit in self.REASONS if self.mask & bit)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "source": "nvidia-smi -lms 200" if self.proc is not None else "nvml, in-process, every 100 ms" if self.mode != "off" else "nvml, before and after"}
 
 
 def run_reference(procs: int, frames_per_proc: int):
@@ -184,9 +226,12 @@ def main():
         step_resident(i)
     net.detect_finish()
     launches_per_step = (0 if net.get_option("input_fused") == 1 else 1) + net.launches_per_forward() + 2
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, "GPU-" + str(torch.cuda.get_device_properties(local).uuid) if hasattr(torch.cuda.get_device_properties(local), "uuid") else None)
     if rank == 0:
-        sampler.start()
+        try:
+            sampler.begin()
+        except Exception as ex:
+            print("bench.py: clock sampler unavailable: %s" % ex, file=sys.stderr)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -199,20 +244,24 @@ def main():
 
     # end to end through the public calls: pinned host frames -> decoded boxes on the host, every batch's H2D copy and
     # D2H read inside the timed region (ffb_submit_u8 / ffb_collect: the copy of batch i+1 overlaps the work on batch i)
-    for i in range(2):
-        net.detect_batch_u8(host[i % NB].data_ptr(), B, NET_W, NET_H, PITCH)
+    def run_e2e(steps):
+        moved = 0
+        net.submit_u8(host[0].data_ptr(), B, NET_W, NET_H, PITCH)
+        for i in range(steps):
+            if i + 1 < steps:
+                net.submit_u8(host[(i + 1) % NB].data_ptr(), B, NET_W, NET_H, PITCH)
+            net.collect()
+            moved += net.last_d2h_bytes()
+        return moved
+
+    run_e2e(W)                      # W untimed warm-up steps of the same pipelined path (copy stream, staging slots, graph)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    KE = max(3, K // 2)
+    KE = K
     d2h = 0
     t_wall = time.time()
     e0.record(stream)
-    net.submit_u8(host[0].data_ptr(), B, NET_W, NET_H, PITCH)
-    for i in range(KE):
-        if i + 1 < KE:
-            net.submit_u8(host[(i + 1) % NB].data_ptr(), B, NET_W, NET_H, PITCH)
-        net.collect()
-        d2h += net.last_d2h_bytes()
+    d2h = run_e2e(KE)
     e1.record(stream)
     barrier()
     ms_e2e = e0.elapsed_time(e1)

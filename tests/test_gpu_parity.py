@@ -17,7 +17,7 @@ import pytest
 import ffcnn_b200 as fb
 from ffcnn_b200 import synth
 from oracle import oracle as orc, ref
-from conftest import boxes_close
+from conftest import boxes_close, REPO
 
 pytestmark = pytest.mark.gpu
 
@@ -398,7 +398,10 @@ def test_cli_prints_the_reference_lines_and_draws_boxes(assets, golden, tmp_path
     lines = r.stdout.splitlines()
     assert lines[0] == "file_bmp    : " + bmp and "2 times inference:" in r.stdout
     assert lines[-len(want):] == want
-    assert sum(l.lstrip().startswith(("conv", "avgpool", "maxpool", "upsample", "dropout", "shortcut", "route", "yolo")) for l in lines) >= 131 + 8
+    import re
+    kinds = "conv|avgpool|maxpool|upsample|dropout|shortcut|route|yolo"
+    assert sum(bool(re.match(r"\s*\d+\s+(%s)\b" % kinds, l)) for l in lines) == 131                # net_dump: one row per layer
+    assert sum(bool(re.match(r"\s*(%s):\s+\d+ ms$" % kinds, l)) for l in lines) == 8                # net_profile: one row per layer type
     src, w, h = ref.load_bmp(bmp)
     out, w2, h2 = ref.load_bmp(str(tmp_path / "out.bmp"))
     assert (w2, h2) == (w, h)
