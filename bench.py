@@ -186,6 +186,11 @@ def main():
     if not torch.cuda.is_available() or fb.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    cpus_before = os.sched_getaffinity(0)
+    near = None
+    if os.environ.get("FFCNN_BENCH_NUMA", "0") == "1":      # opt-in until measured at 8 GPUs: allocate pinned frames next to the GPU
+        near = shard.bind_near_gpu(local)
+        print("bench.py rank %d: bound to GPU-local CPUs %s" % (rank, near), file=sys.stderr)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
@@ -326,6 +331,7 @@ def main():
                                            "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3), "layers": v["layers"]} for k, v in sorted(groups.items())}},
         }
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, cpus_before)         # the CPU baseline uses every host core
             try:
                 fps, desc = run_reference(cores, 40)
                 line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": desc}

@@ -56,3 +56,28 @@ def gather_box_counts(counts: list[int], dist) -> list[int]:
     for r in range(world):
         out += [int(v) for v in bufs[r][:int(sizes[r])]]
     return out
+
+
+def bind_near_gpu(device_index: int, uuid: str | None = None) -> list[int] | None:
+    """Pin this process to the CPUs NVML reports as local to the GPU, so pinned host frames are allocated on the GPU's NUMA
+    node and the H2D copies of the e2e path do not cross the socket interconnect (what `numactl --cpunodebind` does for a
+    per-GPU process).  Best effort: returns the CPU list applied, or None when NVML has no answer, the set is not a proper
+    subset of the CPUs this process may use, or it has fewer than 4 CPUs.  Call before allocating pinned memory; restore
+    with os.sched_setaffinity(0, previous) before starting CPU-side work that should use every core."""
+    import os
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            h = nv.nvmlDeviceGetHandleByUUID(uuid) if uuid else nv.nvmlDeviceGetHandleByIndex(device_index)
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(device_index)
+        allowed = os.sched_getaffinity(0)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (max(allowed) + 64) // 64)
+        near = {b + 64 * w for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & allowed
+        if len(near) < 4 or near == allowed:
+            return None
+        os.sched_setaffinity(0, near)
+        return sorted(near)
+    except Exception:
+        return None
