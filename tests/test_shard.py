@@ -56,3 +56,17 @@ def test_weight_broadcast_and_gather_world2(assets):
     assert n0 == n1 == 356576 * 4                   # one broadcast of the packed buffer, nothing else
     assert s0 == s1 != 0.0
     assert c0 == c1 == list(range(10))              # frame order restored across shards
+
+
+def test_bind_near_gpu_is_best_effort():
+    """Without NVML (this container) or when the GPU-local CPU set is everything the process may use, the helper leaves the
+    affinity mask alone and says so."""
+    import os
+    from ffcnn_b200 import shard
+    before = os.sched_getaffinity(0)
+    got = shard.bind_near_gpu(0)
+    try:
+        assert got is None or (set(got) < before and len(got) >= 4)
+        assert os.sched_getaffinity(0) == (before if got is None else set(got))
+    finally:
+        os.sched_setaffinity(0, before)
