@@ -255,7 +255,7 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
     const int oh = conv_out_dim(ih, op->fs, op->pad, op->stride), ow = conv_out_dim(iw, op->fs, op->pad, op->stride);
     const float *wt = op->d_prep, *sc = wt ? wt + (size_t)op->taps * op->fn_pad : NULL, *bi = sc ? sc + op->fn_pad : NULL;
     /* conv-v6.c:499 geometry -> its 5x5 path drops kernel row 0 on output row oh-2 (422-441) */
-    const bool v6_dw5 = op->pad == 2 && op->fs == 5 && op->stride == 1 && op->ic / op->groups == 1 && oh >= 4 && ow >= 5;
+    const bool v6_dw5 = op->pad == 2 && op->fs == 5 && op->stride == 1 && op->ic / op->groups == 1 && oh >= 4 && ow >= 4;
     const int skip = (v6_dw5 && !op->dw5_exact) ? oh - 2 : -1;
     ConvKind kind = op->kind;
     if ((kind == CK_DW_S1_3 || kind == CK_DW_S1_5 || kind == CK_DW3_S2) && (ldi != op->ic || ldo != op->fn || coff != 0)) kind = CK_GENERIC;

@@ -52,7 +52,7 @@ static float orc_act(float v, int act)
 /* is this the geometry that conv-v6.c:499 sends down its 5x5 depthwise fast path? */
 static int orc_is_v6_dw5(int ic, int ig, int pad, int stride, int fs, int ow, int oh)
 {
-    return pad == 2 && fs == 5 && stride == 1 && ic / ig == 1 && oh >= 4 && ow >= 5;
+    return pad == 2 && fs == 5 && stride == 1 && ic / ig == 1 && oh >= 4 && ow >= 4;   /* below 4x4 the reference reads out of bounds (undefined) */
 }
 
 void orc_groupconv(const float *in, const float *flt, float *out,

@@ -275,6 +275,20 @@ def test_ragged_and_odd_shapes_through_generic_kernel():
         assert rel_err(got, orc.conv_raw(x, f, iw, ih, ic, grp, pad, st, fs, fn, act, False)) < FEAT_TOL
 
 
+def test_dw5_quirk_on_the_smallest_maps():
+    """conv-v6's dropped kernel row on output row oh-2 (conv-v6.c:422-441) holds down to 4x4 maps (a 128-pixel net side);
+    below that the reference reads out of bounds and the GPU path computes the exact convolution."""
+    rng = np.random.default_rng(12)
+    for (iw, ih, ic, quirk) in ((4, 4, 8, True), (4, 9, 4, True), (9, 4, 12, True), (5, 5, 4, True), (3, 6, 4, False), (6, 3, 4, False)):
+        f = np.zeros((ic, 32), np.float32); f[:, :25] = rng.standard_normal((ic, 25)); f[:, 28] = rng.uniform(0.5, 1.5, ic); f[:, 29] = 0.1
+        x = rng.standard_normal((ic, ih, iw)).astype(np.float32)
+        got = fb.groupconv(x, f, iw, ih, ic, ic, 2, 1, 5, ic, 2)
+        want = orc.conv_raw(x, f, iw, ih, ic, ic, 2, 1, 5, ic, 2, quirk)
+        assert rel_err(got, want) < FEAT_TOL, (iw, ih, rel_err(got, want))
+        if quirk:
+            assert rel_err(got, orc.conv_raw(x, f, iw, ih, ic, ic, 2, 1, 5, ic, 2, False)) > 1e-3
+
+
 @pytest.mark.parametrize("fuse_block", [1, 2])
 def test_fused_blocks_against_oracle(assets, oracle_layers, fuse_block):
     """Block fusion (1x1 expand -> 3x3 depthwise -> 1x1 project [+ shortcut] as one kernel, block_mma.cu): every tensor the

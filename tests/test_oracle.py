@@ -146,6 +146,50 @@ def test_live_reference_bit_exact(assets):
     assert raw.tobytes() == rraw.tobytes() and fin.tobytes() == rfin.tobytes()
 
 
+@pytest.mark.skipif(not ref.available("v0"), reason="oracle/_ref not built (needs /root/reference)")
+def test_live_reference_random_shapes_bit_exact():
+    """160 seeded random operator shapes (ragged maps from 4x4 up, 1x1 / 3x3 s1,s2 / 5x5, dense, grouped, depthwise, all three
+    activations) through the restatement and the compiled reference: bit-exact against conv-v0 and against conv-v6.
+    Shapes stay inside what the reference itself computes without undefined behaviour:
+      * "same" padding (pad = fs/2): im2row walks the INPUT columns (conv-v6.c:16), other paddings overrun its scratch rows;
+      * fs*fs*ic/groups a multiple of 4 on the generic path: im2row never writes the pad lanes (conv-v6.c:9-24);
+      * depthwise (ic/groups == 1) with one filter per channel, the only form conv-v6's fast paths handle (conv-v6.c:486-503);
+      * 5x5 depthwise maps of at least 4x4 (conv-v6.c:291-465 reads out of bounds below that)."""
+    rng = np.random.default_rng(2026)
+    done = 0
+    while done < 160:
+        fs = int(rng.choice([1, 3, 5]))
+        st = int(rng.choice([1, 2])) if fs == 3 else 1
+        pad = fs // 2
+        ic = int(rng.choice([4, 8, 12, 16, 24]))
+        if fs > 1 and rng.random() < 0.5:
+            grp, fn = ic, ic                                                        # depthwise
+        else:
+            grp = int(rng.choice([1, 1, 2, 4]))
+            fn = grp * int(rng.integers(1, 6))
+            if grp > 1 and (fs * fs * (ic // grp)) % 4:
+                continue
+            if ic // grp == 1:
+                continue
+        iw, ih, act = int(rng.integers(4, 24)), int(rng.integers(4, 24)), int(rng.choice([0, 1, 2]))
+        k = fs * fs * (ic // grp); row = ((k + 3) & ~3) + 4
+        x = rng.standard_normal((ic, ih, iw)).astype(np.float32)
+        f = np.zeros((fn, row), np.float32); f[:, :k] = rng.standard_normal((fn, k))
+        f[:, row - 4] = rng.uniform(0.5, 1.5, fn); f[:, row - 3] = rng.uniform(-0.5, 0.5, fn)
+        shape = (iw, ih, ic, grp, pad, st, fs, fn, act)
+        assert np.array_equal(bits(orc.conv_raw(x, f, *shape, False)), bits(ref.groupconv(x, f, *shape, "v0"))), shape
+        assert np.array_equal(bits(orc.conv_raw(x, f, *shape, True)), bits(ref.groupconv(x, f, *shape, "v6_O2"))), shape
+        done += 1
+    # the conv-v6 5x5 quirk on the smallest maps it is defined for (4 wide / 4 high)
+    for (iw, ih) in ((4, 4), (4, 9), (9, 4), (5, 5)):
+        x = rng.standard_normal((4, ih, iw)).astype(np.float32)
+        f = np.zeros((4, 32), np.float32); f[:, :25] = rng.standard_normal((4, 25)); f[:, 28] = 1.0
+        a, b = orc.conv_raw(x, f, iw, ih, 4, 4, 2, 1, 5, 4, 0, True), ref.groupconv(x, f, iw, ih, 4, 4, 2, 1, 5, 4, 0, "v6_O2")
+        assert np.array_equal(bits(a), bits(b)), (iw, ih)
+        exact = orc.conv_raw(x, f, iw, ih, 4, 4, 2, 1, 5, 4, 0, False)
+        assert [int(r) for r in np.nonzero(np.abs(a - exact).max(axis=(0, 2)) > 1e-4)[0]] == [ih - 2]
+
+
 def test_second_graph_matches_reference_goldens(tmp_path):
     """Widening case: a yolov3-tiny-like graph (dense 3x3, stride-2 max pools, avgpool, relu, grouped conv,
     relative + absolute routes, two heads) -- the restatement must reproduce the compiled reference bit for bit."""
