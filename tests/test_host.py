@@ -265,3 +265,69 @@ def test_bench_reference_arm_prints_the_contract_line(assets):
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=60, cwd=REPO, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(not ref.available("v6_O2"), reason="oracle/_ref not built")
+def test_net_input_and_size_rounding_against_live_reference(assets):
+    """Random picture sizes (1x1 up), net sizes (including ones net_load rounds up to a multiple of 32, ffcnn.c:133-134), means
+    and norms: the host C net_input, the oracle and the compiled reference give the same input tensor bit for bit and the
+    same s1/s2 box rescale pair (ffcnn.c:259-289)."""
+    cfg, wts, _ = assets
+    rng = np.random.default_rng(7)
+    for case in range(16):
+        nw, nh = int(rng.choice([0, 32, 64, 96, 160, 320, 416])), int(rng.choice([0, 32, 64, 128, 224, 320]))
+        if nw and rng.random() < 0.3:
+            nw += int(rng.integers(1, 31))
+        w, h = (int(rng.integers(1, 500)), int(rng.integers(1, 400))) if case else (1, 1)
+        img = rng.integers(0, 256, (h, (3 * w + 3) & ~3), dtype=np.uint8)
+        mean, norm = tuple(float(v) for v in rng.uniform(0, 128, 3)), tuple(float(v) for v in rng.uniform(0.001, 0.02, 3))
+        r = ref.RefNet(cfg, wts, nw, nh, "v6_O2")
+        r.input_bgr(img, w, h, mean, norm)
+        want, hd = r.input_tensor().copy(), r.head()
+        rs, (RW, RH) = (hd.s1, hd.s2), (r.W, r.H)
+        r.close()
+        n = fb.Net(cfg, None, nw, nh, device=None)
+        assert tuple(n.input_whc[:2]) == (RW, RH), (nw, nh)
+        n.net_input(img, w, h, mean=mean, norm=norm)
+        assert (n.net.s1, n.net.s2) == rs, (w, h, RW, RH)
+        assert np.array_equal(n.input_tensor().view(np.uint32), want.view(np.uint32)), (w, h, RW, RH)
+        n.close()
+        xo, s1, s2 = orc.net_input(img, w, h, RW, RH, mean=mean, norm=norm)
+        assert (s1, s2) == rs and np.array_equal(xo.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.skipif(not ref.available("v6_O2"), reason="oracle/_ref not built")
+def test_loader_against_live_reference_on_random_graphs(tmp_path):
+    """40 random darknet graphs (tests/cfg_fuzz.py) with seeded weights, some truncated, some with an input-size override:
+    ffb_net_parse builds the same layer table as the compiled reference's net_load (type, geometry in and out, kernel,
+    stride, pad, groups, activation -- ffcnn.c:123-211) and the same packed, BN-folded weight buffer bit for bit
+    (ffcnn.c:213-236, short reads included); dependency lists and yolo parameters agree with the oracle's loader."""
+    import cfg_fuzz
+    rng = np.random.default_rng(41)
+    kinds = set()
+    for case in range(40):
+        text, convs, _ = cfg_fuzz.gen(rng)
+        cfg, wts = str(tmp_path / ("g%d.cfg" % case)), str(tmp_path / ("g%d.weights" % case))
+        with open(cfg, "w", newline="") as f:
+            f.write(text)
+        cut = None if rng.random() < 0.8 else float(rng.uniform(0.2, 0.95))
+        with open(wts, "wb") as f:
+            f.write(cfg_fuzz.weights(rng, convs, cut))
+        iw, ih = (0, 0) if rng.random() < 0.7 else (int(rng.integers(33, 200)), int(rng.integers(33, 200)))
+        r = ref.RefNet(cfg, wts, iw, ih, "v6_O2")
+        n = fb.Net(cfg, wts, iw, ih, device=None)
+        assert n.layer_num == r.n, case
+        for i in range(r.n):
+            a, b = n.layer(i), n.layer(i + 1)
+            assert [a.type, a.w, a.h, a.c, b.w, b.h, b.c, a.fs, a.stride, a.pad, a.groups, a.activation] == r.info[i], (case, i)
+            kinds.add(a.type)
+        assert np.array_equal(n.packed_weights().view(np.uint32), r.packed_weights().view(np.uint32)), (case, cut)
+        for i, L in enumerate(orc.load_net(cfg, wts, iw, ih)):
+            a = n.layer(i)
+            if L.type in (orc.SHORTCUT, orc.ROUTE):
+                assert list(a.depend_list)[:a.depend_num] == L.deps, (case, i)
+            if L.type == orc.YOLO:
+                assert a.class_num == L.classes and [tuple(p) for p in a.anchor_list] == L.anchors, (case, i)
+                assert a.ignore_thres == np.float32(L.ignore_thresh) and a.scale_x_y == np.float32(L.scale_x_y), (case, i)
+        n.close(); r.close()
+    assert kinds == set(range(8))                       # every layer type of ffcnn.h:4-14 was exercised

@@ -208,3 +208,39 @@ def test_second_graph_matches_reference_goldens(tmp_path):
                     assert np.array_equal(bits(o), bits(g[f"v0_L{i}"])), i
         assert raw.tobytes() == g[f"v0_f{f}_raw"].tobytes() and fin.tobytes() == g[f"v0_f{f}_final"].tobytes()
         assert fin.tobytes() == g[f"v6_O2_f{f}_final"].tobytes() and len(fin) > 50
+
+
+@pytest.mark.skipif(not ref.available("v0"), reason="oracle/_ref not built (needs /root/reference)")
+def test_random_graphs_forward_bit_exact_against_live_reference(tmp_path):
+    """25 random darknet graphs (tests/cfg_fuzz.py: every layer type, ragged maps, grouped / depthwise / unpadded convs,
+    1-4 input routes, one or two yolo heads) on random pictures of random size: every layer output, the pre-NMS candidates
+    and the final boxes of the restatement equal the compiled reference's (conv-v0, exact math) bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cfg_fuzz
+    rng = np.random.default_rng(77)
+    boxes = 0
+    for case in range(25):
+        text, convs, _ = cfg_fuzz.gen(rng)
+        cfg, wts = str(tmp_path / ("g%d.cfg" % case)), str(tmp_path / ("g%d.weights" % case))
+        with open(cfg, "w", newline="") as f:
+            f.write(text)
+        with open(wts, "wb") as f:
+            f.write(cfg_fuzz.weights(rng, convs))
+        r = ref.RefNet(cfg, wts, 0, 0, "v0")
+        layers = orc.load_net(cfg, wts, 0, 0)
+        w, h = int(rng.integers(20, 200)), int(rng.integers(20, 200))
+        img = rng.integers(0, 256, (h, (3 * w + 3) & ~3), dtype=np.uint8)
+        r.input_bgr(img, w, h)
+        routs, rraw, rfin = r.forward_dump()
+        x, s1, s2 = orc.net_input(img, w, h, r.W, r.H)
+        outs, raw, fin = orc.forward(layers, x, s1, s2, False)
+        for i, (a, b) in enumerate(zip(outs, routs)):
+            assert (a is None) == (b is None), (case, i)
+            if a is not None:
+                assert a.shape == b.shape and np.array_equal(bits(a), bits(b)), (case, i, layers[i].type)
+        assert raw[:4096].tobytes() == rraw.tobytes(), case            # the harness returns at most 4096 candidates
+        assert fin.tobytes() == rfin.tobytes(), case
+        boxes += len(fin)
+        r.close()
+    assert boxes > 1000
