@@ -331,3 +331,49 @@ def test_loader_against_live_reference_on_random_graphs(tmp_path):
                 assert a.ignore_thres == np.float32(L.ignore_thresh) and a.scale_x_y == np.float32(L.scale_x_y), (case, i)
         n.close(); r.close()
     assert kinds == set(range(8))                       # every layer type of ffcnn.h:4-14 was exercised
+
+
+def test_host_decode_and_nms_on_random_graphs(tmp_path):
+    """The host C decode + NMS (host_decode.c, what ffb_detect_finish runs on the GPU's candidates) on the head tensors of
+    random graphs -- 1-4 classes, random masks / anchors / thresholds / scale_x_y, one or two heads, thousands of candidates:
+    same raw candidates and same final boxes, bit for bit, as the oracle's decode (ffcnn.c:438-474, 291-335), which
+    tests/test_oracle.py pins against the compiled reference on the same generator."""
+    import cfg_fuzz
+    L = fb.lib()
+    L.ffb_decode_head_chw.argtypes = [C.POINTER(fb.LAYER), C.POINTER(C.c_float)] + [C.c_int] * 4 + [C.POINTER(fb.BBOX), C.c_int, C.c_int]
+    L.ffb_decode_head_chw.restype = C.c_int
+    L.ffb_nms.argtypes = [C.POINTER(fb.BBOX), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.ffb_nms.restype = C.c_int
+    rng = np.random.default_rng(303)
+    heads = total = 0
+    for case in range(30):
+        text, convs, _ = cfg_fuzz.gen(rng)
+        if "[yolo]" not in text:
+            continue
+        cfg, wts = str(tmp_path / ("g%d.cfg" % case)), str(tmp_path / ("g%d.weights" % case))
+        with open(cfg, "w", newline="") as f:
+            f.write(text)
+        with open(wts, "wb") as f:
+            f.write(cfg_fuzz.weights(rng, convs))
+        layers = orc.load_net(cfg, wts, 0, 0)
+        W, H = layers[0].w, layers[0].h
+        w, h = int(rng.integers(20, 300)), int(rng.integers(20, 300))
+        img = rng.integers(0, 256, (h, (3 * w + 3) & ~3), dtype=np.uint8)
+        x, s1, s2 = orc.net_input(img, w, h, W, H)
+        outs, raw, fin = orc.forward(layers, x, s1, s2, False)
+        net = fb.Net(cfg, wts, 0, 0, device=None)
+        cap = W * H * 3 * 4 // 24                                             # bbox_max of the reference, ffcnn.c:243
+        boxes = (fb.BBOX * cap)()
+        n = 0
+        for i, Ly in enumerate(layers):
+            if Ly.type == orc.YOLO:
+                head = np.ascontiguousarray(outs[i - 1])
+                n = L.ffb_decode_head_chw(C.byref(net.layer(i)), head.ctypes.data_as(C.POINTER(C.c_float)), head.shape[2], head.shape[1], W, H, boxes, n, cap)
+                heads += 1
+        assert n == len(raw), (case, n, len(raw))
+        assert C.string_at(boxes, n * 24) == raw.tobytes(), case
+        m = L.ffb_nms(boxes, n, 0.5, 1, s1, s2)
+        assert m == len(fin) and C.string_at(boxes, m * 24) == fin.tobytes(), case
+        total += n
+        net.close()
+    assert heads >= 10 and total > 5000
