@@ -18,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libffcnn_b200.so")
+LIB_PATH = os.environ.get("FFCNN_LIB") or os.path.join(HERE, "libffcnn_b200.so")     # FFCNN_LIB: a developer build (e.g. `make tc`)
 ASSETS = os.path.join(REPO, "baseline", "_ref")
 
 BOX_DTYPE = np.dtype([("type", "<i4"), ("score", "<f4"), ("x1", "<f4"), ("y1", "<f4"), ("x2", "<f4"), ("y2", "<f4")])

@@ -21,18 +21,20 @@ struct BlkPlan {
     int cin, cexp, cout, S, H, W, OH, OW, res;
     int KS1, NT3, MTW, MINB, G, GC, NC, TH, TW, HH, HW, SEs, xrows, chunk_floats, occ;
     int XH, XW, xo, yo, frame;
+    int tc, nmt, tmem_cols;               /* experimental tcgen05 expand (FFCNN_BLK_TC=1): m-tiles of the x tile, TMEM columns */
     float slope1, sloped, slope3, slope_res;
     size_t smem;
     float *d_chunks, *d_sb3;
     int row1, rowd, row3;
     int num_sms;
-    char desc[96];
+    char desc[128];
 };
 
 typedef void (*BlkKernel)(const CUtensorMap, const BlkArgs);
-struct BlkInst { int KS1, NT3, S, MTW, GC, MINB; BlkKernel fn; size_t configured; };
+struct BlkInst { int KS1, NT3, S, MTW, GC, MINB; BlkKernel fn; size_t configured; int tc; };
 
-#define INST(K, N, S, M, G, B) { K, N, S, M, G, B, k_block_mma<K, N, S, M, G, B>, 0 }
+#define INST(K, N, S, M, G, B) { K, N, S, M, G, B, k_block_mma<K, N, S, M, G, B>, 0, 0 }
+#define INST_TC(K, N, S, M, G) { K, N, S, M, G, 2, k_block_mma<K, N, S, M, G, 2, true>, 0, 1 }
 #define INST3(K, N, S, G) INST(K, N, S, 1, G, 2), INST(K, N, S, 2, G, 2), INST(K, N, S, 4, G, 2)
 #define INST2(K, N, S, G) INST(K, N, S, 1, G, 2), INST(K, N, S, 2, G, 2)
 static BlkInst g_inst[] = {
@@ -44,14 +46,21 @@ static BlkInst g_inst[] = {
     INST2(3, 3, 1, 1), INST2(3, 3, 1, 3),                         /* 24->136->24 */
     INST2(3, 6, 2, 1), INST2(3, 6, 2, 3),                         /* 24->136->48 s2 */
     INST2(6, 6, 1, 1), INST2(6, 6, 1, 2),                         /* 48->224->48 */
+#ifdef FFB_BLK_TC
+    /* experimental: expand GEMM on tcgen05 (build with EXTRA=-DFFB_BLK_TC, run with FFCNN_BLK_TC=1), the (tile, group) shapes the
+       default plan of yolo-fastest-1.1 uses */
+    INST_TC(1, 1, 1, 2, 2), INST_TC(1, 1, 2, 1, 2), INST_TC(1, 1, 1, 2, 3), INST_TC(1, 2, 1, 2, 3),
+    INST_TC(2, 2, 1, 2, 2), INST_TC(2, 3, 2, 1, 3), INST_TC(3, 3, 1, 2, 3), INST_TC(6, 6, 1, 1, 1),
+#endif
 };
 #undef INST3
 #undef INST2
 #undef INST
+#undef INST_TC
 
-static BlkInst *find_inst(int KS1, int NT3, int S, int MTW, int GC)      /* MTW / GC == 0: any */
+static BlkInst *find_inst(int KS1, int NT3, int S, int MTW, int GC, int tc = 0)      /* MTW / GC == 0: any */
 {
-    for (BlkInst &i : g_inst) if (i.KS1 == KS1 && i.NT3 == NT3 && i.S == S && (!MTW || i.MTW == MTW) && (!GC || i.GC == GC)) return &i;
+    for (BlkInst &i : g_inst) if (i.tc == tc && i.KS1 == KS1 && i.NT3 == NT3 && i.S == S && (!MTW || i.MTW == MTW) && (!GC || i.GC == GC)) return &i;
     return nullptr;
 }
 
@@ -80,7 +89,7 @@ static bool plan_tile(BlkPlan *p)
     for (int GC = 1; GC <= G && GC <= 4; GC++) {
         if (G % GC || (fGC && GC != fGC)) continue;
         const int NC = G / GC, SEs = 16 * GC + (S == 1 ? 8 : 4);
-        const BlkChunk off(GC, KS1, NT3);
+        const BlkChunk off(GC, KS1, NT3, p->tc != 0);
         for (int TW = 2; TW <= p->OW && TW <= 80; TW += 2) {
             if (fTW && TW != fTW) continue;
             for (int TH = 1; TH <= p->OH && TH <= 80; TH++) {
@@ -90,16 +99,20 @@ static bool plan_tile(BlkPlan *p)
                 int MTW = (M3 + BLK_WARPS - 1) / BLK_WARPS;
                 if (MTW > 1 && (TH & 1)) continue;                     /* quads need whole row pairs */
                 if (MTW > 1) { const int nquads = ((TH + 1) / 2 * TW + 15) / 16; MTW = 2 * ((nquads + BLK_WARPS - 1) / BLK_WARPS); }
-                const BlkInst *inst = find_inst(KS1, NT3, S, MTW, GC);
+                const BlkInst *inst = find_inst(KS1, NT3, S, MTW, GC, p->tc);
                 if (!inst) continue;
                 const int HH = (TH - 1) * S + 3, HW = (TW - 1) * S + 3;
                 const bool frame = TH >= p->OH && TW >= p->OW;        /* the halo ring is all padding: fetch / expand the image only */
                 const int XH = frame ? p->H : HH, XW = frame ? p->W : HW;
                 if (XH > 256 || XW > 256) continue;
                 const int M1 = (XH * XW + 15) / 16, xrows = 32 * ((M1 + 1) / 2);
-                const size_t smem = 4 * (size_t)(128 + 2 * xrows + 2 * off.total + 2 * xrows * SXs + HH * HW * SEs) + 128;
+                const size_t smem = 4 * (size_t)(128 + 2 * xrows + 2 * off.total + 2 * xrows * SXs + HH * HW * SEs) + 128 + (p->tc ? 1024 : 0);
                 if (smem > 225 * 1024) continue;
                 int occ = (int)((228 * 1024) / (smem + 1024)); if (occ > inst->MINB) occ = inst->MINB; if (occ < 1) occ = 1;
+                /* TC: x_hi | x_lo and the double-buffered accumulators of every 128-pixel m-tile live in TMEM (512 columns per SM) */
+                const int nmt = (XH * XW + 127) / 128;
+                int tmem_cols = 32; while (tmem_cols < nmt * (16 * KS1 + 32 * GC)) tmem_cols *= 2;
+                if (p->tc) { if (tmem_cols > 512) continue; if (occ * tmem_cols > 512) occ = 512 / tmem_cols; }
                 /* per-tile cost on one SM, three candidate limiters (profiles/r1j: shared-memory wavefronts bind first):
                    wf  = shared-memory wavefronts (1 per clk), mma = m16n8k8 tensor ops (2.14 clk each), ins = issue slots / 4 */
                 const int MT = KS1 * GC >= 6 ? 1 : 2, items = (M1 + MT - 1) / MT, rounds = (items + BLK_WARPS - 1) / BLK_WARPS;
@@ -120,7 +133,7 @@ static bool plan_tile(BlkPlan *p)
                     best = score; ok = true;
                     p->GC = GC; p->NC = NC; p->SEs = SEs; p->TH = TH; p->TW = TW; p->HH = HH; p->HW = HW; p->MTW = MTW; p->MINB = inst->MINB;
                     p->xrows = xrows; p->chunk_floats = off.total; p->smem = smem; p->occ = occ;
-                    p->XH = XH; p->XW = XW; p->frame = frame; p->xo = p->yo = frame ? 1 : 0;
+                    p->XH = XH; p->XW = XW; p->frame = frame; p->xo = p->yo = frame ? 1 : 0; p->nmt = nmt; p->tmem_cols = tmem_cols;
                 }
             }
         }
@@ -137,20 +150,32 @@ BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
     p->OH = (h - 3 + 2) / stride + 1; p->OW = (w - 3 + 2) / stride + 1;
     if (p->OW % 2 || p->OH < 1) { delete p; return nullptr; }
     p->KS1 = (cin + 7) / 8; p->NT3 = (cout + 7) / 8; p->G = (cexp + 15) / 16;
+    static const int env_tc = getenv("FFCNN_BLK_TC") ? atoi(getenv("FFCNN_BLK_TC")) : 0;      /* experimental, not yet validated on a GPU */
+    p->tc = env_tc ? 1 : 0;
     /* round up to an instantiated (KS1, NT3) pair: zero-padded K / N lanes cost tensor work, not correctness */
     bool found = false;
     for (int k = p->KS1; k <= 6 && !found; k++)
         for (int n = p->NT3; n <= 6 && !found; n++)
-            if (find_inst(k, n, stride, 0, 0)) { p->KS1 = k; p->NT3 = n; found = true; }
+            if (find_inst(k, n, stride, 0, 0, p->tc)) { p->KS1 = k; p->NT3 = n; found = true; }
+    if (!found && p->tc) {                  /* no tcgen05 instance for this shape: the mma.sync kernel */
+        p->tc = 0;
+        for (int k = p->KS1; k <= 6 && !found; k++)
+            for (int n = p->NT3; n <= 6 && !found; n++)
+                if (find_inst(k, n, stride, 0, 0, 0)) { p->KS1 = k; p->NT3 = n; found = true; }
+    }
     if (!found) { delete p; return nullptr; }
     p->slope1 = slope_of(act1); p->sloped = slope_of(actd); p->slope3 = slope_of(act3); p->slope_res = slope_of(act_res);
     p->row1 = ((cin + 3) & ~3) + 4; p->rowd = 16; p->row3 = ((cexp + 3) & ~3) + 4;
-    if (!plan_tile(p)) { delete p; return nullptr; }
+    if (!plan_tile(p)) {
+        if (!p->tc) { delete p; return nullptr; }
+        p->tc = 0;                              /* the tcgen05 instances cover fewer tiles */
+        if (!plan_tile(p)) { delete p; return nullptr; }
+    }
     int dev = 0; cudaDeviceProp prop;
     cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
     p->num_sms = prop.multiProcessorCount;
-    snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s tile %dx%d%s gc%d mtw%d smem %zuKB occ%d", cin, cexp, cout, stride, res ? "+res" : "",
-             p->TH, p->TW, p->frame ? " (frame)" : "", p->GC, p->MTW, p->smem >> 10, p->occ);
+    snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s tile %dx%d%s gc%d mtw%d smem %zuKB occ%d%s", cin, cexp, cout, stride, res ? "+res" : "",
+             p->TH, p->TW, p->frame ? " (frame)" : "", p->GC, p->MTW, p->smem >> 10, p->occ, p->tc ? " tcgen05-expand" : "");
     return p;
 }
 
@@ -170,14 +195,14 @@ int blk_prepare(BlkPlan *p, const float *p1, const float *pd, const float *p3, c
         ffb_set_error("block_mma: cudaMalloc failed"); return -1;
     }
     k_prep_block<<<(int)((nfl + 16 * p->NT3 + 255) / 256), 256, 0, st>>>(p1, p->row1, p->cin, pd, p->rowd, p3, p->row3, p->cexp, p->cout,
-                                                                         p->KS1, p->NT3, p->GC, p->NC, p->d_chunks, p->d_sb3);
+                                                                         p->KS1, p->NT3, p->GC, p->NC, p->d_chunks, p->d_sb3, p->tc);
     if (cudaGetLastError() != cudaSuccess) { ffb_set_error("block_mma: weight preparation launch failed"); return -1; }
     return 0;
 }
 
 int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st)
 {
-    BlkInst *inst = find_inst(p->KS1, p->NT3, p->S, p->MTW, p->GC);
+    BlkInst *inst = find_inst(p->KS1, p->NT3, p->S, p->MTW, p->GC, p->tc);
     if (!inst) { ffb_set_error("block_mma: no kernel instance"); return -1; }
     if (p->smem > inst->configured) {
         if (cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess) { ffb_set_error("block_mma: cannot set smem %zu", p->smem); return -1; }
@@ -189,6 +214,9 @@ int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
     a.TH = p->TH; a.TW = p->TW; a.HH = p->HH; a.HW = p->HW; a.ntx = (p->OW + p->TW - 1) / p->TW; a.nty = (p->OH + p->TH - 1) / p->TH;
     a.ntiles = (long)n * a.ntx * a.nty;
     a.NC = p->NC; a.xrows = p->xrows;
+#ifdef FFB_BLK_TC
+    a.nmt = p->nmt; a.tmem_cols = (uint32_t)p->tmem_cols;
+#endif
     a.XH = p->XH; a.XW = p->XW; a.xo = p->xo; a.yo = p->yo; a.frame = p->frame;
     a.inv_tpf = 1.0f / (float)(a.ntx * a.nty); a.inv_ntx = 1.0f / (float)a.ntx;
     CUtensorMap tm;

@@ -58,6 +58,9 @@ struct BlkArgs {
     int N, H, W, OH, OW, ldx, ldy, cout;
     int TH, TW, HH, HW, ntx, nty; long ntiles;
     int NC, xrows;
+#ifdef FFB_BLK_TC
+    int nmt; uint32_t tmem_cols;          /* TC: 128-pixel m-tiles of the x tile, TMEM columns to allocate (power of 2) */
+#endif
     int XH, XW, xo, yo, frame;            /* x-tile box and its offset inside the halo; frame: one tile covers the whole image */
     float inv_tpf, inv_ntx;
     float slope1, sloped, slope3, slope_res; int res;
@@ -66,9 +69,12 @@ struct BlkArgs {
 /* per-chunk section offsets (floats) */
 struct BlkChunk {
     int w1, s1, b1, wd, sd, bd, w2, total;
-    __host__ __device__ constexpr BlkChunk(int GC, int KS1, int NT3)
-        : w1(0), s1(GC * 2 * KS1 * 128), b1(s1 + GC * 16), wd(b1 + GC * 16), sd(wd + GC * 144), bd(sd + GC * 16),
-          w2(bd + GC * 16), total(w2 + GC * 2 * NT3 * 128) {}
+    /* TC (tcgen05 expand, experimental): the w1 section is the UMMA B operand instead of mma.sync fragments -- hi and lo
+       parts, each (KS1+3)/4 K-major SWIZZLE_128B sub-tiles of [16*GC channels x 32 cin] floats (128-byte rows, 8-row atoms
+       of 1024 B), so the section starts the chunk and the chunk is padded to a multiple of 1024 B */
+    __host__ __device__ constexpr BlkChunk(int GC, int KS1, int NT3, bool TC = false)
+        : w1(0), s1(TC ? 2 * ((KS1 + 3) / 4) * 16 * GC * 32 : GC * 2 * KS1 * 128), b1(s1 + GC * 16), wd(b1 + GC * 16), sd(wd + GC * 144),
+          bd(sd + GC * 16), w2(bd + GC * 16), total(TC ? (w2 + GC * 2 * NT3 * 128 + 255) / 256 * 256 : w2 + GC * 2 * NT3 * 128) {}
 };
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
@@ -129,7 +135,7 @@ __device__ __forceinline__ BlkTile blk_tile(const BlkArgs &a, long tile)
  * of the (row pair, x) sequence in the upper and the lower row -- so a lane owns a 2x2 pixel quad and its 3x3 stencils
  * share loads: (S+3)^2 shared-memory reads per quad instead of 2 * 3 * (S+3).
  */
-template <int KS1, int NT3, int S, int MTW, int GC, int MINB>
+template <int KS1, int NT3, int S, int MTW, int GC, int MINB, bool TC = false>
 __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_constant__ CUtensorMap tmX, const BlkArgs a)
 {
     extern __shared__ __align__(128) float4 blk_smem4[];
@@ -139,16 +145,23 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     constexpr int MT = (KS1 * GC >= 6) ? 1 : 2;           /* m-tiles per stage-A work item (bounds the accumulator registers; 1 also spreads the 7 m-tiles of a 10x10 frame over 7 warps) */
     constexpr bool QUAD = MTW >= 2;
     constexpr int NQ = QUAD ? MTW / 2 : 1;                /* quads (or single m-tiles) per warp */
-    constexpr BlkChunk off(GC, KS1, NT3);
+    constexpr BlkChunk off(GC, KS1, NT3, TC);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int HW = a.HW;
     float    *sSB3 = smem;                                          /* 96 floats */
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 96);       /* full_x[2], full_w[2] */
     int2     *sMap = reinterpret_cast<int2 *>(smem + 128);          /* [xrows]: x-tile pixel -> { byte offset of its E row or -1, hy | hx << 16 } */
     float    *sW = smem + 128 + 2 * a.xrows;
+#ifdef FFB_BLK_TC
+    if (TC) sW += ((1024u - (sm100::smem_u32(sW) & 1023u)) & 1023u) >> 2;   /* UMMA SWIZZLE_128B atoms are 1024-byte aligned */
+#endif
     float    *sXB = sW + 2 * off.total;                             /* [2][xrows * SXs] */
     float    *sE = sXB + 2 * a.xrows * SXs;
     uint64_t *full_x = bars, *full_w = bars + 2;
+#ifdef FFB_BLK_TC
+    uint64_t *dfull = bars + 4;                                     /* TC: expand accumulator buffer [2] written (tcgen05.commit) */
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+#endif
     const uint32_t sE_addr = sm100::smem_u32(sE), sW_addr = sm100::smem_u32(sW);
     const uint32_t x_bytes = (uint32_t)a.XH * a.XW * SXs * 4;
     constexpr uint32_t w_bytes = (uint32_t)off.total * 4;
@@ -156,9 +169,16 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
 
     if (tid == 0) {
         sm100::tma_prefetch_desc(&tmX);
+#ifdef FFB_BLK_TC
+        for (int i = 0; i < 6; i++) sm100::mbar_init(bars + i, 1);
+#else
         for (int i = 0; i < 4; i++) sm100::mbar_init(bars + i, 1);
+#endif
         sm100::fence_barrier_init();
     }
+#ifdef FFB_BLK_TC
+    if (TC && warp == 0) sm100::tmem_alloc(tmem_slot, a.tmem_cols);
+#endif
     if (tid < 2 * COUT_P) sSB3[tid] = a.sb3[tid];
     for (int xp = tid; xp < a.xrows; xp += BLK_THREADS) {
         const int ry = xp / a.XW, rx = xp - ry * a.XW, hy = ry + a.yo, hx = rx + a.xo;
@@ -180,8 +200,41 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     const int nunits = QUAD ? ((a.TH + 1) / 2 * a.TW + 15) >> 4 : (a.TH * a.TW + 15) >> 4;
     const int nq = warp < nunits ? (nunits - warp + BLK_WARPS - 1) / BLK_WARPS : 0;     /* units this warp owns (warp-uniform) */
     const uint32_t rowpitch = (uint32_t)HW * SEs * 4;
+#ifdef FFB_BLK_TC
+    if (TC) sm100::tc_fence_before_sync();
+#endif
     __syncthreads();
+#ifdef FFB_BLK_TC
+    if (TC) sm100::tc_fence_after_sync();
+#endif
     pdl_trigger(); pdl_wait();
+#ifdef FFB_BLK_TC
+    /* ---- TC: expand GEMM on tcgen05.  TMEM columns: per 128-pixel m-tile mt the A operand [x_hi (KP cols) | x_lo (KP cols)]
+       at mt * 2KP, then the accumulators D[mt][buf] (16*GC cols each, double buffered over chunks) ---- */
+    constexpr int KP = 8 * KS1, KC = (KS1 + 3) / 4;
+    const uint32_t tmem_base = TC ? *tmem_slot : 0u;
+    const uint32_t tq_addr = (uint32_t)((warp & 3) * 32) << 16;                 /* this warp's TMEM lane quarter */
+    const uint32_t dcol0 = tmem_base + (uint32_t)a.nmt * 2 * KP;
+    auto issue_expand = [&](uint32_t wslot, uint32_t buf) {                     /* one thread: chunk in weight slot wslot -> D[.][buf] */
+        constexpr uint32_t sub = 16 * GC * 128;                                 /* bytes of one [16*GC x 32] B sub-tile */
+        constexpr uint32_t idesc = sm100::umma_idesc_tf32(128, 16 * GC);
+        const uint32_t bh = sW_addr + wslot * (uint32_t)off.total * 4, bl = bh + KC * sub;
+        for (int mt = 0; mt < a.nmt; mt++) {
+            const uint32_t d = dcol0 + (uint32_t)(mt * 2 + buf) * 16 * GC;
+            const uint32_t ahi = tmem_base + (uint32_t)mt * 2 * KP, alo = ahi + KP;
+#pragma unroll
+            for (int ks = 0; ks < KS1; ks++)                                    /* x_lo . W_hi */
+                sm100::mma_tf32_ts(d, alo + 8 * ks, sm100::umma_desc_sw128(bh + (ks >> 2) * sub + (ks & 3) * 32), idesc, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < KS1; ks++)                                    /* x_hi . W_lo */
+                sm100::mma_tf32_ts(d, ahi + 8 * ks, sm100::umma_desc_sw128(bl + (ks >> 2) * sub + (ks & 3) * 32), idesc, 1);
+#pragma unroll
+            for (int ks = 0; ks < KS1; ks++)                                    /* x_hi . W_hi */
+                sm100::mma_tf32_ts(d, ahi + 8 * ks, sm100::umma_desc_sw128(bh + (ks >> 2) * sub + (ks & 3) * 32), idesc, 1);
+        }
+        sm100::tc_commit(dfull + buf);
+    };
+#endif
 
     auto load_x = [&](long tile, int b) {                                       /* one thread */
         const BlkTile q = blk_tile<S>(a, tile);
@@ -215,6 +268,37 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                 for (int j = 0; j < 4; j++) pacc[mi][nt][j] = 0.f;
         sm100::mbar_wait(full_x + xb, (it >> 1) & 1);
 
+#ifdef FFB_BLK_TC
+        if constexpr (TC) {
+            /* x tile -> TMEM as the A operand, split hi/lo (thread = pixel = TMEM lane); x itself stays untouched in shared
+               memory for the shortcut.  All expand MMAs of the previous tile have completed (their dfull waits). */
+            for (int mt = warp >> 2; mt < a.nmt; mt += BLK_WARPS / 4) {
+                const int p = mt * 128 + (warp & 3) * 32 + lane;
+                const float *xr = sX + p * SXs;
+                const uint32_t acol = tmem_base + tq_addr + (uint32_t)mt * 2 * KP;
+#pragma unroll
+                for (int ks = 0; ks < KS1; ks++) {
+                    float4 x0 = blk_zero4(), x1 = blk_zero4();
+                    if (p < XP) { x0 = *reinterpret_cast<const float4 *>(xr + 8 * ks); x1 = *reinterpret_cast<const float4 *>(xr + 8 * ks + 4); }
+                    uint32_t hi[8], lo[8];
+                    split_tf32(x0.x, hi[0], lo[0]); split_tf32(x0.y, hi[1], lo[1]); split_tf32(x0.z, hi[2], lo[2]); split_tf32(x0.w, hi[3], lo[3]);
+                    split_tf32(x1.x, hi[4], lo[4]); split_tf32(x1.y, hi[5], lo[5]); split_tf32(x1.z, hi[6], lo[6]); split_tf32(x1.w, hi[7], lo[7]);
+                    sm100::tmem_st8(acol + 8 * ks, hi);
+                    sm100::tmem_st8(acol + KP + 8 * ks, lo);
+                }
+            }
+            sm100::tmem_st_wait();
+            sm100::tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {                               /* chunk 0 of this tile: its weights were requested during the previous tile */
+                const uint32_t ws0 = (a.NC == 1) ? 0u : (cs & 1u);
+                sm100::mbar_wait(full_w + ws0, (a.NC == 1) ? 0u : ((cs >> 1) & 1u));
+                sm100::tc_fence_after_sync();
+                issue_expand(ws0, cs & 1u);
+            }
+        }
+#endif
+
         for (int c = 0; c < a.NC; c++, cs++) {
             const int wb = w_resident ? 0 : cs & 1;
             sm100::mbar_wait(full_w + wb, w_resident ? 0 : (cs >> 1) & 1);
@@ -223,6 +307,43 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
             const float *wc = sW + wb * off.total;
             const float *wl4 = wc + lane * 4, *wt4 = wc + 4 * t;
 
+#ifdef FFB_BLK_TC
+            bool expand_pending = false;
+            if constexpr (TC) {
+                /* ---------------- stage A (TC): the chunk's expand accumulators TMEM -> BN + act -> E rows ---------------- */
+                const uint32_t buf = cs & 1u;
+                sm100::mbar_wait(dfull + buf, (cs >> 1) & 1u);
+                sm100::tc_fence_after_sync();
+                for (int mt = warp >> 2; mt < a.nmt; mt += BLK_WARPS / 4) {
+                    const int p = mt * 128 + (warp & 3) * 32 + lane;
+                    const int2 mp = p < a.xrows ? sMap[p] : make_int2(-1, 0);
+                    bool inside = true;
+                    if (border && mp.x >= 0) {            /* halo pixels outside the image are the depthwise conv's zero padding */
+                        const int iy = q.iy0 + (mp.y & 0xffff), ix = q.ix0 + (mp.y >> 16);
+                        inside = (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W;
+                    }
+                    const uint32_t dcol = dcol0 + tq_addr + (uint32_t)(mt * 2 + buf) * 16 * GC;
+#pragma unroll
+                    for (int gr = 0; gr < GC; gr++) {
+                        uint32_t r[16];
+                        sm100::tmem_ld16(dcol + gr * 16, r);
+                        sm100::tmem_ld_wait();
+                        if (mp.x >= 0) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const float4 s1 = *reinterpret_cast<const float4 *>(wc + off.s1 + gr * 16 + 4 * j);
+                                const float4 b1 = *reinterpret_cast<const float4 *>(wc + off.b1 + gr * 16 + 4 * j);
+                                float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                                v = inside ? bn_act4(v, s1, b1, a.slope1) : blk_zero4();
+                                sm100::sts128(sE_addr + mp.x + (gr * 16 + 4 * j) * 4, v);
+                            }
+                        }
+                    }
+                }
+                sm100::tc_fence_before_sync();
+                expand_pending = c + 1 < a.NC;
+            } else
+#endif
             /* ---------------- stage A: expand GEMM; work item = MT m-tiles x all GC groups of the chunk ----------------
                the A fragments (x, split hi/lo on the fly) are loaded once per k-step and reused by every group */
             for (int item = warp; item < nitems; item += BLK_WARPS) {
@@ -293,6 +414,17 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     }
             }
             __syncthreads();
+#ifdef FFB_BLK_TC
+            if constexpr (TC) {
+                /* the next chunk's expand GEMM runs on the tensor core while the warps do stage B of this one: D[.][buf ^ 1] was
+                   drained before the previous barrier pair, its weights were requested at the top of this chunk */
+                if (tid == 0 && expand_pending && sm100::mbar_try_wait(full_w + (wb ^ 1), ((cs + 1) >> 1) & 1u)) {
+                    sm100::tc_fence_after_sync();
+                    issue_expand((uint32_t)(wb ^ 1), (cs + 1) & 1u);
+                    expand_pending = false;
+                }
+            }
+#endif
 
             /* ---------------- stage B: depthwise 3x3 in registers -> projection GEMM ---------------- */
 #pragma unroll
@@ -361,6 +493,15 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     }
                 }
             }
+#ifdef FFB_BLK_TC
+            if constexpr (TC) {
+                if (tid == 0 && expand_pending) {         /* the next chunk's weights had not landed when stage B started */
+                    sm100::mbar_wait(full_w + (wb ^ 1), ((cs + 1) >> 1) & 1u);
+                    sm100::tc_fence_after_sync();
+                    issue_expand((uint32_t)(wb ^ 1), (cs + 1) & 1u);
+                }
+            }
+#endif
         }
 
         /* ---------------- block epilogue: BN + act [+ shortcut from the resident x tile] -> y ---------------- */
@@ -391,15 +532,22 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
             }
         }
     }
+#ifdef FFB_BLK_TC
+    if constexpr (TC) {
+        sm100::tc_fence_before_sync();
+        __syncthreads();
+        if (warp == 0) { sm100::tc_fence_after_sync(); sm100::tmem_dealloc(tmem_base, a.tmem_cols); }
+    }
+#endif
 }
 
 /* Build the fragment-ordered weight chunks of one block from the three convs' packed reference rows
  * (ffcnn.c:218-234: [weights..., pad, scale', bias', mean, var] per filter). */
 __global__ void k_prep_block(const float *__restrict__ p1, int row1, int cin, const float *__restrict__ pd, int rowd,
                              const float *__restrict__ p3, int row3, int cexp, int cout, int KS1, int NT3, int GC, int NC,
-                             float *__restrict__ chunks, float *__restrict__ sb3)
+                             float *__restrict__ chunks, float *__restrict__ sb3, int tc)
 {
-    const BlkChunk off(GC, KS1, NT3);
+    const BlkChunk off(GC, KS1, NT3, tc != 0);
     const long total = (long)NC * off.total;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total + 16 * NT3; i += (long)gridDim.x * blockDim.x) {
         if (i >= total) {                                  /* projection scale / bias */
@@ -409,7 +557,16 @@ __global__ void k_prep_block(const float *__restrict__ p1, int row1, int cin, co
         }
         const int c = (int)(i / off.total), r = (int)(i - (long)c * off.total);
         float v = 0.f; bool is_w = false; int lohalf = 0;
-        if (r < off.s1) {
+        if (r < off.s1 && tc) {
+            /* UMMA B operand: [hi | lo] x KC sub-tiles of [16*GC rows (channels) x 32 floats (cin)], SWIZZLE_128B:
+               element (n, k) of a sub-tile sits at float n*32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3) */
+            const int KC = (KS1 + 3) / 4, subf = 16 * GC * 32;
+            const int sub = r / subf, rem = r - sub * subf, n = rem >> 5, pos = rem & 31;
+            const int k = ((((pos >> 2) ^ (n & 7)) << 2) | (pos & 3)), part = sub / KC, kc = sub - part * KC;
+            const int ch = c * GC * 16 + n, ci = kc * 32 + k;
+            if (ch < cexp && ci < cin) v = p1[(long)ch * row1 + ci];
+            is_w = true; lohalf = part;
+        } else if (r < off.s1) {
             const int lane4 = r % 128; int rest = r / 128;
             const int ks = rest % KS1; rest /= KS1;
             const int ntl = rest % 2, grp = rest / 2, lane = lane4 >> 2, j = lane4 & 1, g = lane >> 2, t = lane & 3;
