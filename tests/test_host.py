@@ -377,3 +377,13 @@ def test_host_decode_and_nms_on_random_graphs(tmp_path):
         total += n
         net.close()
     assert heads >= 10 and total > 5000
+
+
+def test_public_headers_compile_standalone_as_c_and_cpp():
+    """include/*.h is the drop-in boundary: each header must compile on its own, as strict C99 (the reference is C) and as C++."""
+    inc = os.path.join(REPO, "include")
+    for h in sorted(os.listdir(inc)):
+        for cc, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "c++")):
+            r = subprocess.run([cc, std, "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", lang, "-"],
+                               input='#include "%s"\n' % h, capture_output=True, text=True)
+            assert r.returncode == 0, (h, cc, r.stderr[:400])
