@@ -387,3 +387,29 @@ def test_public_headers_compile_standalone_as_c_and_cpp():
             r = subprocess.run([cc, std, "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", lang, "-"],
                                input='#include "%s"\n' % h, capture_output=True, text=True)
             assert r.returncode == 0, (h, cc, r.stderr[:400])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ffcnn.c"), reason="reference sources not present (GPU box)")
+def test_reference_driver_source_links_against_the_library(tmp_path):
+    """INTEGRATION.md, way A: the reference's own test driver -- main() and its static tick helper, cut out of ffcnn.c where it
+    lies, not copied into the repo -- compiles against include/ffcnn.h + include/bmpfile.h and links against
+    libffcnn_b200.so with no source change; its bmp error path runs (net_load itself needs a GPU)."""
+    fb.build()
+    src = open("/root/reference/ffcnn.c", errors="replace").read().splitlines()
+    keep, on = [], False
+    for line in src:
+        if line.startswith("#ifdef WIN32") or line.startswith("#if _TEST_"):
+            on = True
+        if on:
+            keep.append(line)
+        if on and line.startswith("#endif"):
+            on = False
+    main_c = tmp_path / "main_only.c"
+    main_c.write_text("\n".join(keep) + "\n")
+    exe = str(tmp_path / "ffcnn_ref_driver")
+    r = subprocess.run(["gcc", "-O2", "-D_TEST_=1", "-I", os.path.join(REPO, "include"), "-include", "stdio.h", "-include", "stdlib.h",
+                        "-include", "stdint.h", "-include", "ffcnn.h", str(main_c), "-L", os.path.join(REPO, "ffcnn_b200"), "-lffcnn_b200",
+                        "-Wl,-rpath," + os.path.join(REPO, "ffcnn_b200"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    r = subprocess.run([exe, "1", "/nonexistent.bmp"], capture_output=True, text=True, cwd=tmp_path)
+    assert "failed to load bmp file: /nonexistent.bmp !" in r.stdout
