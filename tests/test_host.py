@@ -413,3 +413,26 @@ def test_reference_driver_source_links_against_the_library(tmp_path):
     assert r.returncode == 0, r.stderr[-800:]
     r = subprocess.run([exe, "1", "/nonexistent.bmp"], capture_output=True, text=True, cwd=tmp_path)
     assert "failed to load bmp file: /nonexistent.bmp !" in r.stdout
+
+
+@pytest.mark.skipif(not ref.available("v6_O2"), reason="oracle/_ref not built")
+def test_net_dump_on_random_graphs_prints_what_the_reference_prints(tmp_path):
+    """net_dump + net_profile (ffcnn.c:522-550) on 8 random graphs (pool / upsample / route / shortcut / yolo rows, unknown
+    activations): byte-identical stdout to the compiled reference."""
+    import cfg_fuzz
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import ffcnn_b200 as fb; from oracle import ref; import ctypes\n"
+            "which, cfg, wts = sys.argv[1:4]\n"
+            "if which == 'mine':\n    n = fb.Net(cfg, wts, 0, 0, device=None); fb.lib().net_dump(n.p); fb.lib().net_profile(n.p)\n"
+            "else:\n    r = ref.RefNet(cfg, wts, 0, 0, 'v6_O2'); r.L.net_dump.argtypes = [ctypes.c_void_p]; r.L.net_dump(r.net)\n"
+            "    r.L.net_profile.argtypes = [ctypes.c_void_p]; r.L.net_profile(r.net)\n") % REPO
+    rng = np.random.default_rng(91)
+    for case in range(8):
+        text, convs, _ = cfg_fuzz.gen(rng)
+        cfg, wts = str(tmp_path / ("g%d.cfg" % case)), str(tmp_path / ("g%d.weights" % case))
+        with open(cfg, "w", newline="") as f:
+            f.write(text)
+        with open(wts, "wb") as f:
+            f.write(cfg_fuzz.weights(rng, convs))
+        outs = [subprocess.run([sys.executable, "-c", code, w, cfg, wts], capture_output=True, text=True, check=True).stdout for w in ("mine", "ref")]
+        assert outs[0] == outs[1] and outs[0].count("\n") > 10, case
