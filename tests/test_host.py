@@ -436,3 +436,52 @@ def test_net_dump_on_random_graphs_prints_what_the_reference_prints(tmp_path):
             f.write(cfg_fuzz.weights(rng, convs))
         outs = [subprocess.run([sys.executable, "-c", code, w, cfg, wts], capture_output=True, text=True, check=True).stdout for w in ("mine", "ref")]
         assert outs[0] == outs[1] and outs[0].count("\n") > 10, case
+
+
+@pytest.mark.skipif(not ref.available("v0"), reason="oracle/_ref not built")
+def test_bmp_helpers_against_live_reference(tmp_path):
+    """bmp_load / bmp_rectangle (corners partly or wholly outside the picture, as detection boxes can be) / bmp_getpixel /
+    bmp_save on 40 random 24-bit pictures from 1x1 up: same BMP struct, same pixel bytes, same saved file as the reference's
+    bmpfile.c (bmpfile.c:42-156).  Out-of-picture bmp_getpixel is left out: the reference reads outside its buffer there."""
+    class BMP(C.Structure):
+        _fields_ = [("width", C.c_int), ("height", C.c_int), ("stride", C.c_int), ("cdepth", C.c_int), ("pdata", C.c_void_p)]
+
+    def bind(L):
+        for f in (L.bmp_load, L.bmp_save):
+            f.argtypes, f.restype = [C.POINTER(BMP), C.c_char_p], C.c_int
+        L.bmp_free.argtypes = [C.POINTER(BMP)]
+        L.bmp_rectangle.argtypes = [C.POINTER(BMP)] + [C.c_int] * 7
+        L.bmp_getpixel.argtypes = [C.POINTER(BMP), C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+        return L
+    M, R = bind(fb.lib()), bind(ref.lib("v0"))
+    rng = np.random.default_rng(3)
+    u32 = lambda v: np.frombuffer(np.uint32(v).tobytes(), np.uint8)
+    for case in range(40):
+        w, h = int(rng.integers(1, 70)), int(rng.integers(1, 50))
+        pitch = (3 * w + 3) & ~3
+        hdr = np.zeros(54, np.uint8)
+        hdr[0:2] = (66, 77); hdr[2:6] = u32(54 + pitch * h); hdr[10:14] = u32(54); hdr[14:18] = u32(40)
+        hdr[18:22] = u32(w); hdr[22:26] = u32(h); hdr[26:28] = (1, 0); hdr[28:30] = (24, 0); hdr[34:38] = u32(pitch * h)
+        path = str(tmp_path / "in.bmp")
+        with open(path, "wb") as f:
+            f.write(hdr.tobytes() + rng.integers(0, 256, (h, pitch), dtype=np.uint8).tobytes())
+        a, b = BMP(), BMP()
+        assert M.bmp_load(C.byref(a), path.encode()) == R.bmp_load(C.byref(b), path.encode()) == 0
+        assert (a.width, a.height, a.stride, a.cdepth) == (b.width, b.height, b.stride, b.cdepth) == (w, h, pitch, 24)
+        pix = lambda q: C.string_at(q.pdata, q.stride * q.height)
+        assert pix(a) == pix(b)
+        for _ in range(6):
+            x1, x2 = sorted(int(v) for v in rng.integers(-10, w + 10, 2))
+            y1, y2 = sorted(int(v) for v in rng.integers(-10, h + 10, 2))
+            col = [int(v) for v in rng.integers(0, 256, 3)]
+            M.bmp_rectangle(C.byref(a), x1, y1, x2, y2, *col); R.bmp_rectangle(C.byref(b), x1, y1, x2, y2, *col)
+            assert pix(a) == pix(b), (w, h, x1, y1, x2, y2)
+        for _ in range(8):
+            x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+            va, vb = [C.c_int(-7) for _ in range(3)], [C.c_int(-7) for _ in range(3)]
+            M.bmp_getpixel(C.byref(a), x, y, *[C.byref(v) for v in va]); R.bmp_getpixel(C.byref(b), x, y, *[C.byref(v) for v in vb])
+            assert [v.value for v in va] == [v.value for v in vb]
+        pa, pb = str(tmp_path / "a.bmp"), str(tmp_path / "b.bmp")
+        assert M.bmp_save(C.byref(a), pa.encode()) == R.bmp_save(C.byref(b), pb.encode()) == 0
+        assert open(pa, "rb").read() == open(pb, "rb").read()
+        M.bmp_free(C.byref(a)); R.bmp_free(C.byref(b))
