@@ -13,7 +13,7 @@
 #include "pw_tc.h"
 #include "block_mma.cuh"
 
-extern "C" void ffb_set_error(const char *fmt, ...);
+#include "ffb_internal.h"
 
 using namespace ffb;
 
@@ -31,10 +31,10 @@ struct BlkPlan {
 };
 
 typedef void (*BlkKernel)(const CUtensorMap, const BlkArgs);
-struct BlkInst { int KS1, NT3, S, MTW, GC, MINB; BlkKernel fn; size_t configured; int tc; };
+struct BlkInst { int KS1, NT3, S, MTW, GC, MINB; BlkKernel fn; ffb_smem_cfg configured; int tc; };
 
-#define INST(K, N, S, M, G, B) { K, N, S, M, G, B, k_block_mma<K, N, S, M, G, B>, 0, 0 }
-#define INST_TC(K, N, S, M, G) { K, N, S, M, G, 2, k_block_mma<K, N, S, M, G, 2, true>, 0, 1 }
+#define INST(K, N, S, M, G, B) { K, N, S, M, G, B, k_block_mma<K, N, S, M, G, B>, {}, 0 }
+#define INST_TC(K, N, S, M, G) { K, N, S, M, G, 2, k_block_mma<K, N, S, M, G, 2, true>, {}, 1 }
 #define INST3(K, N, S, G) INST(K, N, S, 1, G, 2), INST(K, N, S, 2, G, 2), INST(K, N, S, 4, G, 2)
 #define INST2(K, N, S, G) INST(K, N, S, 1, G, 2), INST(K, N, S, 2, G, 2)
 static BlkInst g_inst[] = {
@@ -171,9 +171,7 @@ BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
         p->tc = 0;                              /* the tcgen05 instances cover fewer tiles */
         if (!plan_tile(p)) { delete p; return nullptr; }
     }
-    int dev = 0; cudaDeviceProp prop;
-    cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
-    p->num_sms = prop.multiProcessorCount;
+    p->num_sms = ffb_num_sms();
     snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s tile %dx%d%s gc%d mtw%d smem %zuKB occ%d%s", cin, cexp, cout, stride, res ? "+res" : "",
              p->TH, p->TW, p->frame ? " (frame)" : "", p->GC, p->MTW, p->smem >> 10, p->occ, p->tc ? " tcgen05-expand" : "");
     return p;
@@ -204,10 +202,7 @@ int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
 {
     BlkInst *inst = find_inst(p->KS1, p->NT3, p->S, p->MTW, p->GC, p->tc);
     if (!inst) { ffb_set_error("block_mma: no kernel instance"); return -1; }
-    if (p->smem > inst->configured) {
-        if (cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess) { ffb_set_error("block_mma: cannot set smem %zu", p->smem); return -1; }
-        inst->configured = p->smem;
-    }
+    if (ffb_ensure_smem((const void *)inst->fn, p->smem, &inst->configured) != 0) return -1;
     BlkArgs a;
     a.x = x; a.y = y; a.wchunks = p->d_chunks; a.sb3 = p->d_sb3;
     a.N = n; a.H = p->H; a.W = p->W; a.OH = p->OH; a.OW = p->OW; a.ldx = ldx; a.ldy = ldy; a.cout = p->cout;

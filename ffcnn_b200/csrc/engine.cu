@@ -32,6 +32,7 @@
 #include "pw_tc.h"
 #include "block_mma.h"
 #include "block_reg.h"
+#include "conv_tc.h"
 
 using namespace ffb;
 
@@ -44,7 +45,32 @@ using namespace ffb;
         }                                                                                          \
     } while (0)
 
-static int g_num_sms = 148;
+/* Per-device state.  cudaFuncSetAttribute and the SM count are properties of a (function, device) pair, and several nets
+ * may live on different devices of one process (ffb_multi_*), so nothing here is a process-wide scalar. */
+int ffb_num_sms(void)
+{
+    static int sms[FFB_MAX_DEVICES];                    /* 0 = not queried yet; racing writers store the same value */
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FFB_MAX_DEVICES) return 148;
+    if (!sms[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        sms[dev] = n;
+    }
+    return sms[dev];
+}
+int ffb_ensure_smem(const void *func, size_t smem, ffb_smem_cfg *cfg)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FFB_MAX_DEVICES) { ffb_set_error("cudaGetDevice failed"); return -1; }
+    if (smem <= cfg->bytes[dev]) return 0;
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        ffb_set_error("cannot raise dynamic shared memory to %zu bytes: %s", smem, cudaGetErrorString(cudaGetLastError())); return -1;
+    }
+    cfg->bytes[dev] = smem;
+    return 0;
+}
+#define g_num_sms (ffb_num_sms())
 namespace sm100 { int g_ffb_pdl = 0; }     /* programmatic dependent launch between the kernels of a forward pass: FFCNN_PDL=1 enables. Measured (r1g): back-to-back launches of one layer gain 6 %, the captured graph gains nothing (3.44 vs 3.40 ms) -- the big CTAs (>= 120 KB smem) cannot co-reside with their predecessor -- so it stays off by default. */
 using sm100::launch_pdl;
 
@@ -57,7 +83,7 @@ static inline int grid_for(long total, int block, int waves = 8)
 
 /* =================================================================================== conv operator */
 
-enum ConvKind { CK_GENERIC = 0, CK_PW_FFMA, CK_PW_TC, CK_DW_S1_3, CK_DW_S1_5, CK_DW3_S2, CK_STEM };
+enum ConvKind { CK_GENERIC = 0, CK_PW_FFMA, CK_PW_TC, CK_DW_S1_3, CK_DW_S1_5, CK_DW3_S2, CK_STEM, CK_IGEMM_TC };
 
 struct ffb_conv {
     int ic, groups, pad, stride, fs, fn, act, row, taps;
@@ -70,6 +96,7 @@ struct ffb_conv {
     /* pointwise FFMA tiling */
     int TM, TN, NT, TY; size_t smem;
     PwTcPlan *tc;               /* tcgen05 plan (pw_tc.cu), NULL if not used */
+    IgPlan *ig;                 /* implicit-GEMM tcgen05 plan (conv_tc.cu): dense k x k convs and pointwise layers too large for pw_tc */
     const float *h_packed;      /* host copy of the packed rows, only dereferenced during conv_prepare */
     StemW stemw;                /* stem weights as a kernel-parameter block (constant-bank FFMA operands) */
     char name[48];
@@ -167,12 +194,9 @@ static bool dw_plan(int C, int OH, int OW, int FS, int stride, int max_rc, DwPla
 
 typedef void (*DwKernel)(const CUtensorMap, const DwArgs);
 
-static int dw_launch(DwKernel kernel, size_t *configured, const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t st)
+static int dw_launch(DwKernel kernel, ffb_smem_cfg *configured, const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t st)
 {
-    if (pl.smem > *configured) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) { ffb_set_error("dw_tma: cannot set smem %zu", pl.smem); return -1; }
-        *configured = pl.smem;
-    }
+    if (ffb_ensure_smem((const void *)kernel, pl.smem, configured) != 0) return -1;
     CUtensorMap tm;
     const unsigned long long dims[4] = { (unsigned long long)a.C, (unsigned long long)a.W, (unsigned long long)a.H, (unsigned long long)a.N };
     const unsigned long long strides[3] = { (unsigned long long)a.C * 4, (unsigned long long)a.W * a.C * 4, (unsigned long long)a.H * a.W * a.C * 4 };
@@ -189,12 +213,8 @@ static int dw_launch(DwKernel kernel, size_t *configured, const float *in, DwArg
 template <int TM, int TN, bool RES>
 static cudaError_t pw_launch2(const PwArgs &a, int grid, size_t smem, cudaStream_t st)
 {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_pw_ffma<TM, TN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static ffb_smem_cfg configured;
+    if (ffb_ensure_smem((const void *)k_pw_ffma<TM, TN, RES>, smem, &configured) != 0) return cudaErrorInvalidValue;
     return launch_pdl(k_pw_ffma<TM, TN, RES>, dim3(grid), dim3(256), smem, st, a);
 }
 
@@ -211,14 +231,22 @@ static int conv_prepare(ffb_conv *op, cudaStream_t st)
     op->row  = FFB_ALIGN(op->taps, 4) + 4;
     op->fn_pad = FFB_ALIGN(op->fn, 4);
     op->tc = NULL;
+    if (op->ig) { ig_plan_destroy(op->ig); op->ig = NULL; }
     if (op->kind == CK_PW_FFMA) {
         pw_plan(op);
         if (op->pw_mode != 1) {
             op->tc = pw_tc_plan_create(op->ic, op->fn, op->act, op->pw_mode);
             if (op->tc) op->kind = CK_PW_TC;
         }
+        /* the FFMA kernel keeps the whole [K][N] weight matrix in shared memory and maps N over <= 256 threads: layers too
+           large for that (and for a resident-weight tcgen05 plan) take the implicit-GEMM tcgen05 kernel or the generic one */
+        if (op->kind == CK_PW_FFMA && (op->smem > 227 * 1024 || op->NT > 256 || op->TY < 1)) op->kind = CK_GENERIC;
     }
-    const char *names[] = { "conv_generic", "pw_ffma", "pw_tcgen05", "dw3x3_s1", "dw5x5_s1", "dw3x3_s2", "stem3x3_s2" };
+    if (op->kind == CK_GENERIC && op->pw_mode != 1) {
+        op->ig = ig_plan_create(op->ic, op->fn, op->fs, op->stride, op->pad, op->groups, op->act);
+        if (op->ig) op->kind = CK_IGEMM_TC;
+    }
+    const char *names[] = { "conv_generic", "pw_ffma", "pw_tcgen05", "dw3x3_s1", "dw5x5_s1", "dw3x3_s2", "stem3x3_s2", "igemm_tcgen05_3xtf32" };
     snprintf(op->name, sizeof op->name, "%s", names[op->kind]);
     if (op->kind == CK_PW_TC) snprintf(op->name, sizeof op->name, "pw_tcgen05_%s", pw_tc_mode_name(op->tc));
     if (op->kind == CK_STEM) {
@@ -230,6 +258,7 @@ static int conv_prepare(ffb_conv *op, cudaStream_t st)
         }
     }
     if (op->kind == CK_GENERIC) return 0;
+    if (op->kind == CK_IGEMM_TC) return ig_prepare(op->ig, op->d_packed, op->row, st);
     const size_t nfl = (size_t)op->taps * op->fn_pad + 2 * op->fn_pad;
     if (!op->d_prep) CK(cudaMalloc(&op->d_prep, nfl * sizeof(float)));
     float *wt = op->d_prep, *sc = wt + (size_t)op->taps * op->fn_pad, *bi = sc + op->fn_pad;
@@ -243,6 +272,7 @@ static void conv_release(ffb_conv *op)
 {
     if (!op) return;
     if (op->tc) pw_tc_plan_destroy(op->tc);
+    if (op->ig) ig_plan_destroy(op->ig);
     cudaFree(op->d_prep);
     cudaFree(op->d_owned_packed);
     delete op;
@@ -260,8 +290,11 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
     ConvKind kind = op->kind;
     if ((kind == CK_DW_S1_3 || kind == CK_DW_S1_5 || kind == CK_DW3_S2) && (ldi != op->ic || ldo != op->fn || coff != 0)) kind = CK_GENERIC;
     if (kind == CK_STEM && (ldi != 4 || ldo != 8 || coff != 0)) kind = CK_GENERIC;
+    if (kind == CK_IGEMM_TC && !ig_supports(op->ig, ldi, ldo, coff, ih, iw)) kind = CK_GENERIC;
     if (res && kind != CK_PW_TC && kind != CK_PW_FFMA) { ffb_set_error("fused shortcut needs a pointwise conv"); return -1; }
     switch (kind) {
+    case CK_IGEMM_TC:
+        return ig_run(op->ig, in, ldi, out, ldo, coff, n, ih, iw, st);
     case CK_PW_TC:
         return pw_tc_run(op->tc, in, ldi, out, ldo, coff, (long)n * ih * iw, st, res, ldr, act2);
     case CK_PW_FFMA: {
@@ -287,7 +320,7 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
         return 0; }
     case CK_DW_S1_3: case CK_DW_S1_5: case CK_DW3_S2:
         if (op->dw_mode == 0) {
-            DwPlan pl; static size_t cfg_s1 = 0, cfg_s2 = 0, cfg_5 = 0;
+            DwPlan pl; static ffb_smem_cfg cfg_s1, cfg_s2, cfg_5;
             DwArgs a; a.out = out; a.wt = wt; a.scale = sc; a.bias = bi; a.N = n; a.H = ih; a.W = iw; a.C = op->ic; a.OH = oh; a.OW = ow;
             a.act = op->act; a.skip_row0_at = skip;
             if (kind == CK_DW_S1_3 && dw_plan(op->ic, oh, ow, 3, 1, 1 << 20, &pl)) return dw_launch(k_dw3s1_tma, &cfg_s1, in, a, pl, st);
@@ -358,7 +391,7 @@ struct ffb_engine {
     std::vector<Spp> spps;
     std::vector<int> spp_at, up_into;       /* per layer: index into spps (route layers) / the route an upsample writes into, else -1 */
     std::vector<char> in_spp;               /* pool layers computed by the SPP kernel */
-    int fuse_tail = 1;
+    int fuse_tail = 1, cand_cap = 0;
     Tens input;
     std::vector<Buf> bufs;
     float *d_arena = nullptr; size_t arena_floats = 0;
@@ -373,7 +406,7 @@ struct ffb_engine {
     float *h_stage = nullptr; size_t h_stage_cap = 0;
     /* detection */
     /* two candidate sets: while the host decodes batch i from one, the GPU may already be filtering batch i+1 into the other */
-    struct DetSet { Candidate *d_cand = nullptr, *h_cand = nullptr; int *d_count = nullptr, *h_count = nullptr; int cap = 0, n = 0, s1 = 1, s2 = 1;
+    struct DetSet { Candidate *d_cand = nullptr, *h_cand = nullptr; int *d_count = nullptr, *h_count = nullptr; int cap = 0, n = 0, s1 = 1, s2 = 1; long want = 0;
                     cudaEvent_t done = nullptr; } det[2];
     int det_cur = 0;
     cudaStream_t d2h_stream = nullptr;      /* candidate read-back must not queue behind the next batch's forward pass */
@@ -531,6 +564,9 @@ static int engine_plan(ffb_engine *e)
             if (p < 0 || producer_of(net, d) == p || (use_blocks && (e->in_block[p] || e->blk_at[p] >= 0))) continue;
             const ffb_conv *op = net->layer_list[p].type == LAYER_TYPE_CONV ? e->convs[p] : nullptr;
             if (!op || (op->kind != CK_PW_FFMA && op->kind != CK_PW_TC) || readers[p] != 1 || net->layer_list[p + 1].c % 4) continue;
+            /* the skip tensor must have the conv output's shape (the unfused shortcut kernel checks the same and fails) */
+            const LAYER *po = net->layer_list + p + 1, *so = net->layer_list + d + 1;
+            if (d < 0 || d >= L || so->w != po->w || so->h != po->h || so->c != po->c) continue;
             e->fuse_sc[p] = j; e->fused_away[j] = 1;
         }
     }
@@ -681,6 +717,8 @@ static int engine_prepare_weights(ffb_engine *e)
     return 0;
 }
 
+static int engine_attach_body(ffb_engine *e, NET *net);
+
 int ffb_net_attach(NET *net, int device, int max_batch)
 {
     if (!net) { ffb_set_error("NULL net"); return -1; }
@@ -699,11 +737,19 @@ int ffb_net_attach(NET *net, int device, int max_batch)
     CK(cudaSetDevice(device));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { ffb_set_error("device %d is sm_%d%d; this build only carries sm_100a code", device, prop.major, prop.minor); return -1; }
-    g_num_sms = prop.multiProcessorCount;
     e = new ffb_engine(); e->net = fn; e->device = device; e->max_batch = max_batch;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; ffb_set_error("cudaStreamCreate failed"); return -1; }
     e->stream = e->own_stream;
     fn->engine = e;
+    if (engine_attach_body(e, net) != 0) {                   /* never leave a half-initialised engine behind */
+        ffb_engine_destroy(e); fn->engine = nullptr;
+        return -1;
+    }
+    return 0;
+}
+
+static int engine_attach_body(ffb_engine *e, NET *net)
+{
     e->convs.assign(net->layer_num, nullptr);
     const char *env;
     if ((env = getenv("FFCNN_DW5_EXACT"))) e->dw5_exact = atoi(env);
@@ -774,6 +820,7 @@ int ffb_set_option(NET *net, const char *name, int value)
     else if (!strcmp(name, "keep_all"))  { if (e->keep_all != value) e->plan_dirty = true; e->keep_all = value; }
     else if (!strcmp(name, "fuse_block")) { reweight = e->fuse_block != value; e->fuse_block = value; }
     else if (!strcmp(name, "fuse_tail")) { if (e->fuse_tail != value) e->plan_dirty = true; e->fuse_tail = value; }
+    else if (!strcmp(name, "cand_cap")) { e->cand_cap = value; for (ffb_engine::DetSet &d : e->det) d.want = 0; }   /* test hook: initial candidate capacity */
     else { ffb_set_error("unknown option '%s'", name); return -1; }
     if (reweight) {
         CK(cudaSetDevice(e->device));
@@ -921,13 +968,18 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         break;
     case LAYER_TYPE_MAXPOOL: case LAYER_TYPE_AVGPOOL:
         if (e->keep_all != 1 && (int)e->in_spp.size() > i && e->in_spp[i]) break;      /* computed by the SPP kernel in the route's slot */
-        if (in.c % 4) { ffb_set_error("pool layer %d: channels %d not a multiple of 4", i, in.c); return -1; }
+        if (in.c % 4)
+            CK(launch_pdl(k_pool_scalar, dim3(grid_for((long)n * o.h * o.w * o.c, 256)), dim3(256), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.h, o.w, o.ld, 0,
+                          il->fs, il->stride, (int)(il->type == LAYER_TYPE_MAXPOOL)));
+        else
         CK(launch_pdl(k_pool, dim3(grid_for((long)n * o.h * o.w * (o.c / 4), 128)), dim3(128), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.h, o.w, o.ld, 0,
                       il->fs, il->stride, (int)(il->type == LAYER_TYPE_MAXPOOL)));
         (*launches)++;
         break;
     case LAYER_TYPE_UPSAMPLE:
-        if (in.c % 4) { ffb_set_error("upsample layer %d: channels %d not a multiple of 4", i, in.c); return -1; }
+        if (in.c % 4)
+            CK(launch_pdl(k_upsample_scalar, dim3(grid_for((long)n * o.h * o.w * o.c, 256, 64)), dim3(256), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride));
+        else
         CK(launch_pdl(k_upsample, dim3(grid_for((long)n * o.h * o.w * (o.c / 4), 128, 64)), dim3(128), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride));
         (*launches)++;
         break;
@@ -943,9 +995,9 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         if (il->depend_num > 1 && e->keep_all != 1 && (int)e->spp_at.size() > i && e->spp_at[i] >= 0) {
             const ffb_engine::Spp &sp = e->spps[e->spp_at[i]]; const Tens &x = e->outs[sp.x];
             const size_t spp_bytes = (size_t)4 * x.h * x.w * x.c * sizeof(float);
-            static size_t spp_configured = 0;
+            static ffb_smem_cfg spp_configured;
             if (spp_bytes <= 200 * 1024) {                     /* frame fits in shared memory: separable version, one CTA per frame */
-                if (spp_bytes > spp_configured) { CK(cudaFuncSetAttribute(k_spp_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spp_bytes)); spp_configured = spp_bytes; }
+                if (ffb_ensure_smem((const void *)k_spp_smem, spp_bytes, &spp_configured) != 0) return -1;
                 CK(launch_pdl(k_spp_smem, dim3(n), dim3(256), spp_bytes, st, (const float *)x.p, o.p, x.h, x.w, x.c, x.ld, o.ld,
                               sp.r[0], sp.r[1], sp.r[2], sp.off[0], sp.off[1], sp.off[2], sp.offx));
             } else
@@ -1035,9 +1087,17 @@ int ffb_detect_enqueue(NET *net)
     const int n = e->batch;
     if (n < 1) { ffb_set_error("ffb_detect: no batch"); return -1; }
     int key = 0; std::vector<Head> heads = yolo_heads(e, &key);
-    const int cap = std::max(4096, std::min(key, 2048) * n);
+    /* Candidate capacity: one slot per (frame, cell, anchor) -- the filter can then never overflow -- unless that exceeds
+       64 MB (huge inputs x big batches): then 2048 per frame, and an overflow is reported by ffb_detect_finish, which also
+       records the size that would have been needed so the next enqueue allocates it (ffb_detect retries by itself).
+       The reference keeps at most bbox_max boxes per frame in scan order (ffcnn.c:453); the host decode applies that cap. */
     ffb_engine::DetSet &d = e->det[e->det_cur];
-    if (cap > d.cap) {
+    const long full = (long)key * n;
+    long cap_l = full * (long)sizeof(Candidate) <= (64L << 20) ? full : std::max<long>(4096, 2048L * n);
+    cap_l = std::min<long>(std::max<long>(std::max<long>(cap_l, d.want), 4096), full > 4096 ? full : 4096);
+    if (e->cand_cap > 0 && !d.want) cap_l = e->cand_cap;
+    const int cap = (int)cap_l;
+    if (cap != d.cap && (cap > d.cap || e->cand_cap > 0)) {
         CK(cudaStreamSynchronize(e->stream));
         cudaFree(d.d_cand); cudaFreeHost(d.h_cand); d.d_cand = nullptr; d.h_cand = nullptr;
         CK(cudaMalloc(&d.d_cand, (size_t)cap * sizeof(Candidate)));
@@ -1068,7 +1128,15 @@ int ffb_detect_finish(NET *net)
     const int n = d.n;
     std::vector<Head> heads = yolo_heads(e, nullptr);
     CK(cudaEventSynchronize(d.done));                      /* this batch only: a look-ahead batch may already be queued behind it */
-    int cnt = std::min(*d.h_count, d.cap);
+    if (*d.h_count > d.cap) {
+        /* the filter found more candidates than the buffer holds: which ones were dropped depends on atomic order, so the
+           result would not be the reference's -- fail loudly instead of returning a truncated box set */
+        d.want = (long)*d.h_count + (*d.h_count >> 2);
+        e->boxes.assign(n, std::vector<BBOX>()); e->raw.assign(n, std::vector<BBOX>());
+        ffb_set_error("yolo candidate overflow: %d candidates, capacity %d (the next ffb_detect_enqueue allocates %ld)", *d.h_count, d.cap, d.want);
+        return FFB_E_OVERFLOW;
+    }
+    int cnt = *d.h_count;
     e->d2h_bytes = sizeof(int) + (size_t)cnt * sizeof(Candidate);
     if (cnt > 0) {
         CK(cudaMemcpyAsync(d.h_cand, d.d_cand, (size_t)cnt * sizeof(Candidate), cudaMemcpyDeviceToHost, e->d2h_stream));
@@ -1100,7 +1168,12 @@ int ffb_detect_finish(NET *net)
 int ffb_detect(NET *net)
 {
     if (ffb_detect_enqueue(net) < 0) return -1;
-    return ffb_detect_finish(net);
+    int rc = ffb_detect_finish(net);
+    if (rc == FFB_E_OVERFLOW) {                                /* heads are still resident: filter again into the grown buffer */
+        if (ffb_detect_enqueue(net) < 0) return -1;
+        rc = ffb_detect_finish(net);
+    }
+    return rc;
 }
 
 long ffb_last_d2h_bytes(NET *net) { ffb_engine *e = engine_of(net); return e ? (long)e->d2h_bytes : -1; }
@@ -1212,8 +1285,9 @@ long ffb_layer_output(NET *net, int layer, int frame, float *chw, long capacity)
     ffb_engine *e = engine_of(net);
     if (!e) return -1;
     if (layer < -1 || layer >= net->layer_num || frame < 0 || frame >= e->batch) { ffb_set_error("ffb_layer_output: bad layer/frame"); return -1; }
-    if (!e->keep_all) { ffb_set_error("ffb_layer_output needs option keep_all=1 before ffb_forward"); return -1; }
     const Tens &t = layer < 0 ? e->input : e->outs[layer];
+    /* under the default plan buffers are recycled: only tensors that stay alive to the end (the yolo heads) are readable */
+    if (!e->keep_all && !(t.buf >= 0 && e->bufs[t.buf].last >= (1 << 30))) { ffb_set_error("ffb_layer_output: layer %d is not kept by the default plan (set option keep_all=1 or 2 before ffb_forward)", layer); return -1; }
     if (!t.p) return 0;
     const long count = (long)t.c * t.h * t.w;
     if (!chw) return count;
@@ -1317,9 +1391,6 @@ int ffb_layer_times(NET *net, float *ms, int nlayers, int reps, int flush_l2)
 static int ensure_device()
 {
     if (ffb_device_count() <= 0) { ffb_set_error("no CUDA device available: libffcnn_b200 has no CPU fallback"); return -1; }
-    cudaDeviceProp prop; int dev = 0;
-    CK(cudaGetDevice(&dev)); CK(cudaGetDeviceProperties(&prop, dev));
-    g_num_sms = prop.multiProcessorCount;
     return 0;
 }
 

@@ -50,7 +50,13 @@ int  ffb_decode_head_chw(const LAYER *yolo, const float *head_chw, int gw, int g
 int  ffb_nms(BBOX *boxes, int n, float threshold, int min_mode, int s1, int s2);
 void ffb_fit_geometry(int w, int h, int W, int H, int *sw, int *sh, int *s1, int *s2);
 
-/* engine.cu */
+/* engine.cu: per-device launch state (cudaFuncSetAttribute is per (function, device); several nets on different devices
+ * may share one process).  A ffb_smem_cfg is a zero-initialised static next to the kernel it describes. */
+#define FFB_MAX_DEVICES 64
+typedef struct { size_t bytes[FFB_MAX_DEVICES]; } ffb_smem_cfg;
+int  ffb_num_sms(void);                                                  /* SM count of the current device */
+int  ffb_ensure_smem(const void *func, size_t smem, ffb_smem_cfg *cfg);  /* raise func's dynamic-smem limit on the current device if needed */
+
 void ffb_engine_destroy(struct ffb_engine *e);
 int  ffb_engine_forward_single(ffb_net *net);     /* net_forward(): layer_list[0].data -> bbox_list */
 

@@ -485,6 +485,44 @@ __global__ void k_copy_strided(const float *__restrict__ in, float *__restrict__
 }
 
 /* layout converters for the CHW boundary (groupconv seam, ffb_input_chw): [n][c][h][w] <-> [n][h][w][ld] */
+/* pool / upsample for channel counts that are not a multiple of 4: one thread per output float */
+__global__ void k_pool_scalar(const float *__restrict__ in, float *__restrict__ out, int n, int H, int W, int C, int ldi,
+                              int OH, int OW, int ldo, int coff, int fs, int stride, int is_max)
+{
+    pdl_trigger(); pdl_wait();
+    const long total = (long)n * OH * OW * C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); long p = i / C;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH); const long f = p / OH;
+        const int xa = max(ox * stride - (fs - 1) / 2, 0), xb = min(ox * stride - (fs - 1) / 2 + fs, W);
+        const int ya = max(oy * stride - (fs - 1) / 2, 0), yb = min(oy * stride - (fs - 1) / 2 + fs, H);
+        const float *img = in + f * (long)H * W * ldi + c;
+        float m = is_max ? __ldg(img + ((long)ya * W + xa) * ldi) : 0.f;
+        for (int y = ya; y < yb; y++)
+            for (int x = xa; x < xb; x++) {
+                const float v = __ldg(img + ((long)y * W + x) * ldi);
+                if (is_max) m = m < v ? v : m; else m += v;
+            }
+        if (!is_max) m /= (float)(fs * fs);
+        out[(f * (long)OH * OW + (long)oy * OW + ox) * ldo + coff + c] = m;
+    }
+}
+
+__global__ void k_upsample_scalar(const float *__restrict__ in, float *__restrict__ out, int n, int H, int W, int C, int ldi,
+                                  int ldo, int coff, int s)
+{
+    pdl_trigger(); pdl_wait();
+    const int OH = H * s, OW = W * s;
+    const long total = (long)n * OH * OW * C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); long p = i / C;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH); const long f = p / OH;
+        out[(f * (long)OH * OW + (long)oy * OW + ox) * ldo + coff + c] = __ldg(in + (f * (long)H * W + (long)(oy / s) * W + ox / s) * ldi + c);
+    }
+}
+
 __global__ void k_chw_to_nhwc(const float *__restrict__ src, float *__restrict__ dst, int n, int C, int H, int W, int ld)
 {
     const long total = (long)n * H * W * ld;

@@ -36,7 +36,7 @@
 #include "pw_tc.h"
 #include "sm100.cuh"
 
-extern "C" void ffb_set_error(const char *fmt, ...);
+#include "ffb_internal.h"
 
 using namespace sm100;
 
@@ -431,9 +431,7 @@ PwTcPlan *pw_tc_plan_create(int K, int N, int act, int mode)
     p->ksteps_total = (p->Kc - 1) * 4 + ((K - 32 * (p->Kc - 1)) + 7) / 8;
     p->Kld = (K + 3) & ~3;
     if (!plan_tiling(p)) { delete p; return nullptr; }
-    int dev = 0; cudaDeviceProp prop;
-    cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
-    p->num_sms = prop.multiProcessorCount;
+    p->num_sms = ffb_num_sms();
     return p;
 }
 
@@ -461,11 +459,8 @@ int pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStream_t st)
         if (make_map(&p->tmBh, d_packed, p->K, p->N, row, p->NS) != 0) return -1;
         p->tmBl = p->tmBh;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_pw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { ffb_set_error("pw_tc: cannot raise dynamic smem limit"); return -1; }
-        attr_set = true;
-    }
+    static ffb_smem_cfg attr_set;
+    if (ffb_ensure_smem((const void *)k_pw_tc, 227 * 1024, &attr_set) != 0) return -1;
     if (cudaGetLastError() != cudaSuccess) { ffb_set_error("pw_tc: weight preparation launch failed"); return -1; }
     return 0;
 }

@@ -21,6 +21,8 @@
 extern "C" {
 #endif
 
+#define FFB_E_OVERFLOW (-2)   /* ffb_detect_finish / ffb_collect: more yolo candidates than the device buffer holds (never a silent truncation) */
+
 const char *ffb_last_error(void);
 int         ffb_device_count(void);                      /* 0 without a usable CUDA device */
 

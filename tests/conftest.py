@@ -39,11 +39,33 @@ def oracle_layers(assets):
     return orc.load_net(cfg, wts, 0, 0)
 
 
+MEASURED = {"box_px": 0.0, "score": 0.0, "boxes": 0, "feat_rel": 0.0}      # worst deviations seen by this session's comparisons
+
+
 def boxes_close(got, want, px=1e-4, score=1e-6):
-    """Same count, same classes, coordinates within px pixels, scores within `score`."""
+    """Same count, same classes, coordinates within px pixels, scores within `score`.  The worst deviation seen is
+    recorded (printed in the terminal summary and written to gpurun_out/parity_measured.json on the GPU box)."""
     assert len(got) == len(want), (len(got), len(want))
     for g, e in zip(got, want):
         assert int(g["type"]) == int(e["type"])
-        assert abs(float(g["score"]) - float(e["score"])) <= score, (g, e)
-        for k in ("x1", "y1", "x2", "y2"):
-            assert abs(float(g[k]) - float(e[k])) <= px, (k, g, e)
+        ds = abs(float(g["score"]) - float(e["score"]))
+        dp = max(abs(float(g[k]) - float(e[k])) for k in ("x1", "y1", "x2", "y2"))
+        if px <= 1.0001e-4:                              # comparisons against the named (-O2) oracle only
+            MEASURED["box_px"] = max(MEASURED["box_px"], dp); MEASURED["score"] = max(MEASURED["score"], ds); MEASURED["boxes"] += 1
+        assert ds <= score, (g, e)
+        assert dp <= px, (dp, g, e)
+
+
+def note_feat(err):
+    MEASURED["feat_rel"] = max(MEASURED["feat_rel"], float(err))
+
+
+def pytest_terminal_summary(terminalreporter):
+    if MEASURED["boxes"] or MEASURED["feat_rel"]:
+        terminalreporter.write_line("parity measured this session: max box error %.3g px over %d boxes, max score error %.3g, "
+                                    "max feature-map error %.3g of the layer max" % (MEASURED["box_px"], MEASURED["boxes"], MEASURED["score"], MEASURED["feat_rel"]))
+        out = os.path.join(REPO, "gpurun_out")
+        if os.path.isdir(out):
+            import json
+            with open(os.path.join(out, "parity_measured.json"), "w") as f:
+                json.dump(MEASURED, f)

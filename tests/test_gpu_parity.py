@@ -3,10 +3,12 @@
 Tolerances (written here as the contract):
   * feature maps:  max|gpu - oracle| <= 2e-5 * max|oracle layer|   (the reference differs from itself by 8.8e-6 between
                    its -O2 and -Ofast builds; fp32 FFMA in a different summation order lands around 1e-6)
-  * boxes:         same candidate set (class, cell); coordinates within 2.5e-4 px of the oracle in source-image pixels
-                   (= 4 fp32 ulp at x ~ 600; 1 ulp there is 6.1e-5 px and the reference differs from ITSELF by 9.1e-5 px
-                   between its -O2 and -Ofast builds); scores within 5e-6 (the confidence moves by up to
-                   0.25 * |d logit|, so the feature-map tolerance alone would allow ~1e-4; measured <= 2e-6)
+  * boxes:         same candidate set (class, cell); coordinates within 1e-4 px (BASELINE.json's north_star) of the
+                   oracle / the -O2 reference goldens, in source-image pixels (1 fp32 ulp at x ~ 600 is 6.1e-5 px; the
+                   reference differs from ITSELF by 9.1e-5 px between its -O2 and -Ofast builds, SURVEY app. C -- so
+                   comparisons against the -Ofast goldens add that much); scores within 5e-6 (the confidence moves by up
+                   to 0.25 * |d logit|, so the feature-map tolerance alone would allow ~1e-4; measured <= 2e-6).
+                   The worst deviation every run measures is printed in the pytest summary (conftest.MEASURED).
   * integer/byte:  net_input's u8 -> fp32 conversion is bit-exact.
 """
 import os
@@ -17,18 +19,20 @@ import pytest
 import ffcnn_b200 as fb
 from ffcnn_b200 import synth
 from oracle import oracle as orc, ref
-from conftest import boxes_close, REPO
+from conftest import boxes_close, note_feat, REPO
 
 pytestmark = pytest.mark.gpu
 
 FEAT_TOL = 2e-5
-BOX_TOL = 2.5e-4
+BOX_TOL = 1e-4
 SCORE_TOL = 5e-6
 PW_MODES = [int(m) for m in os.environ.get("FFCNN_TEST_PW_MODES", "0,1").split(",")]
 
 
 def rel_err(a, b):
-    return float(np.abs(a - b).max() / max(float(np.abs(b).max()), 1e-30))
+    e = float(np.abs(a - b).max() / max(float(np.abs(b).max()), 1e-30))
+    note_feat(e)
+    return e
 
 
 @pytest.fixture(scope="module")
@@ -100,7 +104,7 @@ def test_reference_api_flow_and_goldens(assets, golden):
         net = p.contents
         got = np.frombuffer(fb.C.string_at(net.bbox_list, net.bbox_num * 24), fb.BOX_DTYPE)
         boxes_close(got, golden[key]["v6_O2_final"], px=BOX_TOL, score=SCORE_TOL)
-        boxes_close(got, golden[key]["v6_final"], px=BOX_TOL + 1e-4, score=SCORE_TOL)       # the -Ofast build (own noise 9e-5 px)
+        boxes_close(got, golden[key]["v6_final"], px=BOX_TOL + 1.5e-4, score=SCORE_TOL)     # the -Ofast build (own noise 9e-5 px)
         L.net_free(p)
 
 
@@ -241,7 +245,7 @@ def test_dw5_exact_mode_matches_conv_v0(assets, oracle_layers):
     for i in (116, 118, 125, 127, 129):
         assert rel_err(net.layer_output(i, 0), outs[i]) < FEAT_TOL, i
     quirk, _, _ = orc.forward(oracle_layers, x, 640, 320, v6_quirk=True)
-    assert rel_err(net.layer_output(116, 0), quirk[116]) > 1e-3          # and it really differs from the v6 default
+    assert float(np.abs(net.layer_output(116, 0) - quirk[116]).max() / np.abs(quirk[116]).max()) > 1e-3     # and it really differs from the v6 default
     net.close()
 
 
@@ -286,7 +290,8 @@ def test_dw5_quirk_on_the_smallest_maps():
         want = orc.conv_raw(x, f, iw, ih, ic, ic, 2, 1, 5, ic, 2, quirk)
         assert rel_err(got, want) < FEAT_TOL, (iw, ih, rel_err(got, want))
         if quirk:
-            assert rel_err(got, orc.conv_raw(x, f, iw, ih, ic, ic, 2, 1, 5, ic, 2, False)) > 1e-3
+            exact = orc.conv_raw(x, f, iw, ih, ic, ic, 2, 1, 5, ic, 2, False)
+            assert float(np.abs(got - exact).max() / np.abs(exact).max()) > 1e-3
 
 
 @pytest.mark.parametrize("fuse_block", [1, 2])
@@ -332,7 +337,7 @@ def test_fused_blocks_against_oracle(assets, oracle_layers, fuse_block):
     assert net.get_option("blocks") == 0
     net.detect_batch_u8(s2f, 8, 320, 320, 960)
     for f in range(8):
-        boxes_close(fused[f], net.boxes(f), px=BOX_TOL, score=SCORE_TOL)
+        boxes_close(fused[f], net.boxes(f), px=2 * BOX_TOL, score=2 * SCORE_TOL)       # two GPU plans, each within BOX_TOL of the oracle
     net.close()
 
 
@@ -361,7 +366,7 @@ def test_fused_plan_odd_batches_and_geometries(assets):
             net.close()
         assert sum(len(b) for b in res[0]) > 0
         for a, b in zip(*res):
-            boxes_close(a, b, px=BOX_TOL, score=SCORE_TOL)
+            boxes_close(a, b, px=2 * BOX_TOL * max(1, W // 320), score=2 * SCORE_TOL)    # plan vs plan (each within BOX_TOL of the oracle; 1 ulp doubles above 512 px)
 
 
 def test_second_darknet_graph_against_oracle(tmp_path):
@@ -431,3 +436,135 @@ def test_cli_prints_the_reference_lines_and_draws_boxes(assets, golden, tmp_path
         at = lines.index("frame %d: %s" % (f, bmp))
         assert lines[at + 1:at + 1 + len(want)] == want
         assert np.array_equal(ref.load_bmp(str(tmp_path / ("det%d.bmp" % f)))[0], out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: the configuration bench.py times (default fused plan, batch 256), every rank's weight path, overflow
+
+
+def _batch256_mixed(img, w, h):
+    """256 frames with known frames at the positions a persistent tile scheduler treats differently (first, last, the
+    wave boundary around 127/128): set S2 (picture-derived, golden boxes) and set S1 (seeded random, golden heads)."""
+    s2 = synth.shifted_frames_from(img, w, h, 20).reshape(20, 320, 960)
+    s1 = synth.frames_u8(4)
+    frames = np.empty((256, 320, 960), np.uint8)
+    for p in range(256):
+        frames[p] = s2[p % 16] if p % 3 else s1[p % 4]
+    known = {0: ("s2", 0), 1: ("s2", 3), 127: ("s2", 7), 128: ("s2", 19), 254: ("s1", 0), 255: ("s1", 1), 64: ("s1", 2), 200: ("s2", 3)}
+    for p, (kind, f) in known.items():
+        frames[p] = s2[f] if kind == "s2" else s1[f]
+    return frames, known
+
+
+@pytest.mark.parametrize("keep_all", [0, 2])
+def test_batch_256_default_fused_plan_against_oracle_and_goldens(assets, golden, oracle_layers, keep_all):
+    """The benchmarked configuration itself: default options (fused blocks, fused tail, buffer reuse, CUDA-graph replay) at
+    batch 256.  Heads L120 / L129 of frames {0, 1, 64, 127, 128, 200, 254, 255} against the oracle, boxes of the picture
+    frames against the reference goldens (tests/golden/synth_320.npz), candidate counts of the random frames."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    frames, known = _batch256_mixed(img, w, h)
+    net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=256)
+    net.set_option("keep_all", keep_all)
+    assert net.get_option("fuse_block") == 1 and net.get_option("fuse_tail") == 1 and net.get_option("graph") == 1
+    d = fb.DeviceBuffer(frames.nbytes).upload(frames)
+    for _ in range(3):                                                  # eager pass, capture, replay
+        net.input_u8(d.ptr, 256, 320, 320, 960, on_device=True)
+        net.forward()
+    net.detect()
+    assert net.get_option("blocks") > 0 and net.get_option("input_fused") == 1
+    g = golden["synth_320"]
+    cache = {}
+    for p, (kind, f) in sorted(known.items()):
+        if (kind, f) not in cache:
+            x, s1, s2 = orc.net_input(frames[p], 320, 320, 320, 320)
+            cache[(kind, f)] = orc.forward(oracle_layers, x, s1, s2, v6_quirk=True)
+        outs, raw, fin = cache[(kind, f)]
+        for hid in (120, 129):
+            e = rel_err(net.layer_output(hid, p), outs[hid])
+            assert e < FEAT_TOL, (p, hid, e)
+        graw = net.boxes(p, raw=True)
+        if kind == "s2":
+            want_raw, want = g[f"s2_f{f}_raw"], g[f"s2_f{f}_final"]
+            assert len(graw) == len(want_raw) and [int(t) for t in graw["type"]] == [int(t) for t in want_raw["type"]], p
+            boxes_close(net.boxes(p), want, px=BOX_TOL, score=SCORE_TOL)
+        else:
+            assert len(graw) == len(g[f"s1_f{f}_v6_O2_raw"]) == len(raw), p
+    # every copy of a frame gives identical bits wherever it sits in the batch
+    ref_pos = {}
+    for p in range(0, 256, 7):
+        key = frames[p].tobytes()
+        if key in ref_pos:
+            assert np.array_equal(net.layer_output(129, p).view(np.uint32), net.layer_output(129, ref_pos[key]).view(np.uint32)), p
+        else:
+            ref_pos[key] = p
+    net.close(); d.free()
+
+
+def test_commit_weights_path_of_nonzero_ranks(assets):
+    """What every rank > 0 does in the multi-GPU frontend: a net parsed WITHOUT a weights file (zero weights), its device
+    copy of the packed buffer filled from outside (stands in for the NCCL broadcast), ffb_commit_weights -- the heads must
+    be bit-equal to a normally loaded net's, in the default fused plan and in the layer-by-layer plan."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    fr = np.ascontiguousarray(synth.shifted_frames_from(img, w, h, 6).reshape(6, 320, 960))
+    a = fb.Net(cfg, wts, 0, 0, device=0, max_batch=6)
+    b = fb.Net(cfg, None, 0, 0, device=0, max_batch=6)
+    assert not b.packed_weights().any()
+    b.detect_batch_u8(fr, 6, 320, 320, 960)                             # zero weights: runs, finds nothing or garbage -- and must not stick
+    ptr, n = b.packed_weights_device()
+    assert n == a.net.weight_size
+    packed = a.packed_weights()
+    fb._check(fb.lib().ffb_copy_h2d(ptr, packed.ctypes.data, packed.nbytes), "ffb_copy_h2d")
+    b.commit_weights()
+    assert np.array_equal(b.packed_weights().view(np.uint32), packed.view(np.uint32))     # host copy follows the device copy
+    for keep in (0, 1):
+        res = []
+        for net in (a, b):
+            net.set_option("keep_all", keep)
+            net.detect_batch_u8(fr, 6, 320, 320, 960)
+            res.append(([net.layer_output(hid, f).tobytes() for hid in (120, 129) for f in (0, 5)], [net.boxes(f).tobytes() for f in range(6)]))
+        assert res[0] == res[1], keep
+        assert any(len(x) for x in res[0][1])
+    a.close(); b.close()
+
+
+def test_candidate_overflow_is_reported_not_truncated(assets):
+    """ffcnn.c:438-474 keeps every candidate above the threshold (up to bbox_max per frame).  When the device candidate
+    buffer is too small the library must say so (FFB_E_OVERFLOW + ffb_last_error) and ffb_detect must retry with a grown
+    buffer -- never return a silently truncated box set."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    fr = np.ascontiguousarray(synth.shifted_frames_from(img, w, h, 8).reshape(8, 320, 960))
+    net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=8)
+    net.detect_batch_u8(fr, 8, 320, 320, 960)
+    want = [net.boxes(f).tobytes() for f in range(8)]
+    assert sum(len(net.boxes(f, raw=True)) for f in range(8)) > 16
+    net.set_option("cand_cap", 5)
+    net.input_u8(fr, 8, 320, 320, 960); net.forward()
+    assert net.detect_enqueue() == 2
+    rc = fb.lib().ffb_detect_finish(net.p)
+    assert rc == -2 and b"overflow" in fb.lib().ffb_last_error()
+    assert all(len(net.boxes(f)) == 0 for f in range(8))                # nothing half-decoded is left behind
+    net.set_option("cand_cap", 5)
+    net.detect_batch_u8(fr, 8, 320, 320, 960)                           # the blocking call retries with the grown buffer
+    assert [net.boxes(f).tobytes() for f in range(8)] == want
+    net.close()
+
+
+def test_large_pointwise_layers_do_not_break_the_forward():
+    """1x1 convs whose weights fit neither pw_tc's resident plan nor the FFMA kernel's shared memory
+    (yolov3's 1024 -> 256, 512 -> 1024 ...) must still run -- through the implicit-GEMM tcgen05 kernel or the generic one."""
+    rng = np.random.default_rng(21)
+    for (ic, fn, hw, n) in ((1024, 256, 6, 2), (512, 1024, 5, 1), (256, 2304, 4, 1)):
+        row = ic + 4
+        f = np.zeros((fn, row), np.float32)
+        f[:, :ic] = rng.standard_normal((fn, ic)) / np.sqrt(ic)
+        f[:, row - 4] = rng.uniform(0.5, 1.5, fn); f[:, row - 3] = rng.uniform(-0.5, 0.5, fn)
+        x = rng.standard_normal((n, ic, hw, hw)).astype(np.float32)
+        op = fb.ConvOp(f, ic, 1, 0, 1, 1, fn, 2)
+        y = op(np.ascontiguousarray(x.transpose(0, 2, 3, 1)))
+        for b in range(n):
+            want = orc.conv_raw(x[b], f, hw, hw, ic, 1, 0, 1, 1, fn, 2, v6_quirk=True)
+            assert rel_err(y[b].transpose(2, 0, 1), want) < FEAT_TOL, (op.kernel, ic, fn)
+        op.close()
