@@ -118,6 +118,154 @@ class ClockSampler(threading.Thread):
                 "source": "nvidia-smi -lms 200" if self.proc is not None else "nvml, in-process, every 100 ms" if self.mode != "off" else "nvml, before and after"}
 
 
+FFMA_PEAK_TFLOPS = 74.4                # 148 SMs x 128 lanes x 2 flop x 1.965 GHz (nominal)
+
+
+def parity_check(net, fb, synth, np):
+    """In-run correctness (every rank, after the weight broadcast, default plan): the 4 seeded random frames (set S1) and 4
+    picture-derived frames (set S2) whose reference outputs are committed under tests/golden/synth_320.npz (written by the
+    compiled, unmodified reference -- tests/golden/make_golden.py).  S1: head checksums and candidate counts; S2: candidate
+    classes and final boxes within the contract (1e-4 px, 5e-6 score).  Returns a dict with "ok"."""
+    g = np.load(os.path.join(REPO, "tests", "golden", "synth_320.npz"))
+    raw = np.fromfile(os.path.join(fb.ASSETS, "test.bmp"), np.uint8)
+    bw, bh = int(raw[18:22].view("<u4")[0]), int(raw[22:26].view("<u4")[0])
+    bp = (bw * 3 + 3) & ~3
+    img = np.ascontiguousarray(raw[54:54 + bp * bh].reshape(bh, bp)[::-1])
+    s2 = synth.shifted_frames_from(img, bw, bh, 20, NET_W, NET_H).reshape(20, NET_H, PITCH)
+    s2_ids = (0, 3, 7, 19)
+    frames = np.concatenate([synth.frames_u8(4, NET_W, NET_H), s2[list(s2_ids)]], axis=0)
+    res = {"ok": True, "frames": 8, "max_box_px": 0.0, "max_score": 0.0, "max_head_rel": 0.0, "fail": []}
+    for _ in range(2):                                   # eager pass + graph replay
+        net.detect_batch_u8(frames, 8, NET_W, NET_H, PITCH)
+    for f in range(4):
+        for hid in (120, 129):
+            o = net.layer_output(hid, f)
+            tol = 2e-5 * float(g["s1_f%d_v6_O2_maxabs" % f][hid]) * o.size
+            d = abs(float(o.astype(np.float64).sum()) - float(g["s1_f%d_v6_O2_sum" % f][hid]))
+            res["max_head_rel"] = max(res["max_head_rel"], d / (float(g["s1_f%d_v6_O2_maxabs" % f][hid]) * o.size))
+            if not d <= tol:
+                res["fail"].append("s1 frame %d head %d checksum off by %.3g" % (f, hid, d))
+        if len(net.boxes(f, raw=True)) != len(g["s1_f%d_v6_O2_raw" % f]):
+            res["fail"].append("s1 frame %d candidate count" % f)
+    for k, f in enumerate(s2_ids):
+        want_raw, want = g["s2_f%d_raw" % f], g["s2_f%d_final" % f]
+        graw, got = net.boxes(4 + k, raw=True), net.boxes(4 + k)
+        if len(graw) != len(want_raw) or [int(t) for t in graw["type"]] != [int(t) for t in want_raw["type"]] or len(got) != len(want):
+            res["fail"].append("s2 frame %d candidate set" % f)
+            continue
+        for a, b in zip(got, want):
+            dp = max(abs(float(a[c]) - float(b[c])) for c in ("x1", "y1", "x2", "y2"))
+            ds = abs(float(a["score"]) - float(b["score"]))
+            res["max_box_px"] = max(res["max_box_px"], dp); res["max_score"] = max(res["max_score"], ds)
+            if int(a["type"]) != int(b["type"]) or dp > 1e-4 or ds > 5e-6:
+                res["fail"].append("s2 frame %d box off by %.3g px / %.3g score" % (f, dp, ds))
+    res["ok"] = not res["fail"]
+    res["fail"] = res["fail"][:4]
+    return res
+
+
+def launch_table(net, lt, B, peak_gbs, tf32_peak):
+    """One row per kernel launch slot of the plan: the layers it covers, its unfused algorithmic bytes, the bytes
+    a fused kernel MUST move (input of its first layer + output of its last + the weights, each once), its pointwise (tensor
+    pipe) and stencil/stem (FFMA) flops, and the floor time  max(must-move bytes / HBM, 3 x pointwise flops / measured
+    tcgen05 kind::tf32 peak [FFMA peak when the kernel computes them with FFMAs], FFMA flops / 74.4 TFLOP/s)."""
+    L = net.layer_num
+    names = [net.layer_cost(i)[2] for i in range(L)]
+    rows = []
+    for i in range(L):
+        if not lt[i] > 0:
+            continue
+        cover = [i]
+        if names[i].startswith("block_"):
+            k = i + 1
+            while k < L and names[k] == "in_block":
+                cover.append(k); k += 1
+        elif names[i] == "spp_fused":
+            cover = [k for k in range(L) if names[k] == "in_spp"] + [i]
+        alg = sum(net.layer_cost(k)[0] for k in ([i] if len(cover) > 1 else cover))      # a fused slot already reports the sum
+        fl_pw = fl_ffma = wbytes = 0.0
+        for k in cover:
+            a = net.layer(k)
+            if a.type != 0:
+                continue
+            b = net.layer(k + 1)
+            taps = a.fs * a.fs * (a.c // a.groups)
+            wbytes += 4.0 * a.fn * (taps + 2)
+            fl = 2.0 * taps * b.w * b.h * b.c
+            if a.fs == 1 and a.groups == 1:
+                fl_pw += fl
+            else:
+                fl_ffma += fl
+        first, last = net.layer(min(cover)), net.layer(max(cover) + 1)
+        if names[i] == "spp_fused":
+            first = net.layer(min(cover))
+        must = 4.0 * (first.w * first.h * first.c + last.w * last.h * last.c) + wbytes
+        if len(cover) == 1:
+            must = alg
+        tensor = names[i].startswith("block_mma") or "tcgen05" in names[i]
+        t_hbm = must * B / (peak_gbs * 1e9)
+        t_pw = (3.0 * fl_pw * B / (tf32_peak * 1e12)) if tensor else fl_pw * B / (FFMA_PEAK_TFLOPS * 1e12)
+        t_ffma = fl_ffma * B / (FFMA_PEAK_TFLOPS * 1e12)
+        floor_ms = 1e3 * max(t_hbm, t_pw, t_ffma)
+        bound = "hbm" if t_hbm >= max(t_pw, t_ffma) else "tensor" if t_pw >= t_ffma and tensor else "ffma"
+        rows.append({"slot": i, "kernel": names[i], "layers": len(cover), "ms": float(lt[i]), "alg_bytes": alg * B, "must_bytes": must * B,
+                     "pw_flops": fl_pw * B, "ffma_flops": fl_ffma * B, "floor_ms": floor_ms, "bound": bound})
+    return rows
+
+
+def microbench(fb, torch, np, peak_gbs, tf32_peak, stream):
+    """BASELINE configs 3 and 4 at their full sizes, CUDA events on the launching stream, 3 warm-up + 10 timed
+    launches each; inputs far larger than L2 (10 GB / 1.26 GB)."""
+    out = {}
+    rng = np.random.default_rng(5)
+
+    def packed(fn, k):
+        row = ((k + 3) & ~3) + 4
+        f = np.zeros((fn, row), np.float32)
+        f[:, :k] = rng.standard_normal((fn, k)) / np.sqrt(k)
+        f[:, row - 4] = rng.uniform(0.5, 1.5, fn); f[:, row - 3] = rng.uniform(-0.5, 0.5, fn)
+        return f
+
+    def timed(op, x, y, n, h, w, reps=10):
+        for _ in range(3):
+            op.run_ptr(x.data_ptr(), y.data_ptr(), n, h, w, stream.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            op.run_ptr(x.data_ptr(), y.data_ptr(), n, h, w, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # config 3: 3x3 depthwise, 160x160x96, batch 1024, leaky
+    n, h, w, c = 1024, 160, 160, 96
+    x = torch.empty((n, h, w, c), dtype=torch.float32, device="cuda").normal_()
+    y = torch.empty_like(x)
+    op = fb.ConvOp(packed(c, 9), c, c, 1, 1, 3, c, 2)
+    ms = timed(op, x, y, n, h, w)
+    alg = 2.0 * n * h * w * c * 4 + c * 11 * 4
+    out["dw3x3_160x160x96_b1024"] = {"ms": ms, "kernel": op.kernel, "GBps": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak_gbs,
+                                    "alg_bytes": alg, "bound": "hbm"}
+    op.close(); del x, y
+    torch.cuda.empty_cache()
+    # config 4: 1x1 pointwise 40x40, 192 -> 192, batch 1024, leaky
+    n, h, w, c = 1024, 40, 40, 192
+    x = torch.empty((n, h, w, c), dtype=torch.float32, device="cuda").normal_()
+    y = torch.empty_like(x)
+    op = fb.ConvOp(packed(c, c), c, 1, 0, 1, 1, c, 2)
+    ms = timed(op, x, y, n, h, w)
+    M = n * h * w
+    alg = M * (c + c) * 4.0 + c * (c + 2) * 4.0
+    fl = 2.0 * M * c * c
+    passes = 1 if "1xtf32" in op.kernel else 3
+    out["pw_192x192_40x40_b1024"] = {"ms": ms, "kernel": op.kernel, "mode": "%dxTF32" % passes, "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak_gbs,
+                                     "tensor_frac": passes * fl / (ms * 1e-3) / 1e12 / tf32_peak, "tflops_useful": fl / (ms * 1e-3) / 1e12,
+                                     "alg_bytes": alg, "flops": fl, "bound": "hbm" if alg / (peak_gbs * 1e9) > passes * fl / (tf32_peak * 1e12) else "tensor"}
+    op.close(); del x, y
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(procs: int, frames_per_proc: int):
     """The reference's own CPU implementation of the path: oracle/_ref/ffcnn_ref_bench (unmodified ffcnn.c + conv-v6.c,
     build.sh flags), P independent single-threaded processes.  Returns (fps, description)."""
@@ -202,6 +350,21 @@ def main():
     bcast_bytes = 0
     if world > 1:
         bcast_bytes = shard.broadcast_weights(net, dist, device=torch.device("cuda", local))
+
+    pc = parity_check(net, fb, synth, np)
+    pc_all = torch.tensor([1.0 if pc["ok"] else 0.0, pc["max_box_px"]], dtype=torch.float64, device="cuda")
+    pc_min, pc_max = pc_all.clone(), pc_all.clone()
+    if world > 1:
+        dist.all_reduce(pc_min, op=dist.ReduceOp.MIN); dist.all_reduce(pc_max, op=dist.ReduceOp.MAX)
+    if not pc["ok"]:
+        print("bench.py rank %d: PARITY CHECK FAILED: %s" % (rank, pc["fail"]), file=sys.stderr)
+    if float(pc_min[0]) < 1.0:                                  # some rank computes wrong results: no throughput number for wrong answers
+        if rank == 0:
+            os.dup2(saved_stdout, 1)
+            print(json.dumps({"metric": METRIC, "value": None, "unit": "frames/s", "n_gpus": world, "parity_check": {"ok": False, "rank0": pc}}), flush=True)
+        raise SystemExit(3)
+    pc["ranks_ok"] = world
+    pc["max_box_px_all_ranks"] = float(pc_max[1])
 
     # synthetic frames: 4 distinct resident batches per rank (seeded per global frame index), rotated across steps
     NB = 4
@@ -321,6 +484,11 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
+        try:
+            tf32_peak = fb.measure_tf32_peak()
+            tf32_src = "measured live: ffb_measure_tf32_peak (tcgen05.mma.kind::tf32 M128 N256 K8 from shared memory on every SM)"
+        except Exception as ex:
+            tf32_peak, tf32_src = 1125.0, "nominal (half the 2.25 PFLOP/s bf16 figure); live measurement failed: %s" % ex
         value = world * B * K / (ms * 1e-3)
         e2e = world * B * KE / (ms_e2e * 1e-3)
         # per-layer CUDA-event timings (same batch), grouped by kernel: the dominant kernel's roofline
@@ -341,6 +509,18 @@ def main():
                 if lt[i] > 0:
                     print("L%-3d %-16s %8.4f ms %8.1f GB/s  %5.1f%% of HBM peak" % (i, name, lt[i], by * B / (lt[i] * 1e-3) / 1e9,
                                                                                   100 * by * B / (lt[i] * 1e-3) / 1e9 / peak), file=sys.stderr)
+        rows = launch_table(net, lt, B, peak, tf32_peak)
+        fused_by = {}
+        for r in rows:
+            g = fused_by.setdefault(r["kernel"], {"ms": 0.0, "floor_ms": 0.0, "must_bytes": 0.0, "alg_bytes": 0.0, "launches": 0, "bounds": {}})
+            g["ms"] += r["ms"]; g["floor_ms"] += r["floor_ms"]; g["must_bytes"] += r["must_bytes"]; g["alg_bytes"] += r["alg_bytes"]; g["launches"] += 1
+            g["bounds"][r["bound"]] = g["bounds"].get(r["bound"], 0) + 1
+        floor_total = sum(r["floor_ms"] for r in rows)
+        must_total = sum(r["must_bytes"] for r in rows)
+        if args.layers:
+            for r in rows:
+                print("slot L%-3d %-22s %2d layers %8.4f ms  floor %7.4f ms (%s)  %5.1f%% of its floor   must-move %7.1f MB (alg %7.1f MB)" %
+                      (r["slot"], r["kernel"], r["layers"], r["ms"], r["floor_ms"], r["bound"], 100 * r["floor_ms"] / r["ms"], r["must_bytes"] / 1e6, r["alg_bytes"] / 1e6), file=sys.stderr)
         traffic = None
         try:
             tj = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
@@ -367,11 +547,27 @@ def main():
                                        "charged the sum over the layers it replaces, its real DRAM traffic (traffic_of) is far lower -- the expanded tensors never reach HBM", "kernel_share_of_step": tg["ms"] / total_ms, "layers_in_kernel": tg["layers"],
                          "whole_graph": {"achieved": ALG_BYTES_PER_FRAME * B * K / (ms * 1e-3) / 1e9 / 1, "frac": ALG_BYTES_PER_FRAME * B * K / (ms * 1e-3) / 1e9 / peak,
                                          "alg_bytes_per_frame": ALG_BYTES_PER_FRAME},
+                         "fused": {"definition": "per launch: floor = max(bytes the launch must move (input of its first layer + output of its last + weights, "
+                                                 "each once) / HBM peak, 3 x pointwise flops / tf32 tensor peak (FFMA peak for FFMA kernels), stencil+stem flops / FFMA peak); "
+                                                 "frac = floor / measured time.  This is the roofline of the kernels as fused; `frac` above is against the UNFUSED per-layer bytes of SURVEY 8d",
+                                   "kernel": top, "frac": fused_by[top]["floor_ms"] / fused_by[top]["ms"], "floor_ms": fused_by[top]["floor_ms"], "ms": fused_by[top]["ms"],
+                                   "tf32_peak_tflops": tf32_peak, "tf32_peak_source": tf32_src, "ffma_peak_tflops": FFMA_PEAK_TFLOPS,
+                                   "whole_graph": {"floor_ms": floor_total, "ms_per_step": ms / K, "frac": floor_total / (ms / K), "must_move_MB_per_frame": must_total / B / 1e6,
+                                                   "fps_at_floor": B / (floor_total * 1e-3)},
+                                   "by_kernel": {k: {"ms": round(v["ms"], 4), "floor_ms": round(v["floor_ms"], 4), "frac": round(v["floor_ms"] / v["ms"], 3),
+                                                     "launches": v["launches"], "bounds": v["bounds"]} for k, v in sorted(fused_by.items())}},
                          "by_kernel": {k: {"ms": round(v["ms"], 4), "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
                                            "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3), "layers": v["layers"]} for k, v in sorted(groups.items())}},
         }
+        line["parity_check"] = pc
         if pic_result is not None:
             line["e2e"]["picture_frames"] = pic_result
+        if world == 1 and os.environ.get("BENCH_MICRO", "1") == "1":
+            net.close()                                   # the microbench tensors (20 GB) want the arena's room on smaller boxes
+            try:
+                line["microbench"] = microbench(fb, torch, np, peak, tf32_peak, stream)
+            except Exception as ex:                      # never a reason to lose the line
+                line["microbench"] = {"error": str(ex)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, cpus_before)         # the CPU baseline uses every host core
             try:

@@ -100,6 +100,7 @@ def lib():
         "ffb_layer_times": (C.c_int, [NP, fp, C.c_int, C.c_int, C.c_int]),
         "ffb_layer_cost": (C.c_int, [NP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_char_p, C.c_int]),
         "ffb_launches_per_forward": (C.c_int, [NP]),
+        "ffb_measure_tf32_peak": (C.c_int, [C.POINTER(C.c_double)]),
         "ffb_conv_create": (vp, [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "ffb_conv_destroy": (None, [vp]),
         "ffb_conv_run": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -131,7 +132,7 @@ EXPORTS = ["ffb_last_error", "ffb_device_count", "ffb_net_parse", "ffb_net_attac
            "ffb_commit_weights", "ffb_set_option", "ffb_get_option", "ffb_set_stream", "ffb_get_stream", "ffb_sync",
            "ffb_input_u8", "ffb_input_chw", "ffb_forward", "ffb_detect", "ffb_detect_enqueue", "ffb_detect_finish",
            "ffb_last_d2h_bytes", "ffb_boxes", "ffb_raw_boxes",
-           "ffb_detect_batch_u8", "ffb_submit_u8", "ffb_collect", "ffb_layer_output", "ffb_layer_times", "ffb_layer_cost", "ffb_launches_per_forward",
+           "ffb_detect_batch_u8", "ffb_submit_u8", "ffb_collect", "ffb_layer_output", "ffb_layer_times", "ffb_layer_cost", "ffb_launches_per_forward", "ffb_measure_tf32_peak",
            "ffb_conv_create", "ffb_conv_destroy", "ffb_conv_run", "ffb_conv_kernel_name", "ffb_dev_alloc", "ffb_dev_free",
            "ffb_copy_h2d", "ffb_copy_d2h", "ffb_host_alloc_pinned", "ffb_host_free_pinned", "ffb_chw_to_nhwc",
            "ffb_nhwc_to_chw", "net_load", "net_free", "net_input", "net_forward", "net_dump", "net_profile", "groupconv",
@@ -150,6 +151,13 @@ def _check(rc: int, what: str):
 
 def device_count() -> int:
     return lib().ffb_device_count()
+
+
+def measure_tf32_peak() -> float:
+    """Measured dense tcgen05 kind::tf32 TFLOP/s of the current device (roofline denominator)."""
+    v = C.c_double(0)
+    _check(lib().ffb_measure_tf32_peak(C.byref(v)), "ffb_measure_tf32_peak")
+    return v.value
 
 
 def default_model() -> tuple[str, str]:
@@ -385,6 +393,10 @@ class ConvOp:
     @property
     def kernel(self) -> str:
         return lib().ffb_conv_kernel_name(self.h).decode()
+
+    def run_ptr(self, in_ptr: int, out_ptr: int, n: int, ih: int, iw: int, stream: int | None = None):
+        """Raw device pointers (NHWC fp32, channel pitch = ALIGN(c, 4)); asynchronous on `stream`."""
+        _check(lib().ffb_conv_run(self.h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), n, ih, iw, C.c_void_p(stream) if stream else None), "ffb_conv_run")
 
     def run(self, d_in: DeviceBuffer, d_out: DeviceBuffer, n: int, ih: int, iw: int, stream: int | None = None):
         _check(lib().ffb_conv_run(self.h, d_in.ptr, d_out.ptr, n, ih, iw, C.c_void_p(stream) if stream else None), "ffb_conv_run")

@@ -371,6 +371,59 @@ int ffb_make_tensor_map(CUtensorMap *m, const void *base, int rank, const unsign
     return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Measured tensor-pipe peak for the roofline denominators ("measure TF32 peak on device"): every SM issues
+ * back-to-back tcgen05.mma.kind::tf32 M=128 N=256 K=8 instructions on operand tiles resident in shared memory (contents
+ * irrelevant: zeros), four independent TMEM accumulators... the tensor pipe is the only thing working.  Not a product
+ * path: bench.py calls it once to report `roofline.fused` against a measured number instead of a nominal one. */
+__global__ void __launch_bounds__(128, 1) k_tf32_peak(int iters)
+{
+    extern __shared__ uint8_t peak_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(peak_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar; __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<float4 *>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before_sync(); __syncthreads(); tc_fence_after_sync();
+    const uint32_t tmem = slot;
+    if (warp == 1 && elect_one()) {
+        const uint32_t idesc = umma_idesc_tf32(128, 256);
+        const uint32_t a0 = smem_u32(sm), b0 = a0 + 16384;            /* A: [128 x 32] SW128, B: [256 x 32] SW128 */
+        for (int it = 0; it < iters; it++)
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++)
+                mma_tf32_ss(tmem + (uint32_t)((it & 1) * 256), umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc, 1);
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+    }
+    tc_fence_before_sync(); __syncthreads();
+    if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+}
+
+extern "C" int ffb_measure_tf32_peak(double *tflops)
+{
+    static ffb_smem_cfg cfg;
+    const size_t smem = 16384 + 32768 + 1024;
+    if (ffb_ensure_smem((const void *)k_tf32_peak, smem, &cfg) != 0) return -1;
+    const int sms = ffb_num_sms(), iters = 20000;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { ffb_set_error("cudaEventCreate failed"); return -1; }
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(a, 0);
+        k_tf32_peak<<<sms, 128, smem, 0>>>(iters);
+        cudaEventRecord(b, 0);
+        if (cudaEventSynchronize(b) != cudaSuccess) { ffb_set_error("tf32 peak kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (tflops) *tflops = (double)sms * iters * 4.0 * 2.0 * 128 * 256 * 8 / (best * 1e-3) / 1e12;
+    return 0;
+}
+
 static long long *g_tc_trace = nullptr;
 extern "C" void ffb_tc_set_trace(long long *dev_buf) { g_tc_trace = dev_buf; }   /* developer hook, effective only in -DFFB_TC_TRACE builds */
 

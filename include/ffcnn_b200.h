@@ -121,6 +121,10 @@ int  ffb_layer_cost(NET *net, int layer, double *bytes, double *flops, char *ker
 
 int  ffb_launches_per_forward(NET *net);                 /* kernels enqueued by one ffb_forward */
 
+/* Measured dense tcgen05.mma.kind::tf32 rate of the current device in TFLOP/s (every SM issuing M=128 N=256 K=8 MMAs
+ * back to back from shared memory): the tensor-pipe denominator of the roofline report.  ~10 ms. */
+int  ffb_measure_tf32_peak(double *tflops);
+
 /* ---- single operator on device tensors (configs 3 and 4 of BASELINE.json; op-level parity) - */
 
 typedef struct ffb_conv ffb_conv;

@@ -39,7 +39,7 @@ def oracle_layers(assets):
     return orc.load_net(cfg, wts, 0, 0)
 
 
-MEASURED = {"box_px": 0.0, "score": 0.0, "boxes": 0, "feat_rel": 0.0}      # worst deviations seen by this session's comparisons
+MEASURED = {"box_px": 0.0, "box_px_large_nets": 0.0, "score": 0.0, "boxes": 0, "feat_rel": 0.0}      # worst deviations seen by this session's comparisons
 
 
 def boxes_close(got, want, px=1e-4, score=1e-6):
@@ -50,8 +50,10 @@ def boxes_close(got, want, px=1e-4, score=1e-6):
         assert int(g["type"]) == int(e["type"])
         ds = abs(float(g["score"]) - float(e["score"]))
         dp = max(abs(float(g[k]) - float(e[k])) for k in ("x1", "y1", "x2", "y2"))
-        if px <= 1.0001e-4:                              # comparisons against the named (-O2) oracle only
+        if px <= 1.0001e-4:                              # comparisons against the named (-O2) oracle at the 320x320 geometry
             MEASURED["box_px"] = max(MEASURED["box_px"], dp); MEASURED["score"] = max(MEASURED["score"], ds); MEASURED["boxes"] += 1
+        elif px <= 2.0001e-4:
+            MEASURED["box_px_large_nets"] = max(MEASURED["box_px_large_nets"], dp)
         assert ds <= score, (g, e)
         assert dp <= px, (dp, g, e)
 
@@ -62,8 +64,9 @@ def note_feat(err):
 
 def pytest_terminal_summary(terminalreporter):
     if MEASURED["boxes"] or MEASURED["feat_rel"]:
-        terminalreporter.write_line("parity measured this session: max box error %.3g px over %d boxes, max score error %.3g, "
-                                    "max feature-map error %.3g of the layer max" % (MEASURED["box_px"], MEASURED["boxes"], MEASURED["score"], MEASURED["feat_rel"]))
+        terminalreporter.write_line("parity measured this session: max box error %.3g px over %d boxes at 320x320 (%.3g px on larger nets / plan-vs-plan), "
+                                    "max score error %.3g, max feature-map error %.3g of the layer max"
+                                    % (MEASURED["box_px"], MEASURED["boxes"], MEASURED["box_px_large_nets"], MEASURED["score"], MEASURED["feat_rel"]))
         out = os.path.join(REPO, "gpurun_out")
         if os.path.isdir(out):
             import json
