@@ -101,6 +101,15 @@ def lib():
         "ffb_layer_cost": (C.c_int, [NP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_char_p, C.c_int]),
         "ffb_launches_per_forward": (C.c_int, [NP]),
         "ffb_measure_tf32_peak": (C.c_int, [C.POINTER(C.c_double)]),
+        "ffb_multi_create": (vp, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, ip, C.c_int, C.c_int]),
+        "ffb_multi_destroy": (None, [vp]),
+        "ffb_multi_devices": (C.c_int, [vp]),
+        "ffb_multi_net": (NP, [vp, C.c_int]),
+        "ffb_multi_broadcast_bytes": (C.c_long, [vp]),
+        "ffb_multi_detect_u8": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]),
+        "ffb_multi_submit_u8": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]),
+        "ffb_multi_collect": (C.c_int, [vp]),
+        "ffb_multi_boxes": (C.c_int, [vp, C.c_int, C.POINTER(C.POINTER(BBOX))]),
         "ffb_conv_create": (vp, [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "ffb_conv_destroy": (None, [vp]),
         "ffb_conv_run": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -133,6 +142,8 @@ EXPORTS = ["ffb_last_error", "ffb_device_count", "ffb_net_parse", "ffb_net_attac
            "ffb_input_u8", "ffb_input_chw", "ffb_forward", "ffb_detect", "ffb_detect_enqueue", "ffb_detect_finish",
            "ffb_last_d2h_bytes", "ffb_boxes", "ffb_raw_boxes",
            "ffb_detect_batch_u8", "ffb_submit_u8", "ffb_collect", "ffb_layer_output", "ffb_layer_times", "ffb_layer_cost", "ffb_launches_per_forward", "ffb_measure_tf32_peak",
+           "ffb_multi_create", "ffb_multi_destroy", "ffb_multi_devices", "ffb_multi_net", "ffb_multi_broadcast_bytes",
+           "ffb_multi_detect_u8", "ffb_multi_submit_u8", "ffb_multi_collect", "ffb_multi_boxes",
            "ffb_conv_create", "ffb_conv_destroy", "ffb_conv_run", "ffb_conv_kernel_name", "ffb_dev_alloc", "ffb_dev_free",
            "ffb_copy_h2d", "ffb_copy_d2h", "ffb_host_alloc_pinned", "ffb_host_free_pinned", "ffb_chw_to_nhwc",
            "ffb_nhwc_to_chw", "net_load", "net_free", "net_input", "net_forward", "net_dump", "net_profile", "groupconv",
@@ -333,6 +344,57 @@ class Net:
 
     def commit_weights(self):
         _check(self._L.ffb_commit_weights(self.p), "ffb_commit_weights")
+
+
+class MultiNet:
+    """ffb_multi_*: the C multi-GPU frontend (one NET, host thread and CUDA graph per device; NCCL weight broadcast at load)."""
+
+    def __init__(self, cfg: str, weights: str | None, inputw: int = 0, inputh: int = 0, devices=None, max_batch_per_device: int = 1):
+        L = lib()
+        self._L = L
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        self.h = L.ffb_multi_create(cfg.encode(), weights.encode() if weights else None, inputw, inputh, arr, len(devices) if devices else 0, max_batch_per_device)
+        if not self.h:
+            raise FfcnnError(f"ffb_multi_create: {_err()}")
+
+    @property
+    def devices(self) -> int:
+        return self._L.ffb_multi_devices(self.h)
+
+    @property
+    def broadcast_bytes(self) -> int:
+        return self._L.ffb_multi_broadcast_bytes(self.h)
+
+    def set_option(self, name: str, value: int):
+        for g in range(self.devices):
+            _check(self._L.ffb_set_option(self._L.ffb_multi_net(self.h, g), name.encode(), int(value)), f"ffb_set_option({name})")
+
+    def detect_u8(self, frames, n: int, w: int, h: int, pitch: int):
+        ptr = frames if isinstance(frames, int) else np.ascontiguousarray(frames, np.uint8).ctypes.data
+        _check(self._L.ffb_multi_detect_u8(self.h, ptr, n, w, h, pitch, None, None), "ffb_multi_detect_u8")
+
+    def submit_u8(self, frames, n: int, w: int, h: int, pitch: int):
+        ptr = frames if isinstance(frames, int) else np.ascontiguousarray(frames, np.uint8).ctypes.data
+        _check(self._L.ffb_multi_submit_u8(self.h, ptr, n, w, h, pitch, None, None), "ffb_multi_submit_u8")
+
+    def collect(self):
+        _check(self._L.ffb_multi_collect(self.h), "ffb_multi_collect")
+
+    def boxes(self, frame: int) -> np.ndarray:
+        ptr = C.POINTER(BBOX)()
+        n = _check(self._L.ffb_multi_boxes(self.h, frame, C.byref(ptr)), "ffb_multi_boxes")
+        return _boxes_to_np(ptr, n)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.ffb_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def groupconv(x: np.ndarray, filt: np.ndarray, iw, ih, ic, ig, pad, stride, fs, fn, act) -> np.ndarray:

@@ -46,12 +46,11 @@ static BlkInst g_inst[] = {
     INST2(3, 3, 1, 1), INST2(3, 3, 1, 3),                         /* 24->136->24 */
     INST2(3, 6, 2, 1), INST2(3, 6, 2, 3),                         /* 24->136->48 s2 */
     INST2(6, 6, 1, 1), INST2(6, 6, 1, 2),                         /* 48->224->48 */
-#ifdef FFB_BLK_TC
-    /* experimental: expand GEMM on tcgen05 (build with EXTRA=-DFFB_BLK_TC, run with FFCNN_BLK_TC=1), the (tile, group) shapes the
-       default plan of yolo-fastest-1.1 uses */
+    /* expand GEMM on tcgen05 (x split hi/lo into TMEM as the A operand, W1 chunk as SWIZZLE_128B B sub-tiles, accumulators in
+       TMEM one chunk ahead of the depthwise stage): the (tile, group) shapes the plan of yolo-fastest-1.1 uses.  Selected per
+       block shape where it measured faster (tc_wanted below); FFCNN_BLK_TC=1 forces it wherever an instance exists, -1 disables it. */
     INST_TC(1, 1, 1, 2, 2), INST_TC(1, 1, 2, 1, 2), INST_TC(1, 1, 1, 2, 3), INST_TC(1, 2, 1, 2, 3),
-    INST_TC(2, 2, 1, 2, 2), INST_TC(2, 3, 2, 1, 3), INST_TC(3, 3, 1, 2, 3), INST_TC(6, 6, 1, 1, 1),
-#endif
+    INST_TC(2, 2, 1, 2, 2), INST_TC(2, 3, 2, 1, 3), INST_TC(3, 3, 1, 2, 3), INST_TC(6, 6, 1, 1, 1), INST_TC(6, 6, 1, 1, 2),
 };
 #undef INST3
 #undef INST2
@@ -150,8 +149,11 @@ BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
     p->OH = (h - 3 + 2) / stride + 1; p->OW = (w - 3 + 2) / stride + 1;
     if (p->OW % 2 || p->OH < 1) { delete p; return nullptr; }
     p->KS1 = (cin + 7) / 8; p->NT3 = (cout + 7) / 8; p->G = (cexp + 15) / 16;
-    static const int env_tc = getenv("FFCNN_BLK_TC") ? atoi(getenv("FFCNN_BLK_TC")) : 0;      /* experimental, not yet validated on a GPU */
-    p->tc = env_tc ? 1 : 0;
+    /* measured on a B200 at batch 256 (profiles/r2a_block_tc.txt): the tcgen05 expand stage wins on the 96- and 224-channel
+       blocks (L38-L57 -5 %, L58 -12 %, L84-L108 -9 %), is neutral at 32 / 48 channels and loses where its TMEM budget
+       forces one CTA per SM (L22, L35, L61-L80) */
+    static const int env_tc = getenv("FFCNN_BLK_TC") ? atoi(getenv("FFCNN_BLK_TC")) : 0;
+    p->tc = env_tc > 0 ? 1 : env_tc < 0 ? 0 : (cexp == 96 || cexp == 224) ? 1 : 0;
     /* round up to an instantiated (KS1, NT3) pair: zero-padded K / N lanes cost tensor work, not correctness */
     bool found = false;
     for (int k = p->KS1; k <= 6 && !found; k++)
@@ -185,6 +187,7 @@ void blk_plan_destroy(BlkPlan *p)
 }
 
 const char *blk_describe(const BlkPlan *p) { return p ? p->desc : ""; }
+int blk_uses_tcgen05(const BlkPlan *p) { return p && p->tc; }
 
 int blk_prepare(BlkPlan *p, const float *p1, const float *pd, const float *p3, cudaStream_t st)
 {
@@ -209,9 +212,7 @@ int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
     a.TH = p->TH; a.TW = p->TW; a.HH = p->HH; a.HW = p->HW; a.ntx = (p->OW + p->TW - 1) / p->TW; a.nty = (p->OH + p->TH - 1) / p->TH;
     a.ntiles = (long)n * a.ntx * a.nty;
     a.NC = p->NC; a.xrows = p->xrows;
-#ifdef FFB_BLK_TC
     a.nmt = p->nmt; a.tmem_cols = (uint32_t)p->tmem_cols;
-#endif
     a.XH = p->XH; a.XW = p->XW; a.xo = p->xo; a.yo = p->yo; a.frame = p->frame;
     a.inv_tpf = 1.0f / (float)(a.ntx * a.nty); a.inv_ntx = 1.0f / (float)a.ntx;
     CUtensorMap tm;

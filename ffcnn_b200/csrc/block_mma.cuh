@@ -58,9 +58,7 @@ struct BlkArgs {
     int N, H, W, OH, OW, ldx, ldy, cout;
     int TH, TW, HH, HW, ntx, nty; long ntiles;
     int NC, xrows;
-#ifdef FFB_BLK_TC
     int nmt; uint32_t tmem_cols;          /* TC: 128-pixel m-tiles of the x tile, TMEM columns to allocate (power of 2) */
-#endif
     int XH, XW, xo, yo, frame;            /* x-tile box and its offset inside the halo; frame: one tile covers the whole image */
     float inv_tpf, inv_ntx;
     float slope1, sloped, slope3, slope_res; int res;
@@ -152,16 +150,12 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 96);       /* full_x[2], full_w[2] */
     int2     *sMap = reinterpret_cast<int2 *>(smem + 128);          /* [xrows]: x-tile pixel -> { byte offset of its E row or -1, hy | hx << 16 } */
     float    *sW = smem + 128 + 2 * a.xrows;
-#ifdef FFB_BLK_TC
-    if (TC) sW += ((1024u - (sm100::smem_u32(sW) & 1023u)) & 1023u) >> 2;   /* UMMA SWIZZLE_128B atoms are 1024-byte aligned */
-#endif
+    if constexpr (TC) sW += ((1024u - (sm100::smem_u32(sW) & 1023u)) & 1023u) >> 2;   /* UMMA SWIZZLE_128B atoms are 1024-byte aligned */
     float    *sXB = sW + 2 * off.total;                             /* [2][xrows * SXs] */
     float    *sE = sXB + 2 * a.xrows * SXs;
     uint64_t *full_x = bars, *full_w = bars + 2;
-#ifdef FFB_BLK_TC
     uint64_t *dfull = bars + 4;                                     /* TC: expand accumulator buffer [2] written (tcgen05.commit) */
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
-#endif
     const uint32_t sE_addr = sm100::smem_u32(sE), sW_addr = sm100::smem_u32(sW);
     const uint32_t x_bytes = (uint32_t)a.XH * a.XW * SXs * 4;
     constexpr uint32_t w_bytes = (uint32_t)off.total * 4;
@@ -169,16 +163,10 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
 
     if (tid == 0) {
         sm100::tma_prefetch_desc(&tmX);
-#ifdef FFB_BLK_TC
-        for (int i = 0; i < 6; i++) sm100::mbar_init(bars + i, 1);
-#else
-        for (int i = 0; i < 4; i++) sm100::mbar_init(bars + i, 1);
-#endif
+        for (int i = 0; i < (TC ? 6 : 4); i++) sm100::mbar_init(bars + i, 1);
         sm100::fence_barrier_init();
     }
-#ifdef FFB_BLK_TC
     if (TC && warp == 0) sm100::tmem_alloc(tmem_slot, a.tmem_cols);
-#endif
     if (tid < 2 * COUT_P) sSB3[tid] = a.sb3[tid];
     for (int xp = tid; xp < a.xrows; xp += BLK_THREADS) {
         const int ry = xp / a.XW, rx = xp - ry * a.XW, hy = ry + a.yo, hx = rx + a.xo;
@@ -200,15 +188,10 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     const int nunits = QUAD ? ((a.TH + 1) / 2 * a.TW + 15) >> 4 : (a.TH * a.TW + 15) >> 4;
     const int nq = warp < nunits ? (nunits - warp + BLK_WARPS - 1) / BLK_WARPS : 0;     /* units this warp owns (warp-uniform) */
     const uint32_t rowpitch = (uint32_t)HW * SEs * 4;
-#ifdef FFB_BLK_TC
     if (TC) sm100::tc_fence_before_sync();
-#endif
     __syncthreads();
-#ifdef FFB_BLK_TC
     if (TC) sm100::tc_fence_after_sync();
-#endif
     pdl_trigger(); pdl_wait();
-#ifdef FFB_BLK_TC
     /* ---- TC: expand GEMM on tcgen05.  TMEM columns: per 128-pixel m-tile mt the A operand [x_hi (KP cols) | x_lo (KP cols)]
        at mt * 2KP, then the accumulators D[mt][buf] (16*GC cols each, double buffered over chunks) ---- */
     constexpr int KP = 8 * KS1, KC = (KS1 + 3) / 4;
@@ -234,7 +217,6 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
         }
         sm100::tc_commit(dfull + buf);
     };
-#endif
 
     auto load_x = [&](long tile, int b) {                                       /* one thread */
         const BlkTile q = blk_tile<S>(a, tile);
@@ -268,7 +250,6 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                 for (int j = 0; j < 4; j++) pacc[mi][nt][j] = 0.f;
         sm100::mbar_wait(full_x + xb, (it >> 1) & 1);
 
-#ifdef FFB_BLK_TC
         if constexpr (TC) {
             /* x tile -> TMEM as the A operand, split hi/lo (thread = pixel = TMEM lane); x itself stays untouched in shared
                memory for the shortcut.  All expand MMAs of the previous tile have completed (their dfull waits). */
@@ -297,7 +278,6 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                 issue_expand(ws0, cs & 1u);
             }
         }
-#endif
 
         for (int c = 0; c < a.NC; c++, cs++) {
             const int wb = w_resident ? 0 : cs & 1;
@@ -307,8 +287,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
             const float *wc = sW + wb * off.total;
             const float *wl4 = wc + lane * 4, *wt4 = wc + 4 * t;
 
-#ifdef FFB_BLK_TC
-            bool expand_pending = false;
+            [[maybe_unused]] bool expand_pending = false;
             if constexpr (TC) {
                 /* ---------------- stage A (TC): the chunk's expand accumulators TMEM -> BN + act -> E rows ---------------- */
                 const uint32_t buf = cs & 1u;
@@ -343,7 +322,6 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                 sm100::tc_fence_before_sync();
                 expand_pending = c + 1 < a.NC;
             } else
-#endif
             /* ---------------- stage A: expand GEMM; work item = MT m-tiles x all GC groups of the chunk ----------------
                the A fragments (x, split hi/lo on the fly) are loaded once per k-step and reused by every group */
             for (int item = warp; item < nitems; item += BLK_WARPS) {
@@ -414,7 +392,6 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     }
             }
             __syncthreads();
-#ifdef FFB_BLK_TC
             if constexpr (TC) {
                 /* the next chunk's expand GEMM runs on the tensor core while the warps do stage B of this one: D[.][buf ^ 1] was
                    drained before the previous barrier pair, its weights were requested at the top of this chunk */
@@ -424,7 +401,6 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     expand_pending = false;
                 }
             }
-#endif
 
             /* ---------------- stage B: depthwise 3x3 in registers -> projection GEMM ---------------- */
 #pragma unroll
@@ -493,7 +469,6 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     }
                 }
             }
-#ifdef FFB_BLK_TC
             if constexpr (TC) {
                 if (tid == 0 && expand_pending) {         /* the next chunk's weights had not landed when stage B started */
                     sm100::mbar_wait(full_w + (wb ^ 1), ((cs + 1) >> 1) & 1u);
@@ -501,7 +476,6 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     issue_expand((uint32_t)(wb ^ 1), (cs + 1) & 1u);
                 }
             }
-#endif
         }
 
         /* ---------------- block epilogue: BN + act [+ shortcut from the resident x tile] -> y ---------------- */
@@ -532,13 +506,11 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
             }
         }
     }
-#ifdef FFB_BLK_TC
     if constexpr (TC) {
         sm100::tc_fence_before_sync();
         __syncthreads();
         if (warp == 0) { sm100::tc_fence_after_sync(); sm100::tmem_dealloc(tmem_base, a.tmem_cols); }
     }
-#endif
 }
 
 /* Build the fragment-ordered weight chunks of one block from the three convs' packed reference rows

@@ -14,3 +14,4 @@ void     blk_plan_destroy(BlkPlan *p);
 int      blk_prepare(BlkPlan *p, const float *p1, const float *pd, const float *p3, cudaStream_t st);
 int      blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st);
 const char *blk_describe(const BlkPlan *p);          /* "tile 16x32 gc1 mtw4 smem 93KB occ2" */
+int      blk_uses_tcgen05(const BlkPlan *p);         /* the expand GEMM of this plan runs on tcgen05 (TMEM accumulators) */

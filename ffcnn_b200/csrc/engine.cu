@@ -1340,7 +1340,7 @@ int ffb_layer_cost(NET *net, int i, double *bytes, double *flops, char *kname, i
             g_cost_recursing = true;
             for (int k = i + 1; k <= (b.sc >= 0 ? b.sc : i + 2); k++) { double b2 = 0, f2 = 0; ffb_layer_cost(net, k, &b2, &f2, NULL, 0); by += b2; fl += f2; }
             g_cost_recursing = false;
-            nm = b.plan ? "block_mma_3xtf32" : "block_reg_fp32";
+            nm = b.plan ? (blk_uses_tcgen05(b.plan) ? "block_mma_tcgen05_3xtf32" : "block_mma_3xtf32") : "block_reg_fp32";
         }
     }
     if (bytes) *bytes = by;

@@ -103,6 +103,31 @@ int  ffb_submit_u8(NET *net, const unsigned char *frames_host, int n, int w, int
                    const float *mean, const float *norm);
 int  ffb_collect(NET *net);
 
+/* ---- multi-GPU frontend (one box) --------------------------------------------------------- */
+
+/* The reference runs one image on one thread (ffcnn.c:476-520) and has no device notion; frames are independent, so the
+ * batched frontend is data parallel: one NET per device, each with its own host thread, stream and CUDA graph; a batch of
+ * n frames is cut into contiguous shards (device g of G gets frames [g*n/G, (g+1)*n/G)); nothing crosses devices per
+ * forward pass.  Load: the first device's NET reads the weights file (ffcnn.c:211-239), every other device receives the
+ * packed buffer NET.weight_buf (ffcnn.c:150: weight_size floats) through ONE ncclBroadcast over NVLink/NVSwitch
+ * (libnccl.so.2 is dlopen'ed -- $FFCNN_NCCL_LIB overrides -- so a single-device program never needs it) and rebuilds its
+ * kernel-side layouts.  devices == NULL / ndev <= 0: every visible device.  A device may be listed twice (two replicas
+ * sharing one GPU; the weights then travel by a device-to-device copy).  Calls are made from ONE caller thread. */
+typedef struct ffb_multi ffb_multi;
+ffb_multi *ffb_multi_create(const char *cfgfile, const char *weightsfile, int inputw, int inputh,
+                            const int *devices, int ndev, int max_batch_per_device);
+void  ffb_multi_destroy(ffb_multi *m);
+int   ffb_multi_devices(ffb_multi *m);
+NET  *ffb_multi_net(ffb_multi *m, int index);            /* the per-device NET (options, inspection) */
+long  ffb_multi_broadcast_bytes(ffb_multi *m);           /* bytes the NCCL weight broadcast moved (0 for one device) */
+/* Sharded ffb_detect_batch_u8 / ffb_submit_u8 / ffb_collect: same arguments and pipelining rules, n = frames in total. */
+int   ffb_multi_detect_u8(ffb_multi *m, const unsigned char *frames_host, int n, int w, int h, int pitch,
+                          const float *mean, const float *norm);
+int   ffb_multi_submit_u8(ffb_multi *m, const unsigned char *frames_host, int n, int w, int h, int pitch,
+                          const float *mean, const float *norm);
+int   ffb_multi_collect(ffb_multi *m);
+int   ffb_multi_boxes(ffb_multi *m, int frame, BBOX **boxes);   /* frame = index in the whole batch */
+
 /* ---- inspection / measurement ------------------------------------------------------------ */
 
 /* Copy the output of layer `layer` for frame `frame` to host as CHW fp32 (the reference layout).
