@@ -52,7 +52,7 @@ def boxes_close(got, want, px=1e-4, score=1e-6):
         dp = max(abs(float(g[k]) - float(e[k])) for k in ("x1", "y1", "x2", "y2"))
         if px <= 1.0001e-4:                              # comparisons against the named (-O2) oracle at the 320x320 geometry
             MEASURED["box_px"] = max(MEASURED["box_px"], dp); MEASURED["score"] = max(MEASURED["score"], ds); MEASURED["boxes"] += 1
-        elif px <= 2.0001e-4:
+        elif px <= 3.0001e-4:
             MEASURED["box_px_large_nets"] = max(MEASURED["box_px_large_nets"], dp)
         assert ds <= score, (g, e)
         assert dp <= px, (dp, g, e)
