@@ -32,6 +32,7 @@
 #include "pw_tc.h"
 #include "block_mma.h"
 #include "block_reg.h"
+#include "block_tc.h"
 #include "conv_tc.h"
 
 using namespace ffb;
@@ -380,11 +381,11 @@ struct ffb_engine {
     int fuse_shortcut = 1;
     /* fused inverted-residual blocks (block_mma.cu): expand conv `first`, depthwise first+1, projection first+2 and, when
        sc >= 0, the shortcut layer sc run as ONE kernel launched in the slot of layer `first` */
-    struct Block { int first, sc; BlkPlan *plan; RegPlan *reg; };      /* exactly one of plan (block_mma.cu) / reg (block_reg.cu) is set */
+    struct Block { int first, sc; BlkPlan *plan; RegPlan *reg; Blk2Plan *tc2; };      /* exactly one of plan (block_mma.cu) / reg (block_reg.cu) / tc2 (block_tc.cu) is set */
     std::vector<Block> blocks;
     std::vector<int> blk_at;                /* per layer: index into blocks if the layer is a block's first conv, else -1 */
     std::vector<char> in_block;             /* per layer: computed inside a block (its own launch slot is empty) */
-    int fuse_block = 1;
+    int fuse_block = 1, blk2 = 0;           /* blk2: use the all-tcgen05 block kernel (block_tc.cu) where it has a plan */
     /* tail fusions: the SPP block (three max pools of one tensor + their route) as one kernel launched in the route's
        slot, and upsample layers that write straight into the concat tensor of the route that reads them */
     struct Spp { int route, x, r[3], off[3], offx; };
@@ -453,7 +454,7 @@ void ffb_engine_destroy(ffb_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     engine_free_plan(e);
     for (ffb_conv *c : e->convs) conv_release(c);
-    for (ffb_engine::Block &b : e->blocks) { blk_plan_destroy(b.plan); reg_plan_destroy(b.reg); }
+    for (ffb_engine::Block &b : e->blocks) { blk_plan_destroy(b.plan); reg_plan_destroy(b.reg); blk2_plan_destroy(b.tc2); }
     cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_flush);
     cudaFreeHost(e->h_stage);
     for (ffb_engine::DetSet &d : e->det) { cudaFree(d.d_cand); cudaFree(d.d_count); cudaFreeHost(d.h_cand); cudaFreeHost(d.h_count); if (d.done) cudaEventDestroy(d.done); }
@@ -491,7 +492,7 @@ static std::vector<int> count_readers(const NET *net)
 static int engine_find_blocks(ffb_engine *e)
 {
     NET *net = &e->net->pub; const int L = net->layer_num;
-    for (ffb_engine::Block &b : e->blocks) { blk_plan_destroy(b.plan); reg_plan_destroy(b.reg); }
+    for (ffb_engine::Block &b : e->blocks) { blk_plan_destroy(b.plan); reg_plan_destroy(b.reg); blk2_plan_destroy(b.tc2); }
     e->blocks.clear(); e->blk_at.assign(L, -1); e->in_block.assign(L, 0);
     if (!e->fuse_block) return 0;
     const std::vector<int> readers = count_readers(net);
@@ -513,11 +514,16 @@ static int engine_find_blocks(ffb_engine *e)
            the shared-memory / tensor-core one (block_mma.cu) for the rest.  fuse_block 1 (default) uses the latter only for
            the block shapes where it beats the three separate layers on a B200 (measured, profiles/r1k_block_fusion.txt: it
            loses on the stride-2 136-channel block); 2: every supported block; 3: block_mma only */
-        BlkPlan *plan = nullptr; RegPlan *reg = nullptr;
+        BlkPlan *plan = nullptr; RegPlan *reg = nullptr; Blk2Plan *tc2 = nullptr;
         if (e->fuse_block != 3)
             reg = reg_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res,
                                   a->filter, d->filter, p->filter);
-        if (!reg) {
+        if (!reg && e->blk2) {
+            const bool wanted2 = e->blk2 >= 2 || e->fuse_block >= 2 || a->fn >= 32;
+            if (wanted2) tc2 = blk2_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res);
+            if (tc2 && blk2_prepare(tc2, e->convs[i]->d_packed, e->convs[i + 1]->d_packed, e->convs[i + 2]->d_packed, e->stream) != 0) { blk2_plan_destroy(tc2); return -1; }
+        }
+        if (!reg && !tc2) {
             const bool wanted = e->fuse_block >= 2 || a->fn == 32 || a->fn == 48 || a->fn == 96 || (a->fn == 136 && d->stride == 1) || a->fn == 224;
             if (!wanted) continue;
             plan = blk_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res);
@@ -526,8 +532,8 @@ static int engine_find_blocks(ffb_engine *e)
         }
         e->blk_at[i] = (int)e->blocks.size(); e->in_block[i + 1] = e->in_block[i + 2] = 1;
         if (sc >= 0) e->in_block[sc] = 1;
-        e->blocks.push_back({ i, sc, plan, reg });
-        if (getenv("FFCNN_BLK_VERBOSE")) fprintf(stderr, "ffcnn_b200: block L%d-L%d: %s\n", i, sc >= 0 ? sc : i + 2, plan ? blk_describe(plan) : reg_describe(reg));
+        e->blocks.push_back({ i, sc, plan, reg, tc2 });
+        if (getenv("FFCNN_BLK_VERBOSE")) fprintf(stderr, "ffcnn_b200: block L%d-L%d: %s\n", i, sc >= 0 ? sc : i + 2, tc2 ? blk2_describe(tc2) : plan ? blk_describe(plan) : reg_describe(reg));
         i += 2;
     }
     return 0;
@@ -758,6 +764,7 @@ static int engine_attach_body(ffb_engine *e, NET *net)
     if ((env = getenv("FFCNN_DW_MODE")))   e->dw_mode = atoi(env);
     if ((env = getenv("FFCNN_PDL")))       sm100::g_ffb_pdl = atoi(env);
     if ((env = getenv("FFCNN_FUSE_BLOCK"))) e->fuse_block = atoi(env);
+    if ((env = getenv("FFCNN_BLK2")))      e->blk2 = atoi(env);
     CK(cudaMalloc(&e->d_packed, std::max(1, net->weight_size) * sizeof(float)));
     CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     if (engine_prepare_weights(e) != 0) return -1;
@@ -819,6 +826,7 @@ int ffb_set_option(NET *net, const char *name, int value)
     else if (!strcmp(name, "fuse_shortcut")) { if (e->fuse_shortcut != value) e->plan_dirty = true; e->fuse_shortcut = value; }
     else if (!strcmp(name, "keep_all"))  { if (e->keep_all != value) e->plan_dirty = true; e->keep_all = value; }
     else if (!strcmp(name, "fuse_block")) { reweight = e->fuse_block != value; e->fuse_block = value; }
+    else if (!strcmp(name, "blk2"))      { reweight = e->blk2 != value; e->blk2 = value; }
     else if (!strcmp(name, "fuse_tail")) { if (e->fuse_tail != value) e->plan_dirty = true; e->fuse_tail = value; }
     else if (!strcmp(name, "cand_cap")) { e->cand_cap = value; for (ffb_engine::DetSet &d : e->det) d.want = 0; }   /* test hook: initial candidate capacity */
     else { ffb_set_error("unknown option '%s'", name); return -1; }
@@ -844,6 +852,7 @@ int ffb_get_option(NET *net, const char *name)
     if (!strcmp(name, "fuse_shortcut")) return e->fuse_shortcut;
     if (!strcmp(name, "keep_all")) return e->keep_all;
     if (!strcmp(name, "fuse_block")) return e->fuse_block;
+    if (!strcmp(name, "blk2")) return e->blk2;
     if (!strcmp(name, "fuse_tail")) return e->fuse_tail;
     if (!strcmp(name, "blocks")) return (int)e->blocks.size();
     if (!strcmp(name, "max_batch")) return e->max_batch;
@@ -951,8 +960,8 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         if (e->in_block[i]) return 0;                          /* computed by the block kernel launched in an earlier slot */
         if (e->blk_at[i] >= 0) {
             const ffb_engine::Block &b = e->blocks[e->blk_at[i]]; const Tens &y = e->outs[i + 2];
-            if ((b.plan ? blk_run(b.plan, in.p, in.ld, y.p, y.ld, n, st) : reg_run(b.reg, in.p, in.ld, y.p, y.ld, n, st)) != 0) return -1;
-            *launches += b.plan ? 1 : reg_launches(b.reg);
+            if ((b.tc2 ? blk2_run(b.tc2, in.p, in.ld, y.p, y.ld, n, st) : b.plan ? blk_run(b.plan, in.p, in.ld, y.p, y.ld, n, st) : reg_run(b.reg, in.p, in.ld, y.p, y.ld, n, st)) != 0) return -1;
+            *launches += b.reg ? reg_launches(b.reg) : 1;
             return 0;
         }
     }
@@ -1340,7 +1349,7 @@ int ffb_layer_cost(NET *net, int i, double *bytes, double *flops, char *kname, i
             g_cost_recursing = true;
             for (int k = i + 1; k <= (b.sc >= 0 ? b.sc : i + 2); k++) { double b2 = 0, f2 = 0; ffb_layer_cost(net, k, &b2, &f2, NULL, 0); by += b2; fl += f2; }
             g_cost_recursing = false;
-            nm = b.plan ? (blk_uses_tcgen05(b.plan) ? "block_mma_tcgen05_3xtf32" : "block_mma_3xtf32") : "block_reg_fp32";
+            nm = b.tc2 ? "block_tcgen05_3xtf32" : b.plan ? (blk_uses_tcgen05(b.plan) ? "block_mma_tcgen05_3xtf32" : "block_mma_3xtf32") : "block_reg_fp32";
         }
     }
     if (bytes) *bytes = by;
