@@ -292,6 +292,7 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
     if ((kind == CK_DW_S1_3 || kind == CK_DW_S1_5 || kind == CK_DW3_S2) && (ldi != op->ic || ldo != op->fn || coff != 0)) kind = CK_GENERIC;
     if (kind == CK_STEM && (ldi != 4 || ldo != 8 || coff != 0)) kind = CK_GENERIC;
     if (kind == CK_IGEMM_TC && !ig_supports(op->ig, ldi, ldo, coff, ih, iw)) kind = CK_GENERIC;
+    if (kind == CK_PW_TC && !pw_tc_supports(op->tc, ldo, coff)) kind = op->smem <= 227 * 1024 && op->NT <= 256 && op->TY >= 1 ? CK_PW_FFMA : CK_GENERIC;
     if (res && kind != CK_PW_TC && kind != CK_PW_FFMA) { ffb_set_error("fused shortcut needs a pointwise conv"); return -1; }
     switch (kind) {
     case CK_IGEMM_TC:

@@ -55,6 +55,7 @@ struct TcArgs {
     uint32_t tmem_cols;
     const float *scale, *bias;          /* [nsl*NS], zero padded */
     const float *res; int ldr, act2, N; /* optional fused shortcut (ffcnn.c:418-423): out = act2(conv + res[m][n]) */
+    float *out; int ldo, coff, direct;  /* direct != 0: the epilogue stores straight from registers (no staging tiles: their 32 KB go to the A ring) */
     long long *trace;                   /* developer timeline (tools/tc_trace.py): CTA 0 stamps [role][iteration][event] */
 };
 
@@ -96,7 +97,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     uint8_t *sBl = sBh + (size_t)Kc * b_sub;
     uint8_t *sA  = sBl + (a.split ? (size_t)Kc * b_sub : 0);
     uint8_t *sO  = sA + (size_t)S * A_SUB;
-    float   *sSc = reinterpret_cast<float *>(sO + (size_t)a.G * 8 * 4096);
+    float   *sSc = reinterpret_cast<float *>(sO + (a.direct ? 0 : (size_t)a.G * 8 * 4096));
     float   *sBi = sSc + NS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBi + NS);
     uint64_t *full = bars, *empty = bars + S, *conv = bars + 2 * S, *tfull = bars + 3 * S, *tempty = tfull + 2, *bfull = tempty + 2;
@@ -209,8 +210,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 uint32_t r[2][16];
                 tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32, r[0]);
                 if (ncols > 16) tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32 + 16, r[1]);
-                if (lane == 0) tma_store_wait_read<0>();     /* the previous box of this warp has left shared memory */
-                __syncwarp();
+                if (!a.direct) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }    /* the previous box of this warp has left shared memory */
                 tmem_ld_wait();
 #pragma unroll
                 for (int hf = 0; hf < 2; hf++) {
@@ -236,14 +236,21 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                                 v.x = act_apply(v.x + rv[c].x, slope2); v.y = act_apply(v.y + rv[c].y, slope2);
                                 v.z = act_apply(v.z + rv[c].z, slope2); v.w = act_apply(v.w + rv[c].w, slope2);
                             }
-                            const int chunk = hf * 4 + c;
-                            sts128(stage_addr + lane * 128 + ((chunk ^ (lane & 7)) << 4), v);
+                            if (a.direct) {                  /* 64 contiguous bytes per thread and half: whole sectors, merged in L2 */
+                                const int n0 = slice * NS + cl + 4 * c;
+                                if (m < a.M && n0 < a.N) *reinterpret_cast<float4 *>(a.out + m * a.ldo + a.coff + n0) = v;
+                            } else {
+                                const int chunk = hf * 4 + c;
+                                sts128(stage_addr + lane * 128 + ((chunk ^ (lane & 7)) << 4), v);
+                            }
                         }
                     }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) { tma_store_2d(&tmD, stage, slice * NS + j * 32, t * BM + q * 32); tma_store_commit(); }
+                if (!a.direct) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmD, stage, slice * NS + j * 32, t * BM + q * 32); tma_store_commit(); }
+                }
             }
             tc_fence_before_sync();
             mbar_arrive(tempty + ab);                        /* accumulator drained (all 256 threads arrive) */
@@ -424,19 +431,50 @@ extern "C" int ffb_measure_tf32_peak(double *tflops)
     return 0;
 }
 
+/* general form: optional element strides (a stride-S conv reads every S-th pixel: box = S x the elements wanted), swizzle */
+int ffb_make_tensor_map_ex(CUtensorMap *m, const void *base, int rank, const unsigned long long *dims,
+                           const unsigned long long *strides_bytes, const unsigned *box, const unsigned *elem_strides, int swizzle128)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { ffb_set_error("cuTensorMapEncodeTiled unavailable"); return -1; }
+    cuuint64_t gdim[5], gstr[4]; cuuint32_t bx[5], estr[5] = { 1, 1, 1, 1, 1 };
+    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; if (elem_strides) estr[i] = elem_strides[i]; if (i + 1 < rank) gstr[i] = strides_bytes[i]; }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ffb_set_error("cuTensorMapEncodeTiled failed (%d), rank %d, box %u x %u, stride %u", (int)r, rank, box[0], rank > 1 ? box[1] : 0, estr[1]); return -1; }
+    return 0;
+}
+
 static long long *g_tc_trace = nullptr;
 extern "C" void ffb_tc_set_trace(long long *dev_buf) { g_tc_trace = dev_buf; }   /* developer hook, effective only in -DFFB_TC_TRACE builds */
 
 struct PwTcPlan {
     int K, N, act, mode, split;
-    int Kc, ksteps_total, NS, nsl, S, OB, NP, Kld;
+    int Kc, ksteps_total, NS, nsl, S, OB, NP, Kld, direct;
     uint32_t tmem_cols; size_t smem;
     float *d_bhi, *d_blo, *d_scb;
     CUtensorMap tmBh, tmBl;
     int num_sms;
 };
 
+static bool plan_tiling_with(PwTcPlan *p, int direct);
+
+/* The epilogue's staging tiles (TMA store, 32 KB per warp group) compete with the A ring for shared memory.  When the ring
+ * cannot hold two tiles' worth of K chunks next to the resident weights (K >= 96 with N >= 96: config 4 of BASELINE.json,
+ * the 120 -> 255 heads) the loads in flight per SM -- not the tensor pipe -- bound the kernel, and storing straight from
+ * registers buys 2 more 16 KB slots.  FFCNN_PW_DIRECT = 1 / 0 forces / forbids it. */
 static bool plan_tiling(PwTcPlan *p)
+{
+    static const int env = getenv("FFCNN_PW_DIRECT") ? atoi(getenv("FFCNN_PW_DIRECT")) : -1;
+    if (env == 1) return plan_tiling_with(p, 1);
+    if (!plan_tiling_with(p, 0)) return plan_tiling_with(p, 1);
+    if (env == 0 || p->S >= std::min(8, 2 * p->Kc)) return true;
+    PwTcPlan q = *p;
+    if (plan_tiling_with(&q, 1) && q.nsl <= p->nsl && q.S > p->S) *p = q;
+    return true;
+}
+
+static bool plan_tiling_with(PwTcPlan *p, int direct)
 {
     const int N16 = (p->N + 15) & ~15;
     const size_t limit = 227 * 1024 - 2048;          /* dynamic smem ceiling minus alignment slack */
@@ -455,10 +493,10 @@ static bool plan_tiling(PwTcPlan *p)
                        always serve the same group (S a multiple of 2 * Kc), or a group would skip mbarrier phases and its
                        parity wait would alias (found as a hang on 48 -> 224 with S = 2, Kc = 2) */
                     if (OB == 2 && S % (2 * p->Kc) != 0) continue;
-                    const size_t smem = B + (size_t)S * A_SUB + (size_t)OB * 8 * 4096 + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
+                    const size_t smem = B + (size_t)S * A_SUB + (direct ? 0 : (size_t)OB * 8 * 4096) + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
                     const int tmem = 2 * NS + (p->split ? S * 32 : 0);
                     if (smem <= limit && tmem <= 512) {
-                        p->NS = NS; p->nsl = nsl; p->S = S; p->OB = OB; p->NP = nsl * NS;
+                        p->NS = NS; p->nsl = nsl; p->S = S; p->OB = OB; p->NP = nsl * NS; p->direct = direct;
                         p->smem = smem + 1024;
                         if (p->smem < 120 * 1024) p->smem = 120 * 1024;       /* one CTA per SM: TMEM is allocated per CTA */
                         uint32_t c = 32; while ((int)c < tmem) c <<= 1;
@@ -495,6 +533,14 @@ void pw_tc_plan_destroy(PwTcPlan *p)
     delete p;
 }
 
+/* a direct-store plan writes whole groups of 4 channels: N % 4 != 0 needs the tensor's own zero pad lanes behind it */
+bool pw_tc_supports(const PwTcPlan *p, int ldo, int coff)
+{
+    if (!p || !p->direct) return true;
+    if (ldo % 4 || coff % 4) return false;
+    return p->N % 4 == 0 || (coff == 0 && ldo == ((p->N + 3) & ~3));
+}
+
 const char *pw_tc_mode_name(const PwTcPlan *p) { return p && p->mode == 3 ? "1xtf32" : "3xtf32"; }
 
 int pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStream_t st)
@@ -529,6 +575,8 @@ int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int co
     a.act = p->act; a.split = p->split; a.tiles = (int)((M + BM - 1) / BM); a.tmem_cols = p->tmem_cols;
     a.scale = p->d_scb; a.bias = p->d_scb + p->NP;
     a.res = res; a.ldr = ldr; a.act2 = act2; a.N = p->N;
+    a.out = out; a.ldo = ldo; a.coff = coff; a.direct = p->direct;
+    if (p->direct && !pw_tc_supports(p, ldo, coff)) { ffb_set_error("pw_tc: direct-store plan cannot write %d channels at offset %d of a %d-float pixel", p->N, coff, ldo); return -1; }
     a.trace = g_tc_trace;
     long want = (long)a.tiles * p->nsl;
     int grid = (int)(want < p->num_sms ? want : p->num_sms);

