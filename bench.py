@@ -369,14 +369,29 @@ def main():
     # synthetic frames: 4 distinct resident batches per rank (seeded per global frame index), rotated across steps
     NB = 4
     lo, _ = shard.shard_range(B * world, rank, world)
-    host = torch.empty((NB, B, NET_H, PITCH), dtype=torch.uint8).pin_memory()
+    if os.environ.get("BENCH_PINNED", "") == "wc":          # developer knob: write-combined pinned frames (profiles/r2h_e2e_8gpu.txt)
+        wc_ptr = fb.lib().ffb_host_alloc_pinned_wc(NB * B * NET_H * PITCH)
+        if not wc_ptr:
+            raise SystemExit("bench.py: write-combined pinned allocation failed")
+        hv = np.ctypeslib.as_array((fb.C.c_uint8 * (NB * B * NET_H * PITCH)).from_address(wc_ptr)).reshape(NB, B, NET_H, PITCH)
+
+        class _HostView:                                  # host[i].data_ptr() as the pinned torch tensor offers it
+            def __init__(self, base, stride): self.base, self.stride = base, stride
+            def __getitem__(self, i):
+                p = self.base + i * self.stride
+                return type("P", (), {"data_ptr": staticmethod(lambda p=p: p)})
+        host = _HostView(wc_ptr, B * NET_H * PITCH)
+        host_t = None
+    else:
+        host = torch.empty((NB, B, NET_H, PITCH), dtype=torch.uint8).pin_memory()
+        hv = host.numpy()
+        host_t = host
     base = synth.frames_u8(16, NET_W, NET_H, seed0=0xFFC0 + 16 * rank)
-    hv = host.numpy()
     for b in range(NB):
         for f in range(B):
             hv[b, f] = base[(b * 5 + f) % 16]
             hv[b, f, f % NET_H, :8] = (lo + f + b) & 0xFF          # every frame distinct
-    dev = host.cuda(non_blocking=False)
+    dev = (host_t if host_t is not None else torch.from_numpy(np.ascontiguousarray(hv))).cuda(non_blocking=False)
     frame_bytes = B * NET_H * PITCH
 
     def step_resident(i):

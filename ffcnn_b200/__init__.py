@@ -119,6 +119,7 @@ def lib():
         "ffb_copy_h2d": (C.c_int, [vp, vp, C.c_size_t]),
         "ffb_copy_d2h": (C.c_int, [vp, vp, C.c_size_t]),
         "ffb_host_alloc_pinned": (vp, [C.c_size_t]),
+        "ffb_host_alloc_pinned_wc": (vp, [C.c_size_t]),
         "ffb_host_free_pinned": (None, [vp]),
         "ffb_chw_to_nhwc": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "ffb_nhwc_to_chw": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
@@ -145,7 +146,7 @@ EXPORTS = ["ffb_last_error", "ffb_device_count", "ffb_net_parse", "ffb_net_attac
            "ffb_multi_create", "ffb_multi_destroy", "ffb_multi_devices", "ffb_multi_net", "ffb_multi_broadcast_bytes",
            "ffb_multi_detect_u8", "ffb_multi_submit_u8", "ffb_multi_collect", "ffb_multi_boxes",
            "ffb_conv_create", "ffb_conv_destroy", "ffb_conv_run", "ffb_conv_kernel_name", "ffb_dev_alloc", "ffb_dev_free",
-           "ffb_copy_h2d", "ffb_copy_d2h", "ffb_host_alloc_pinned", "ffb_host_free_pinned", "ffb_chw_to_nhwc",
+           "ffb_copy_h2d", "ffb_copy_d2h", "ffb_host_alloc_pinned", "ffb_host_alloc_pinned_wc", "ffb_host_free_pinned", "ffb_chw_to_nhwc",
            "ffb_nhwc_to_chw", "net_load", "net_free", "net_input", "net_forward", "net_dump", "net_profile", "groupconv",
            "bmp_load", "bmp_save", "bmp_free", "bmp_setpixel", "bmp_getpixel", "bmp_rectangle"]
 

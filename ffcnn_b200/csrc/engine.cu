@@ -416,6 +416,7 @@ struct ffb_engine {
     std::vector<std::vector<BBOX>> boxes, raw;
     int s1 = 1, s2 = 1; size_t d2h_bytes = 0;
     /* submit/collect pipeline: two device frame slots filled on a copy stream while the previous batch computes */
+    cudaStream_t copy_stream2 = nullptr; cudaEvent_t ev_join = nullptr; int h2d_chunks = 1;    /* FFCNN_H2D_CHUNKS: split each batch copy over two copy streams */
     cudaStream_t copy_stream = nullptr; unsigned char *d_slot[2] = { nullptr, nullptr }; size_t slot_cap[2] = { 0, 0 };
     cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr };
     long submitted = 0, collected = 0;
@@ -462,6 +463,8 @@ void ffb_engine_destroy(ffb_engine *e)
     if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
     for (int i = 0; i < 2; i++) { cudaFree(e->d_slot[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]); }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->copy_stream2) cudaStreamDestroy(e->copy_stream2);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -1223,6 +1226,9 @@ int ffb_submit_u8(NET *net, const unsigned char *frames_host, int n, int w, int 
     if (!e->copy_stream) {
         CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming)); }
+        const char *ch = getenv("FFCNN_H2D_CHUNKS");
+        e->h2d_chunks = ch ? std::max(1, std::min(64, atoi(ch))) : 1;
+        if (e->h2d_chunks > 1) { CK(cudaStreamCreateWithFlags(&e->copy_stream2, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming)); }
     }
     const int slot = (int)(e->submitted & 1);
     const size_t bytes = (size_t)n * h * pitch;
@@ -1232,7 +1238,18 @@ int ffb_submit_u8(NET *net, const unsigned char *frames_host, int n, int w, int 
         CK(cudaMalloc(&e->d_slot[slot], bytes)); e->slot_cap[slot] = bytes;
     }
     if (e->submitted >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->ev_free[slot], 0));     /* the batch that used this slot has consumed it */
-    CK(cudaMemcpyAsync(e->d_slot[slot], frames_host, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    if (e->h2d_chunks > 1) {
+        /* several smaller copies alternating over two streams keep two DMA transfers in flight (developer knob; measured in
+           profiles/r2h_e2e_8gpu.txt) */
+        if (e->submitted >= 2) CK(cudaStreamWaitEvent(e->copy_stream2, e->ev_free[slot], 0));
+        const size_t chunk = ((bytes + e->h2d_chunks - 1) / e->h2d_chunks + 4095) & ~(size_t)4095;
+        int k = 0;
+        for (size_t off = 0; off < bytes; off += chunk, k++)
+            CK(cudaMemcpyAsync(e->d_slot[slot] + off, frames_host + off, std::min(chunk, bytes - off), cudaMemcpyHostToDevice, (k & 1) ? e->copy_stream2 : e->copy_stream));
+        CK(cudaEventRecord(e->ev_join, e->copy_stream2));
+        CK(cudaStreamWaitEvent(e->copy_stream, e->ev_join, 0));
+    } else
+        CK(cudaMemcpyAsync(e->d_slot[slot], frames_host, bytes, cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
     ffb_engine::SlotMeta &m = e->slot_meta[slot];
     m.n = n; m.w = w; m.h = h; m.pitch = pitch; m.has_mean = mean != nullptr; m.has_norm = norm != nullptr;
@@ -1435,6 +1452,7 @@ void *ffb_dev_alloc(size_t bytes) { void *p = NULL; if (cudaMalloc(&p, bytes) !=
 void  ffb_dev_free(void *p) { cudaFree(p); }
 int   ffb_copy_h2d(void *d, const void *s, size_t b) { CK(cudaMemcpy(d, s, b, cudaMemcpyHostToDevice)); return 0; }
 int   ffb_copy_d2h(void *d, const void *s, size_t b) { CK(cudaMemcpy(d, s, b, cudaMemcpyDeviceToHost)); return 0; }
+void *ffb_host_alloc_pinned_wc(size_t bytes) { void *p = NULL; if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) { ffb_set_error("cudaHostAlloc(write-combined) failed: %s", cudaGetErrorString(cudaGetLastError())); return NULL; } return p; }
 void *ffb_host_alloc_pinned(size_t bytes) { void *p = NULL; if (cudaMallocHost(&p, bytes) != cudaSuccess) { ffb_set_error("cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError())); return NULL; } return p; }
 void  ffb_host_free_pinned(void *p) { cudaFreeHost(p); }
 

@@ -168,6 +168,7 @@ void  ffb_dev_free(void *p);
 int   ffb_copy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int   ffb_copy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 void *ffb_host_alloc_pinned(size_t bytes);
+void *ffb_host_alloc_pinned_wc(size_t bytes);            /* write-combined pinned memory (host writes only; free with ffb_host_free_pinned) */
 void  ffb_host_free_pinned(void *p);
 /* layout helpers on device: [n][c][h][w] <-> [n][h][w][c] */
 int   ffb_chw_to_nhwc(const float *src_dev, float *dst_dev, int n, int c, int h, int w, void *cuda_stream);
