@@ -55,6 +55,7 @@ struct TcArgs {
     uint32_t tmem_cols;
     const float *scale, *bias;          /* [nsl*NS], zero padded */
     const float *res; int ldr, act2, N; /* optional fused shortcut (ffcnn.c:418-423): out = act2(conv + res[m][n]) */
+    int allwait;                        /* developer A/B: every split thread waits on every chunk's barrier */
     float *out; int ldo, coff, direct;  /* direct != 0: the epilogue stores straight from registers (no staging tiles: their 32 KB go to the A ring) */
     long long *trace;                   /* developer timeline (tools/tc_trace.py): CTA 0 stamps [role][iteration][event] */
 };
@@ -83,11 +84,12 @@ __device__ __forceinline__ float tf32_round(float x)
 
 /* activation as a negative-side slope: linear 1, relu 0, leaky 0.1 (utils.h:15-23) -- branch free in the epilogue */
 __device__ __forceinline__ float act_slope(int act) { return act == 2 ? 0.1f : act == 1 ? 0.f : 1.f; }
-__device__ __forceinline__ float act_apply(float v, float slope) { return v > 0.f ? v : v * slope; }
+__device__ __forceinline__ float act_apply(float v, float slope) { return fmaxf(v, v * slope); }     /* slope in [0, 1]: max(v, slope * v) == (v > 0 ? v : slope * v) */
 
-__global__ void __launch_bounds__(MAX_THREADS, 1)
-k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-        const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmD, const TcArgs a)
+/* NG = split + epilogue warp groups (1 or 2): a template parameter only so that the one-group launch (320 threads) may use
+   up to 200 registers -- under the two-group bound (576 threads, 112 registers) the epilogue spilled 212 bytes */
+template <int NG>
+__device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtensorMap &tmBh, const CUtensorMap &tmBl, const CUtensorMap &tmD, const TcArgs &a)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,7 +112,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmD);
         if (a.split) tma_prefetch_desc(&tmBl);
-        for (int s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(conv + s, EPI_THREADS); }
+        for (int s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(conv + s, NG == 1 ? EPI_THREADS / 2 : EPI_THREADS); }
         for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, EPI_THREADS); }
         mbar_init(bfull, 1);
         fence_barrier_init();
@@ -165,17 +167,28 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     tc_fence_after_sync();
                     const uint32_t a_base = smem_u32(sA + (size_t)s * A_SUB);
                     const int nk = min(4, a.ksteps_total - kc * 4);            /* k-steps (of 8) in this chunk */
+                    /* descriptors once per chunk; a k-step advances the start-address field (bytes >> 4) by 32 B = 2.  Building
+                       each descriptor from its address cost ~13 uniform-pipe instructions per MMA, and the single issuing thread
+                       -- ~97 cycles per MMA against 48 of tensor time at N = 96 -- paced the whole CTA (profiles/r2k_pwtc_trace.txt) */
+                    const uint64_t da = umma_desc_sw128(a_base), dbh = umma_desc_sw128(bh_base + kc * b_sub), dbl = umma_desc_sw128(bl_base + kc * b_sub);
                     if (a.split) {
                         const uint32_t alo = tmem_base + alo_col0 + s * 32;
-                        for (int kk = 0; kk < nk; kk++) {                       /* A_lo (TMEM) x W_hi */
-                            mma_tf32_ts(d, alo + kk * 8, umma_desc_sw128(bh_base + kc * b_sub + kk * 32), idesc, accum); accum = 1;
+                        if (nk == 4) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) mma_tf32_ts(d, alo + kk * 8, dbh + 2 * kk, idesc, kk ? 1u : accum);      /* A_lo (TMEM) x W_hi */
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) mma_tf32_ss(d, da + 2 * kk, dbl + 2 * kk, idesc, 1);                    /* A_hi x W_lo */
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) mma_tf32_ss(d, da + 2 * kk, dbh + 2 * kk, idesc, 1);                    /* A_hi x W_hi */
+                        } else {
+                            for (int kk = 0; kk < nk; kk++) mma_tf32_ts(d, alo + kk * 8, dbh + 2 * kk, idesc, kk ? 1u : accum);
+                            for (int kk = 0; kk < nk; kk++) mma_tf32_ss(d, da + 2 * kk, dbl + 2 * kk, idesc, 1);
+                            for (int kk = 0; kk < nk; kk++) mma_tf32_ss(d, da + 2 * kk, dbh + 2 * kk, idesc, 1);
                         }
-                        for (int kk = 0; kk < nk; kk++)                         /* A_hi x W_lo */
-                            mma_tf32_ss(d, umma_desc_sw128(a_base + kk * 32), umma_desc_sw128(bl_base + kc * b_sub + kk * 32), idesc, 1);
+                    } else {
+                        for (int kk = 0; kk < nk; kk++) mma_tf32_ss(d, da + 2 * kk, dbh + 2 * kk, idesc, kk ? 1u : accum);         /* raw x raw in 1xTF32 mode */
                     }
-                    for (int kk = 0; kk < nk; kk++) {                           /* A_hi x W_hi (or raw x raw in 1xTF32 mode) */
-                        mma_tf32_ss(d, umma_desc_sw128(a_base + kk * 32), umma_desc_sw128(bh_base + kc * b_sub + kk * 32), idesc, accum); accum = 1;
-                    }
+                    accum = 1;
                     tc_commit(empty + s);        /* ring slot (and its A_lo columns) reusable once these MMAs retire */
                 }
                 tc_commit(tfull + ab);           /* accumulator ready for the epilogue */
@@ -211,7 +224,9 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32, r[0]);
                 if (ncols > 16) tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32 + 16, r[1]);
                 if (!a.direct) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }    /* the previous box of this warp has left shared memory */
+                if (et == 0) TRACE(4, it, j == half ? 0 : 2);
                 tmem_ld_wait();
+                if (et == 0) TRACE(4, it, j == half ? 1 : 3);
 #pragma unroll
                 for (int hf = 0; hf < 2; hf++) {
                     const int cl = j * 32 + hf * 16;
@@ -224,9 +239,18 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                                 rv[c] = n0 < a.N ? __ldg(reinterpret_cast<const float4 *>(a.res + m * a.ldr + n0)) : make_float4(0.f, 0.f, 0.f, 0.f);
                             }
                         }
+                        /* scale / bias of the 16 columns first, as eight independent read-only loads: the shared-memory accessors are
+                           volatile asm (ordered), and with one load pair per group of 4 columns the whole epilogue ran as a chain of
+                           exposed latencies -- 2.5 k cycles per 32 x 32 chunk (tools/tc_trace.py, profiles/r2k_pwtc_trace.txt) */
+                        float4 scv[4], biv[4];
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
-                            const float4 sc = lds128(sc_addr + (cl + 4 * c) * 4), bi = lds128(bi_addr + (cl + 4 * c) * 4);
+                            scv[c] = __ldg(reinterpret_cast<const float4 *>(a.scale + slice * NS + cl + 4 * c));
+                            biv[c] = __ldg(reinterpret_cast<const float4 *>(a.bias + slice * NS + cl + 4 * c));
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const float4 sc = scv[c], bi = biv[c];
                             float4 v;
                             v.x = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 0]), sc.x, bi.x), slope1);
                             v.y = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 1]), sc.y, bi.y), slope1);
@@ -252,6 +276,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     if (lane == 0) { tma_store_2d(&tmD, stage, slice * NS + j * 32, t * BM + q * 32); tma_store_commit(); }
                 }
             }
+            if (et == 0) TRACE(5, it + 2, 3);
             tc_fence_before_sync();
             mbar_arrive(tempty + ab);                        /* accumulator drained (all 256 threads arrive) */
             if (et == 0) TRACE(3, it, 2);
@@ -265,23 +290,32 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     const uint32_t cq = (uint32_t)it * Kc + kc;
                     const int s = cq % S; const uint32_t ph = (cq / S) & 1;
                     if (et == 0 && kc == 0) TRACE(2, it, 0);
-                    mbar_wait(full + s, ph);
+                    /* the K chunks of a tile alternate between the two warp quartets of the group (thread = tile row, all four
+                       8-channel units of the chunk): a chunk's split is one latency chain -- loads, stores, proxy fence,
+                       tcgen05.wait::st, arrive: ~1 k cycles (profiles/r2k_pwtc_trace.txt) -- so two chunks are kept in flight */
+                    /* One group (NG == 1, K > 96): the K chunks of a tile alternate between the two warp quartets (thread = tile row,
+                       all four 8-channel units): a chunk's split is one latency chain -- loads, stores, proxy fence, tcgen05.wait::st,
+                       arrive: ~1 k cycles (profiles/r2k_pwtc_trace.txt) -- so two chunks are kept in flight.
+                       Two groups (96 registers): both quartets share every chunk, two units per thread. */
+                    constexpr int NU = NG == 1 ? 4 : 2;
+                    const bool mine = NG != 1 || (kc & 1) == half;
+                    if (mine || a.allwait) mbar_wait(full + s, ph);
+                    if (!mine) continue;
                     if (et == 0 && kc == 0) TRACE(2, it, 1);
                     const uint32_t arow = smem_u32(sA + (size_t)s * A_SUB + row * 128);
                     const uint32_t alo = tmem_base + lane_addr + alo_col0 + s * 32;
                     const int nu = min(4, (a.K - kc * 32 + 7) / 8);             /* valid units (8 consecutive k each) in this chunk */
-                    /* this warp half's two units of the chunk (half, half + 2), all loads issued first */
-                    float4 x[2][2]; uint32_t pp[2][2];
+                    float4 x[NU][2]; uint32_t pp[NU][2];
 #pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        const int c2 = half + 2 * i;
+                    for (int i = 0; i < NU; i++) {                              /* all loads issued first */
+                        const int c2 = NG == 1 ? i : half + 2 * i;
                         pp[i][0] = arow + (((2 * c2) ^ (row & 7)) << 4);
                         pp[i][1] = arow + (((2 * c2 + 1) ^ (row & 7)) << 4);
                         if (c2 < nu) { x[i][0] = lds128(pp[i][0]); x[i][1] = lds128(pp[i][1]); }
                     }
 #pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        const int c2 = half + 2 * i;
+                    for (int i = 0; i < NU; i++) {
+                        const int c2 = NG == 1 ? i : half + 2 * i;
                         if (c2 < nu) {
                             const float4 x0 = x[i][0], x1 = x[i][1];
                             float4 h0, h1; uint32_t lo[8];
@@ -315,6 +349,17 @@ k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     if (threadIdx.x == 0) TRACE(5, 1, 2);
     if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, a.tmem_cols); }
 }
+
+template <int NG> __global__ void k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                                          const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmD, const TcArgs a);
+template <> __global__ void __launch_bounds__(64 + EPI_THREADS, 1)
+k_pw_tc<1>(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+           const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmD, const TcArgs a) { pw_tc_body<1>(tmA, tmBh, tmBl, tmD, a); }
+/* 576 threads = 18 warps, allocated as 20 (granularity 4): 96 registers is the most that launches (104 and 112 via __maxnreg__
+   compile but the launch is refused), so this variant keeps a small spill (the two-group plan only serves K <= 96 layers) */
+template <> __global__ void __launch_bounds__(64 + 2 * EPI_THREADS, 1)
+k_pw_tc<2>(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+           const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmD, const TcArgs a) { pw_tc_body<2>(tmA, tmBh, tmBl, tmD, a); }
 
 __global__ void k_split_weights(const float *__restrict__ flt, int row, int N, int K, int Kld, float *__restrict__ hi, float *__restrict__ lo)
 {
@@ -459,52 +504,60 @@ struct PwTcPlan {
 
 static bool plan_tiling_with(PwTcPlan *p, int direct);
 
-/* The epilogue's staging tiles (TMA store, 32 KB per warp group) compete with the A ring for shared memory.  When the ring
- * cannot hold two tiles' worth of K chunks next to the resident weights (K >= 96 with N >= 96: config 4 of BASELINE.json,
- * the 120 -> 255 heads) the loads in flight per SM -- not the tensor pipe -- bound the kernel, and storing straight from
- * registers buys 2 more 16 KB slots.  FFCNN_PW_DIRECT = 1 / 0 forces / forbids it. */
+/* The epilogue's staging tiles (TMA store, 32 KB per warp group) compete with the A ring for shared memory; a direct-store
+ * epilogue (registers -> global, no staging) buys 2 more 16 KB ring slots.  FFCNN_PW_DIRECT = 1 forces it. */
 static bool plan_tiling(PwTcPlan *p)
 {
     static const int env = getenv("FFCNN_PW_DIRECT") ? atoi(getenv("FFCNN_PW_DIRECT")) : -1;
     if (env == 1) return plan_tiling_with(p, 1);
-    if (!plan_tiling_with(p, 0)) return plan_tiling_with(p, 1);
-    if (env == 0 || p->S >= std::min(8, 2 * p->Kc)) return true;
-    PwTcPlan q = *p;
-    if (plan_tiling_with(&q, 1) && q.nsl <= p->nsl && q.S > p->S) *p = q;
-    return true;
+    /* measured (profiles/r2g_pw_direct.txt): the direct-store epilogue is 10-25 % SLOWER on every shape despite the deeper
+       ring -- the ring depth was not the limiter (the epilogue's latency chain was, profiles/r2k_pwtc_trace.txt) -- so it is
+       only a fallback for shapes whose staged plan does not fit */
+    return plan_tiling_with(p, 0) || plan_tiling_with(p, 1);
 }
 
 static bool plan_tiling_with(PwTcPlan *p, int direct)
 {
     const int N16 = (p->N + 15) & ~15;
     const size_t limit = 227 * 1024 - 2048;          /* dynamic smem ceiling minus alignment slack */
-    /* fewest N slices first (every slice re-reads and re-splits the activation tile), then as many 16 KB ring slots as fit
-       (at least 2 -- one K chunk in flight while another is being consumed -- and no more than 2 tiles' worth or 8) */
-    for (int minS = 2; minS >= 1; minS--)
-        for (int nsl = 1; nsl <= 8; nsl++) {
-            int NS = (N16 + nsl - 1) / nsl;
-            NS = nsl > 1 ? (NS + 31) & ~31 : (NS + 15) & ~15;
-            if (NS > 256) continue;
-            const size_t B = (size_t)(p->split ? 2 : 1) * p->Kc * NS * 128;
-            const int maxS = std::min(8, std::max(2, 2 * p->Kc));
-            for (int S = maxS; S >= minS; S--)
-                for (int OB = (p->Kc <= 3 ? MAX_GROUPS : 1); OB >= 1; OB--) {   /* OB = warp groups (a second one pays off when tiles are small); staging = 8 warps x 4 KB each */
-                    /* two groups take alternate tiles and each waits only on its own tiles' ring slots: a slot must then
-                       always serve the same group (S a multiple of 2 * Kc), or a group would skip mbarrier phases and its
-                       parity wait would alias (found as a hang on 48 -> 224 with S = 2, Kc = 2) */
-                    if (OB == 2 && S % (2 * p->Kc) != 0) continue;
-                    const size_t smem = B + (size_t)S * A_SUB + (direct ? 0 : (size_t)OB * 8 * 4096) + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
-                    const int tmem = 2 * NS + (p->split ? S * 32 : 0);
-                    if (smem <= limit && tmem <= 512) {
-                        p->NS = NS; p->nsl = nsl; p->S = S; p->OB = OB; p->NP = nsl * NS; p->direct = direct;
-                        p->smem = smem + 1024;
-                        if (p->smem < 120 * 1024) p->smem = 120 * 1024;       /* one CTA per SM: TMEM is allocated per CTA */
+    /* Few N slices (every slice re-reads and re-splits the activation tile) against a deep A ring (the chain
+       TMA -> split -> MMA -> commit -> refill has ~3 k cycles of latency per slot): take the first slice count whose resident
+       weights leave `want` 16 KB slots -- half a tile's K chunks, at least 2 -- else the deepest ring any slice count allows.
+       Measured (profiles/r2l_pw_tc.txt): 192 -> 192 (6 chunks) runs 0.87 ms with 3 slices / 5 slots against 1.00 ms with 2 slices /
+       2 slots; 120 -> 255 (4 chunks) 0.057 ms with 2 slices / 3 slots against 0.067 ms with 3 slices / 6 slots. */
+    static const int env_nsl = getenv("FFCNN_PW_NSL") ? atoi(getenv("FFCNN_PW_NSL")) : 0;       /* developer override: minimum number of N slices */
+    const int maxS = std::min(8, std::max(2, 2 * p->Kc)), want = std::min(maxS, std::max(2, (p->Kc + 1) / 2));
+    bool have = false; PwTcPlan best = *p;
+    for (int nsl = std::max(1, env_nsl); nsl <= 8; nsl++) {
+        int NS = (N16 + nsl - 1) / nsl;
+        NS = nsl > 1 ? (NS + 31) & ~31 : (NS + 15) & ~15;
+        if (NS > 256) continue;
+        const size_t B = (size_t)(p->split ? 2 : 1) * p->Kc * NS * 128;
+        bool found = false;
+        for (int S = maxS; S >= 1 && !found; S--)
+            for (int OB = (p->Kc <= 3 ? MAX_GROUPS : 1); OB >= 1 && !found; OB--) {   /* OB = warp groups (a second one pays off when tiles are small); staging = 8 warps x 4 KB each */
+                /* two groups take alternate tiles and each waits only on its own tiles' ring slots: a slot must then
+                   always serve the same group (S a multiple of 2 * Kc), or a group would skip mbarrier phases and its
+                   parity wait would alias (found as a hang on 48 -> 224 with S = 2, Kc = 2) */
+                if (OB == 2 && S % (2 * p->Kc) != 0) continue;
+                const size_t smem = B + (size_t)S * A_SUB + (direct ? 0 : (size_t)OB * 8 * 4096) + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
+                const int tmem = 2 * NS + (p->split ? S * 32 : 0);
+                if (smem <= limit && tmem <= 512) {
+                    found = true;
+                    if (!have || S > best.S) {
+                        best = *p;
+                        best.NS = NS; best.nsl = nsl; best.S = S; best.OB = OB; best.NP = nsl * NS; best.direct = direct;
+                        best.smem = smem + 1024;
+                        if (best.smem < 120 * 1024) best.smem = 120 * 1024;       /* one CTA per SM: TMEM is allocated per CTA */
                         uint32_t c = 32; while ((int)c < tmem) c <<= 1;
-                        p->tmem_cols = c;
-                        return true;
+                        best.tmem_cols = c;
+                        have = true;
                     }
                 }
-        }
+            }
+        if (have && best.S >= want) break;
+    }
+    if (have) { *p = best; return true; }
     return false;
 }
 
@@ -559,7 +612,9 @@ int pw_tc_prepare(PwTcPlan *p, const float *d_packed, int row, cudaStream_t st)
         p->tmBl = p->tmBh;
     }
     static ffb_smem_cfg attr_set;
-    if (ffb_ensure_smem((const void *)k_pw_tc, 227 * 1024, &attr_set) != 0) return -1;
+    if (ffb_ensure_smem((const void *)k_pw_tc<1>, 227 * 1024, &attr_set) != 0) return -1;
+    static ffb_smem_cfg attr_set2;
+    if (ffb_ensure_smem((const void *)k_pw_tc<2>, 227 * 1024, &attr_set2) != 0) return -1;
     if (cudaGetLastError() != cudaSuccess) { ffb_set_error("pw_tc: weight preparation launch failed"); return -1; }
     return 0;
 }
@@ -576,13 +631,17 @@ int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int co
     a.scale = p->d_scb; a.bias = p->d_scb + p->NP;
     a.res = res; a.ldr = ldr; a.act2 = act2; a.N = p->N;
     a.out = out; a.ldo = ldo; a.coff = coff; a.direct = p->direct;
+    /* every split thread observes every phase of every ring slot (3 % on the 192 -> 192 microbenchmark): a quartet that only
+       waited on its own chunks could test a slot's barrier one phase early, and mbarrier parity waits alias modulo 2 */
+    { static const int aw = getenv("FFCNN_PW_ALLWAIT") ? atoi(getenv("FFCNN_PW_ALLWAIT")) : 1; a.allwait = aw; }
     if (p->direct && !pw_tc_supports(p, ldo, coff)) { ffb_set_error("pw_tc: direct-store plan cannot write %d channels at offset %d of a %d-float pixel", p->N, coff, ldo); return -1; }
     a.trace = g_tc_trace;
     long want = (long)a.tiles * p->nsl;
     int grid = (int)(want < p->num_sms ? want : p->num_sms);
     grid -= grid % p->nsl;
     if (grid < p->nsl) grid = p->nsl;
-    cudaError_t e = launch_pdl(k_pw_tc, dim3(grid), dim3(64 + p->OB * EPI_THREADS), p->smem, st, tmA, p->tmBh, p->tmBl, tmD, a);
+    cudaError_t e = p->OB == 2 ? launch_pdl(k_pw_tc<2>, dim3(grid), dim3(64 + 2 * EPI_THREADS), p->smem, st, tmA, p->tmBh, p->tmBl, tmD, a)
+                               : launch_pdl(k_pw_tc<1>, dim3(grid), dim3(64 + EPI_THREADS), p->smem, st, tmA, p->tmBh, p->tmBl, tmD, a);
     if (e != cudaSuccess) { ffb_set_error("pw_tc launch failed: %s (grid %d smem %zu)", cudaGetErrorString(e), grid, p->smem); return -1; }
     return 0;
 }

@@ -28,6 +28,6 @@ for it in list(range(0, 3)) + list(range(3, 8)):
     row = []
     for r in range(4):
         row.append(" ".join("%6d" % (v - t0) if v else "     -" for v in t[r, it, :3]))
-    inner = " ".join("%6d" % (v - t0) if v else "     -" for v in [t[5, it, 0]] + list(t[4, it, :4]))
-    print("it %2d | P %s | M %s | S %s | E %s | Einner(wait_read,ld,sts,fence,store) %s" % (it, row[0][:6], row[1], row[2], row[3], inner))
+    inner = " ".join("%6d" % (v - t0) if v else "     -" for v in list(t[4, it, :4]) + [t[5, it + 2, 3] if it + 2 < 64 else 0])
+    print("it %2d | P %s | M %s | S %s | E %s | Einner(chunk0: store-slot free, tmem loaded; chunk1: free, loaded; stores issued) %s" % (it, row[0][:6], row[1], row[2], row[3], inner))
 d = np.diff(t[3, 3:40, 2]); print("cycles per tile (epilogue-done to epilogue-done), median:", np.median(d[d > 0]))
