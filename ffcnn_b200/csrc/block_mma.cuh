@@ -202,18 +202,21 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
         constexpr uint32_t sub = 16 * GC * 128;                                 /* bytes of one [16*GC x 32] B sub-tile */
         constexpr uint32_t idesc = sm100::umma_idesc_tf32(128, 16 * GC);
         const uint32_t bh = sW_addr + wslot * (uint32_t)off.total * 4, bl = bh + KC * sub;
+        /* descriptors once per chunk: a k-step / sub-tile only moves the start-address field (bytes >> 4); building every
+           descriptor from its address cost the issuing thread ~100 cycles per MMA (profiles/r2k_pwtc_trace.txt) */
+        const uint64_t dbh = sm100::umma_desc_sw128(bh), dbl = sm100::umma_desc_sw128(bl);
         for (int mt = 0; mt < a.nmt; mt++) {
             const uint32_t d = dcol0 + (uint32_t)(mt * 2 + buf) * 16 * GC;
             const uint32_t ahi = tmem_base + (uint32_t)mt * 2 * KP, alo = ahi + KP;
 #pragma unroll
             for (int ks = 0; ks < KS1; ks++)                                    /* x_lo . W_hi */
-                sm100::mma_tf32_ts(d, alo + 8 * ks, sm100::umma_desc_sw128(bh + (ks >> 2) * sub + (ks & 3) * 32), idesc, ks > 0);
+                sm100::mma_tf32_ts(d, alo + 8 * ks, dbh + (((ks >> 2) * sub + (ks & 3) * 32) >> 4), idesc, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < KS1; ks++)                                    /* x_hi . W_lo */
-                sm100::mma_tf32_ts(d, ahi + 8 * ks, sm100::umma_desc_sw128(bl + (ks >> 2) * sub + (ks & 3) * 32), idesc, 1);
+                sm100::mma_tf32_ts(d, ahi + 8 * ks, dbl + (((ks >> 2) * sub + (ks & 3) * 32) >> 4), idesc, 1);
 #pragma unroll
             for (int ks = 0; ks < KS1; ks++)                                    /* x_hi . W_hi */
-                sm100::mma_tf32_ts(d, ahi + 8 * ks, sm100::umma_desc_sw128(bh + (ks >> 2) * sub + (ks & 3) * 32), idesc, 1);
+                sm100::mma_tf32_ts(d, ahi + 8 * ks, dbh + (((ks >> 2) * sub + (ks & 3) * 32) >> 4), idesc, 1);
         }
         sm100::tc_commit(dfull + buf);
     };

@@ -159,32 +159,34 @@ __global__ void __launch_bounds__(B2_THREADS, 2) k_block_tc(const __grid_constan
     auto issue_expand = [&](uint32_t wslot) {                               /* one thread: chunk in weight slot wslot -> D1 */
         constexpr uint32_t idesc = sm100::umma_idesc_tf32(128, B2_CH);
         const uint32_t bh = sW_addr + wslot * w_bytes, bl = bh + KC * 4096;
+        const uint64_t dbh = sm100::umma_desc_sw128(bh), dbl = sm100::umma_desc_sw128(bl);      /* k-steps only move the start-address field */
         for (int mt = 0; mt < a.nmt; mt++) {
             const uint32_t d = colD1 + (uint32_t)mt * B2_CH, ahi = colX + (uint32_t)mt * 2 * KP, alo = ahi + KP;
 #pragma unroll
             for (int ks = 0; ks < KS1; ks++)                                /* x_lo . W1_hi (small terms first) */
-                sm100::mma_tf32_ts(d, alo + 8 * ks, sm100::umma_desc_sw128(bh + (ks >> 2) * 4096 + (ks & 3) * 32), idesc, ks > 0);
+                sm100::mma_tf32_ts(d, alo + 8 * ks, dbh + (((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idesc, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < KS1; ks++)                                /* x_hi . W1_lo */
-                sm100::mma_tf32_ts(d, ahi + 8 * ks, sm100::umma_desc_sw128(bl + (ks >> 2) * 4096 + (ks & 3) * 32), idesc, 1);
+                sm100::mma_tf32_ts(d, ahi + 8 * ks, dbl + (((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idesc, 1);
 #pragma unroll
             for (int ks = 0; ks < KS1; ks++)                                /* x_hi . W1_hi */
-                sm100::mma_tf32_ts(d, ahi + 8 * ks, sm100::umma_desc_sw128(bh + (ks >> 2) * 4096 + (ks & 3) * 32), idesc, 1);
+                sm100::mma_tf32_ts(d, ahi + 8 * ks, dbh + (((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idesc, 1);
         }
         sm100::tc_commit(dfull);
     };
     auto issue_project = [&](uint32_t wslot, bool first) {                  /* one thread: D2 (+)= d . W2 of the chunk in slot wslot */
         constexpr uint32_t idesc = sm100::umma_idesc_tf32(128, N3);
         const uint32_t bh = sW_addr + wslot * w_bytes + (uint32_t)off.w2 * 4, bl = bh + N3 * 128;
+        const uint64_t dbh = sm100::umma_desc_sw128(bh), dbl = sm100::umma_desc_sw128(bl), da = sm100::umma_desc_sw128(sA2_addr);
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)                                      /* d_lo (TMEM) . W2_hi */
-            sm100::mma_tf32_ts(colD2, colA2 + 8 * kk, sm100::umma_desc_sw128(bh + kk * 32), idesc, !(first && kk == 0));
+            sm100::mma_tf32_ts(colD2, colA2 + 8 * kk, dbh + 2 * kk, idesc, !(first && kk == 0));
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)                                      /* d_hi . W2_lo */
-            sm100::mma_tf32_ss(colD2, sm100::umma_desc_sw128(sA2_addr + kk * 32), sm100::umma_desc_sw128(bl + kk * 32), idesc, 1);
+            sm100::mma_tf32_ss(colD2, da + 2 * kk, dbl + 2 * kk, idesc, 1);
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)                                      /* d_hi . W2_hi */
-            sm100::mma_tf32_ss(colD2, sm100::umma_desc_sw128(sA2_addr + kk * 32), sm100::umma_desc_sw128(bh + kk * 32), idesc, 1);
+            sm100::mma_tf32_ss(colD2, da + 2 * kk, dbh + 2 * kk, idesc, 1);
         sm100::tc_commit(pbar);
     };
     auto load_x = [&](long tile, int b) {                                   /* one thread */

@@ -122,9 +122,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t a_base = smem_u32(smem + (size_t)s * a.slot_bytes), bh = a_base + IG_A_BYTES, bl = bh + b_bytes;
                     const uint32_t alo = tmem_base + alo_col0 + s * 32;
                     const int nk = min(4, (a.ic - kc * 32 + 7) / 8);          /* k-steps (of 8 channels) that carry data in this block */
-                    for (int kk = 0; kk < nk; kk++) { mma_tf32_ts(d, alo + kk * 8, umma_desc_sw128(bh + kk * 32), idesc, accum); accum = 1; }   /* A_lo . W_hi */
-                    for (int kk = 0; kk < nk; kk++) mma_tf32_ss(d, umma_desc_sw128(a_base + kk * 32), umma_desc_sw128(bl + kk * 32), idesc, 1);   /* A_hi . W_lo */
-                    for (int kk = 0; kk < nk; kk++) mma_tf32_ss(d, umma_desc_sw128(a_base + kk * 32), umma_desc_sw128(bh + kk * 32), idesc, 1);   /* A_hi . W_hi */
+                    /* descriptors once per K block; a k-step advances the start-address field (bytes >> 4) by 32 B = 2 */
+                    const uint64_t da = umma_desc_sw128(a_base), dbh = umma_desc_sw128(bh), dbl = umma_desc_sw128(bl);
+                    if (nk == 4) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) mma_tf32_ts(d, alo + kk * 8, dbh + 2 * kk, idesc, kk ? 1u : accum);     /* A_lo . W_hi */
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) mma_tf32_ss(d, da + 2 * kk, dbl + 2 * kk, idesc, 1);                   /* A_hi . W_lo */
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) mma_tf32_ss(d, da + 2 * kk, dbh + 2 * kk, idesc, 1);                   /* A_hi . W_hi */
+                    } else {
+                        for (int kk = 0; kk < nk; kk++) mma_tf32_ts(d, alo + kk * 8, dbh + 2 * kk, idesc, kk ? 1u : accum);
+                        for (int kk = 0; kk < nk; kk++) mma_tf32_ss(d, da + 2 * kk, dbl + 2 * kk, idesc, 1);
+                        for (int kk = 0; kk < nk; kk++) mma_tf32_ss(d, da + 2 * kk, dbh + 2 * kk, idesc, 1);
+                    }
+                    accum = 1;
                     tc_commit(empty + s);
                 }
                 tc_commit(tfull + ab);

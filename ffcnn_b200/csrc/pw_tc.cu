@@ -243,14 +243,16 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
                            volatile asm (ordered), and with one load pair per group of 4 columns the whole epilogue ran as a chain of
                            exposed latencies -- 2.5 k cycles per 32 x 32 chunk (tools/tc_trace.py, profiles/r2k_pwtc_trace.txt) */
                         float4 scv[4], biv[4];
+                        if constexpr (NG == 1) {             /* (the 96-register two-group variant keeps the per-group shared-memory loads) */
 #pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            scv[c] = __ldg(reinterpret_cast<const float4 *>(a.scale + slice * NS + cl + 4 * c));
-                            biv[c] = __ldg(reinterpret_cast<const float4 *>(a.bias + slice * NS + cl + 4 * c));
+                            for (int c = 0; c < 4; c++) {
+                                scv[c] = __ldg(reinterpret_cast<const float4 *>(a.scale + slice * NS + cl + 4 * c));
+                                biv[c] = __ldg(reinterpret_cast<const float4 *>(a.bias + slice * NS + cl + 4 * c));
+                            }
                         }
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
-                            const float4 sc = scv[c], bi = biv[c];
+                            const float4 sc = NG == 1 ? scv[c] : lds128(sc_addr + (cl + 4 * c) * 4), bi = NG == 1 ? biv[c] : lds128(bi_addr + (cl + 4 * c) * 4);
                             float4 v;
                             v.x = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 0]), sc.x, bi.x), slope1);
                             v.y = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 1]), sc.y, bi.y), slope1);
