@@ -47,6 +47,7 @@ constexpr int A_SUB = BM * 128;         /* bytes of one [128 x 32 fp32] sub-tile
 constexpr int EPI_THREADS = 256;          /* one split+epilogue group = 8 warps, two threads per tile row */
 constexpr int MAX_GROUPS = 2;             /* groups take alternate tiles (group g owns accumulator buffer g) */
 constexpr int MAX_THREADS = 64 + MAX_GROUPS * EPI_THREADS;
+constexpr int SEP_EPI_THREADS = 128;      /* NG == 1: four more warps (10-13) run the epilogue, warps 2-9 only split */
 
 struct TcArgs {
     long M;
@@ -99,7 +100,7 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
     uint8_t *sBl = sBh + (size_t)Kc * b_sub;
     uint8_t *sA  = sBl + (a.split ? (size_t)Kc * b_sub : 0);
     uint8_t *sO  = sA + (size_t)S * A_SUB;
-    float   *sSc = reinterpret_cast<float *>(sO + (a.direct ? 0 : (size_t)a.G * 8 * 4096));
+    float   *sSc = reinterpret_cast<float *>(sO + (a.direct ? 0 : (size_t)(NG == 2 ? 16 : 4) * 4096));
     float   *sBi = sSc + NS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBi + NS);
     uint64_t *full = bars, *empty = bars + S, *conv = bars + 2 * S, *tfull = bars + 3 * S, *tempty = tfull + 2, *bfull = tempty + 2;
@@ -113,7 +114,7 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmD);
         if (a.split) tma_prefetch_desc(&tmBl);
         for (int s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(conv + s, NG == 1 ? EPI_THREADS / 2 : EPI_THREADS); }
-        for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, EPI_THREADS); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, NG == 1 ? SEP_EPI_THREADS : EPI_THREADS); }
         mbar_init(bfull, 1);
         fence_barrier_init();
         /* the layer's weights do not depend on the previous kernel: fetch them before the PDL wait */
@@ -197,17 +198,22 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
         }
     } else {
         /* ===================== split + epilogue warps (two threads per tile row) ===================== */
+        /* One group (NG == 1): warps 2-9 only split, warps 10-13 only run the epilogue (thread = tile row, every column chunk) --
+           on the same warps the two stages were serial, 3.7 k + 1.9 k cycles per (tile, slice) against 2.3 k of MMA time
+           (profiles/r2k_pwtc_trace.txt).  Two groups (NG == 2, K <= 96): each group of 8 warps splits its tile and then runs the
+           epilogue of its previous one. */
+        const bool epi_warp = NG == 1 && warp >= 10;
         const int q = warp & 3;                              /* TMEM lane quarter this warp may access */
-        const int grp = (warp - 2) >> 3;                     /* warp group: takes the tiles with it % G == grp */
-        const int half = ((warp - 2) >> 2) & 1;              /* which alternate unit of the row this warp handles */
+        const int grp = NG == 1 ? 0 : (warp - 2) >> 3;       /* warp group: takes the tiles with it % G == grp */
+        const int half = epi_warp ? 0 : ((warp - 2) >> 2) & 1;   /* which alternate chunk / unit this warp handles */
         const int row = q * 32 + lane;
-        const int et = threadIdx.x - 64 - grp * EPI_THREADS + (grp ? 1024 : 0);   /* 0 only for the first thread of group 0 (trace) */
+        const int et = NG == 1 ? ((threadIdx.x == 64 || threadIdx.x == 320) ? 0 : 1) : threadIdx.x - 64 - grp * EPI_THREADS + (grp ? 1024 : 0);   /* 0 for the tracing thread(s) */
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int nchunks = (NS + 31) / 32;
         const float slope1 = act_slope(a.act), slope2 = act_slope(a.act2);
         /* warp-private staging: this warp's [32 rows x 128 B] box, 1024-byte aligned, SWIZZLE_128B like the tensor map.
            No CTA-level barrier anywhere in the epilogue: a warp stages its rows, __syncwarp()s and stores its own box. */
-        uint8_t *stage = sO + (size_t)(warp - 2) * 4096;
+        uint8_t *stage = sO + (size_t)(epi_warp ? warp - 10 : warp - 2) * 4096;
         const uint32_t stage_addr = smem_u32(stage), sc_addr = smem_u32(sSc), bi_addr = smem_u32(sBi);
 
         auto epilogue = [&](int t, int it) {
@@ -218,7 +224,7 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
             mbar_wait(tfull + ab, aph);
             if (et == 0) TRACE(3, it, 1);
             tc_fence_after_sync();
-            for (int j = half; j < nchunks; j += 2) {        /* this warp's 32-column chunks of its 32 rows */
+            for (int j = half; j < nchunks; j += (NG == 1 ? 1 : 2)) {        /* this warp's 32-column chunks of its 32 rows */
                 const int ncols = min(32, NS - j * 32);
                 uint32_t r[2][16];
                 tmem_ld16(tmem_base + lane_addr + acc_col0 + ab * NS + j * 32, r[0]);
@@ -243,16 +249,14 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
                            volatile asm (ordered), and with one load pair per group of 4 columns the whole epilogue ran as a chain of
                            exposed latencies -- 2.5 k cycles per 32 x 32 chunk (tools/tc_trace.py, profiles/r2k_pwtc_trace.txt) */
                         float4 scv[4], biv[4];
-                        if constexpr (NG == 1) {             /* (the 96-register two-group variant keeps the per-group shared-memory loads) */
 #pragma unroll
-                            for (int c = 0; c < 4; c++) {
-                                scv[c] = __ldg(reinterpret_cast<const float4 *>(a.scale + slice * NS + cl + 4 * c));
-                                biv[c] = __ldg(reinterpret_cast<const float4 *>(a.bias + slice * NS + cl + 4 * c));
-                            }
+                        for (int c = 0; c < 4; c++) {
+                            scv[c] = __ldg(reinterpret_cast<const float4 *>(a.scale + slice * NS + cl + 4 * c));
+                            biv[c] = __ldg(reinterpret_cast<const float4 *>(a.bias + slice * NS + cl + 4 * c));
                         }
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
-                            const float4 sc = NG == 1 ? scv[c] : lds128(sc_addr + (cl + 4 * c) * 4), bi = NG == 1 ? biv[c] : lds128(bi_addr + (cl + 4 * c) * 4);
+                            const float4 sc = scv[c], bi = biv[c];
                             float4 v;
                             v.x = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 0]), sc.x, bi.x), slope1);
                             v.y = act_apply(fmaf(__uint_as_float(r[hf][4 * c + 1]), sc.y, bi.y), slope1);
@@ -285,6 +289,9 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
         };
 
         int it = 0, prev_t = -1, prev_it = -1;
+        if (epi_warp) {
+            for (int t = group; t < a.tiles; t += ngroups, it++) epilogue(t, it);
+        } else
         for (int t = group; t < a.tiles; t += ngroups, it++) {
             if (it % a.G != grp) continue;
             if (a.split) {
@@ -339,10 +346,11 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
                 }
                 if (et == 0) TRACE(2, it, 2);
             }
+            if (NG == 1) continue;                           /* the epilogue has its own warps */
             if (prev_t >= 0) epilogue(prev_t, prev_it);
             prev_t = t; prev_it = it;
         }
-        if (prev_t >= 0) epilogue(prev_t, prev_it);
+        if (NG != 1 && prev_t >= 0) epilogue(prev_t, prev_it);
         if (lane == 0) tma_store_wait_all<0>();
     }
 
@@ -354,7 +362,7 @@ __device__ __forceinline__ void pw_tc_body(const CUtensorMap &tmA, const CUtenso
 
 template <int NG> __global__ void k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                                           const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmD, const TcArgs a);
-template <> __global__ void __launch_bounds__(64 + EPI_THREADS, 1)
+template <> __global__ void __launch_bounds__(64 + EPI_THREADS + SEP_EPI_THREADS, 1)
 k_pw_tc<1>(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
            const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmD, const TcArgs a) { pw_tc_body<1>(tmA, tmBh, tmBl, tmD, a); }
 /* 576 threads = 18 warps, allocated as 20 (granularity 4): 96 registers is the most that launches (104 and 112 via __maxnreg__
@@ -542,7 +550,7 @@ static bool plan_tiling_with(PwTcPlan *p, int direct)
                    always serve the same group (S a multiple of 2 * Kc), or a group would skip mbarrier phases and its
                    parity wait would alias (found as a hang on 48 -> 224 with S = 2, Kc = 2) */
                 if (OB == 2 && S % (2 * p->Kc) != 0) continue;
-                const size_t smem = B + (size_t)S * A_SUB + (direct ? 0 : (size_t)OB * 8 * 4096) + 2 * NS * 4 + (3 * S + 5) * 8 + 16;
+                const size_t smem = B + (size_t)S * A_SUB + (direct ? 0 : (size_t)(OB == 2 ? 16 : 4) * 4096) + 2 * NS * 4 + (3 * S + 5) * 8 + 16;   /* staging: 4 KB per epilogue warp */
                 const int tmem = 2 * NS + (p->split ? S * 32 : 0);
                 if (smem <= limit && tmem <= 512) {
                     found = true;
@@ -643,7 +651,7 @@ int pw_tc_run(PwTcPlan *p, const float *in, int ldi, float *out, int ldo, int co
     grid -= grid % p->nsl;
     if (grid < p->nsl) grid = p->nsl;
     cudaError_t e = p->OB == 2 ? launch_pdl(k_pw_tc<2>, dim3(grid), dim3(64 + 2 * EPI_THREADS), p->smem, st, tmA, p->tmBh, p->tmBl, tmD, a)
-                               : launch_pdl(k_pw_tc<1>, dim3(grid), dim3(64 + EPI_THREADS), p->smem, st, tmA, p->tmBh, p->tmBl, tmD, a);
+                               : launch_pdl(k_pw_tc<1>, dim3(grid), dim3(64 + EPI_THREADS + SEP_EPI_THREADS), p->smem, st, tmA, p->tmBh, p->tmBl, tmD, a);
     if (e != cudaSuccess) { ffb_set_error("pw_tc launch failed: %s (grid %d smem %zu)", cudaGetErrorString(e), grid, p->smem); return -1; }
     return 0;
 }
