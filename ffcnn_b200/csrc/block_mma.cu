@@ -63,6 +63,9 @@ static BlkInst *find_inst(int KS1, int NT3, int S, int MTW, int GC, int tc = 0) 
     return nullptr;
 }
 
+static long long *g_blk_trace = nullptr;
+extern "C" void ffb_blk_set_trace(long long *dev_buf) { g_blk_trace = dev_buf; }      /* developer hook, effective only in -DFFB_BLK_TRACE builds */
+
 static float slope_of(int act) { return act == 2 ? 0.1f : act == 1 ? 0.f : 1.f; }
 
 /* Tile search: minimise an estimate of SM cycles per output pixel (tensor pipe: 2.14 clk per m16n8k8 on the SM, measured
@@ -149,11 +152,12 @@ BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
     p->OH = (h - 3 + 2) / stride + 1; p->OW = (w - 3 + 2) / stride + 1;
     if (p->OW % 2 || p->OH < 1) { delete p; return nullptr; }
     p->KS1 = (cin + 7) / 8; p->NT3 = (cout + 7) / 8; p->G = (cexp + 15) / 16;
-    /* measured on a B200 at batch 256 (profiles/r2a_block_tc.txt): the tcgen05 expand stage wins on the 96- and 224-channel
-       blocks (L38-L57 -5 %, L58 -12 %, L84-L108 -9 %), is neutral at 32 / 48 channels and loses where its TMEM budget
-       forces one CTA per SM (L22, L35, L61-L80) */
+    /* measured on a B200 at batch 256 (profiles/r2a_block_tc.txt, r2r_block_tc_policy.txt): with the MMAs issued from the warp
+       that has no depthwise unit, the tcgen05 expand stage wins on the 96- and 224-channel blocks (L38-L57 -10 %, L58 -17 %,
+       L84-L108 -14 % against mma.sync) and on the stride-1 32-channel blocks (L12, L17 -3 %); it ties at 136 channels and
+       loses where its TMEM budget forces one CTA per SM (L22, L35) */
     static const int env_tc = getenv("FFCNN_BLK_TC") ? atoi(getenv("FFCNN_BLK_TC")) : 0;
-    p->tc = env_tc > 0 ? 1 : env_tc < 0 ? 0 : (cexp == 96 || cexp == 224) ? 1 : 0;
+    p->tc = env_tc > 0 ? 1 : env_tc < 0 ? 0 : (cexp == 96 || cexp == 224 || (cexp == 32 && stride == 1)) ? 1 : 0;
     /* round up to an instantiated (KS1, NT3) pair: zero-padded K / N lanes cost tensor work, not correctness */
     bool found = false;
     for (int k = p->KS1; k <= 6 && !found; k++)
@@ -222,6 +226,11 @@ int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
     const unsigned box[4] = { (unsigned)SXs, (unsigned)p->XW, (unsigned)p->XH, 1u };
     if (ffb_make_tensor_map(&tm, x, 4, dims, strides, box, 0) != 0) return -1;
     a.slope1 = p->slope1; a.sloped = p->sloped; a.slope3 = p->slope3; a.slope_res = p->slope_res; a.res = p->res;
+    {   /* FFCNN_BLK_TRACE_SHAPE="cexp,stride" picks the block shape whose launches stamp the developer timeline */
+        static int tc = -1, ts = 0;
+        if (tc < 0) { tc = 0; if (const char *e = getenv("FFCNN_BLK_TRACE_SHAPE")) sscanf(e, "%d,%d", &tc, &ts); }
+        a.trace = (g_blk_trace && p->cexp == tc && p->S == ts) ? g_blk_trace : nullptr;
+    }
     const int grid = (int)std::min<long>(a.ntiles, (long)p->num_sms * p->occ);
     cudaError_t e = sm100::launch_pdl(inst->fn, dim3(grid), dim3(BLK_THREADS), p->smem, st, tm, a);
     if (e != cudaSuccess) { ffb_set_error("block_mma launch failed: %s (grid %d smem %zu)", cudaGetErrorString(e), grid, p->smem); return -1; }

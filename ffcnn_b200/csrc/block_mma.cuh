@@ -62,7 +62,14 @@ struct BlkArgs {
     int XH, XW, xo, yo, frame;            /* x-tile box and its offset inside the halo; frame: one tile covers the whole image */
     float inv_tpf, inv_ntx;
     float slope1, sloped, slope3, slope_res; int res;
+    long long *trace;                     /* developer timeline (-DFFB_BLK_TRACE, tools/blk_trace.py): CTA 0, warps 0 and 7 stamp clock64 per stage */
 };
+
+#ifdef FFB_BLK_TRACE
+#define BTRACE(ev) do { if (a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7) && tr_n < 250) a.trace[(warp ? 1 : 0) * 512 + 2 * tr_n] = (ev), a.trace[(warp ? 1 : 0) * 512 + 2 * tr_n + 1] = clock64(), tr_n++; } while (0)
+#else
+#define BTRACE(ev) do { } while (0)
+#endif
 
 /* per-chunk section offsets (floats) */
 struct BlkChunk {
@@ -144,6 +151,10 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     constexpr bool QUAD = MTW >= 2;
     constexpr int NQ = QUAD ? MTW / 2 : 1;                /* quads (or single m-tiles) per warp */
     constexpr BlkChunk off(GC, KS1, NT3, TC);
+    /* the thread that issues the tcgen05 expand GEMMs: lane 0 of the LAST warp -- on the 40x40 and 10x10 blocks that warp has no
+       stage-B unit (5 / 7 units for 8 warps), so the ~0.5-1.5 k cycles of MMA issue per chunk leave the critical path
+       (profiles/r2q_blockmma_timeline.txt: with thread 0 issuing, warp 0 -- a stage-B worker -- reached every stage that much later) */
+    constexpr int ISSUER = (BLK_WARPS - 1) * 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int HW = a.HW;
     float    *sSB3 = smem;                                          /* 96 floats */
@@ -234,6 +245,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     /* weights: with a single chunk they stay resident for the whole kernel; otherwise the two-slot ring runs continuously
        across tiles (chunk (c+1) % NC is requested while chunk c is being used), so no tile ever waits for L2 */
     const bool w_resident = a.NC == 1;
+    [[maybe_unused]] int tr_n = 0;
     uint32_t it = 0, cs = 0;                                                    /* tiles / weight chunks consumed so far by this CTA */
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
         const BlkTile q = blk_tile<S>(a, tile);
@@ -241,7 +253,9 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
         const float *sX = sXB + xb * a.xrows * SXs;
         const bool border = !a.frame && (q.iy0 < 0 || q.ix0 < 0 || q.iy0 + a.HH > a.H || q.ix0 + HW > a.W);
 
+        BTRACE(1);
         __syncthreads();                                  /* the previous tile no longer reads sW / sE / the other x buffer */
+        BTRACE(2);
         const bool last_tile = tile + gridDim.x >= a.ntiles;
         if (tid == 0 && !last_tile) load_x(tile + gridDim.x, xb ^ 1);
         float pacc[MTW][NT3][4];
@@ -252,6 +266,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 4; j++) pacc[mi][nt][j] = 0.f;
         sm100::mbar_wait(full_x + xb, (it >> 1) & 1);
+        BTRACE(3);
 
         if constexpr (TC) {
             /* x tile -> TMEM as the A operand, split hi/lo (thread = pixel = TMEM lane); x itself stays untouched in shared
@@ -274,7 +289,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
             sm100::tmem_st_wait();
             sm100::tc_fence_before_sync();
             __syncthreads();
-            if (tid == 0) {                               /* chunk 0 of this tile: its weights were requested during the previous tile */
+            if (tid == ISSUER) {                          /* chunk 0 of this tile: its weights were requested during the previous tile */
                 const uint32_t ws0 = (a.NC == 1) ? 0u : (cs & 1u);
                 sm100::mbar_wait(full_w + ws0, (a.NC == 1) ? 0u : ((cs >> 1) & 1u));
                 sm100::tc_fence_after_sync();
@@ -285,7 +300,9 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
         for (int c = 0; c < a.NC; c++, cs++) {
             const int wb = w_resident ? 0 : cs & 1;
             sm100::mbar_wait(full_w + wb, w_resident ? 0 : (cs >> 1) & 1);
+            BTRACE(10);
             if (c > 0) __syncthreads();                   /* every warp is done with chunk c-1: E and the other weight buffer are free */
+            BTRACE(11);
             if (tid == 0 && !w_resident && !(last_tile && c + 1 == a.NC)) load_chunk(c + 1 < a.NC ? c + 1 : 0, wb ^ 1);
             const float *wc = sW + wb * off.total;
             const float *wl4 = wc + lane * 4, *wt4 = wc + 4 * t;
@@ -295,6 +312,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                 /* ---------------- stage A (TC): the chunk's expand accumulators TMEM -> BN + act -> E rows ---------------- */
                 const uint32_t buf = cs & 1u;
                 sm100::mbar_wait(dfull + buf, (cs >> 1) & 1u);
+                BTRACE(12);
                 sm100::tc_fence_after_sync();
                 for (int mt = warp >> 2; mt < a.nmt; mt += BLK_WARPS / 4) {
                     const int p = mt * 128 + (warp & 3) * 32 + lane;
@@ -309,14 +327,20 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     for (int gr = 0; gr < GC; gr++) {
                         uint32_t r[16];
                         sm100::tmem_ld16(dcol + gr * 16, r);
+                        /* the group's scale / bias first, as eight independent loads under the TMEM load's latency: the stores below are
+                           ordered (volatile asm), and one load pair per store made this stage a chain of exposed shared-memory latencies */
+                        float4 s1v[4], b1v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            s1v[j] = *reinterpret_cast<const float4 *>(wc + off.s1 + gr * 16 + 4 * j);
+                            b1v[j] = *reinterpret_cast<const float4 *>(wc + off.b1 + gr * 16 + 4 * j);
+                        }
                         sm100::tmem_ld_wait();
                         if (mp.x >= 0) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const float4 s1 = *reinterpret_cast<const float4 *>(wc + off.s1 + gr * 16 + 4 * j);
-                                const float4 b1 = *reinterpret_cast<const float4 *>(wc + off.b1 + gr * 16 + 4 * j);
                                 float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                                v = inside ? bn_act4(v, s1, b1, a.slope1) : blk_zero4();
+                                v = inside ? bn_act4(v, s1v[j], b1v[j], a.slope1) : blk_zero4();
                                 sm100::sts128(sE_addr + mp.x + (gr * 16 + 4 * j) * 4, v);
                             }
                         }
@@ -394,11 +418,13 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                         }
                     }
             }
+            BTRACE(13);
             __syncthreads();
+            BTRACE(14);
             if constexpr (TC) {
                 /* the next chunk's expand GEMM runs on the tensor core while the warps do stage B of this one: D[.][buf ^ 1] was
                    drained before the previous barrier pair, its weights were requested at the top of this chunk */
-                if (tid == 0 && expand_pending && sm100::mbar_try_wait(full_w + (wb ^ 1), ((cs + 1) >> 1) & 1u)) {
+                if (tid == ISSUER && expand_pending && sm100::mbar_try_wait(full_w + (wb ^ 1), ((cs + 1) >> 1) & 1u)) {
                     sm100::tc_fence_after_sync();
                     issue_expand((uint32_t)(wb ^ 1), (cs + 1) & 1u);
                     expand_pending = false;
@@ -472,8 +498,9 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     }
                 }
             }
+            BTRACE(15);
             if constexpr (TC) {
-                if (tid == 0 && expand_pending) {         /* the next chunk's weights had not landed when stage B started */
+                if (tid == ISSUER && expand_pending) {    /* the next chunk's weights had not landed when stage B started */
                     sm100::mbar_wait(full_w + (wb ^ 1), ((cs + 1) >> 1) & 1u);
                     sm100::tc_fence_after_sync();
                     issue_expand((uint32_t)(wb ^ 1), (cs + 1) & 1u);
@@ -482,6 +509,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
         }
 
         /* ---------------- block epilogue: BN + act [+ shortcut from the resident x tile] -> y ---------------- */
+        BTRACE(20);
 #pragma unroll
         for (int mi = 0; mi < MTW; mi++) {
             const int qi = QUAD ? mi >> 1 : mi;
