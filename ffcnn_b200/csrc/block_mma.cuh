@@ -48,6 +48,21 @@ __device__ __forceinline__ void blk_fma4(float4 &acc, const float4 v, const floa
 }
 __device__ __forceinline__ float4 blk_zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+/* Four channels as two packed fp32 pairs (sm100.cuh: FFMA2 / FMUL2 / FADD2 do two IEEE fp32 operations per issue slot, results
+ * bit-identical to the scalar instructions).  The depthwise stage is bound by instruction issue on the warps that own a unit,
+ * so its 9 taps, BN and the lo half of the tf32 split run on pairs. */
+using sm100::f32x2;
+struct f4p { f32x2 a, b; };                                         /* channels (0, 1) and (2, 3) */
+__device__ __forceinline__ f4p blk_zero4p() { f4p r; r.a = 0ull; r.b = 0ull; return r; }
+__device__ __forceinline__ f4p lds128p(uint32_t addr)
+{
+    f4p v;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.a), "=l"(v.b) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ f4p ld4p(const float *p) { const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p); f4p r; r.a = t.x; r.b = t.y; return r; }
+__device__ __forceinline__ void blk_fma4p(f4p &acc, const f4p v, const f4p w) { acc.a = sm100::f2_fma(v.a, w.a, acc.a); acc.b = sm100::f2_fma(v.b, w.b, acc.b); }
+
 constexpr int BLK_THREADS = 256;
 constexpr int BLK_WARPS = BLK_THREADS / 32;
 
@@ -104,6 +119,28 @@ __device__ __forceinline__ float4 bn_act4(float4 a, float4 s, float4 b, float sl
     r.x = slope_act(fmaf(a.x, s.x, b.x), slope); r.y = slope_act(fmaf(a.y, s.y, b.y), slope);
     r.z = slope_act(fmaf(a.z, s.z, b.z), slope); r.w = slope_act(fmaf(a.w, s.w, b.w), slope);
     return r;
+}
+
+/* BN + activation of four channels held as pairs; the result comes back as scalars (the max is a scalar instruction) */
+__device__ __forceinline__ float4 bn_act4p(f4p a, f4p s, f4p b, f32x2 slope2)
+{
+    const f32x2 va = sm100::f2_fma(a.a, s.a, b.a), vb = sm100::f2_fma(a.b, s.b, b.b);
+    const f32x2 ma = sm100::f2_mul(va, slope2), mb = sm100::f2_mul(vb, slope2);
+    return make_float4(fmaxf(sm100::f2_lo(va), sm100::f2_lo(ma)), fmaxf(sm100::f2_hi(va), sm100::f2_hi(ma)),
+                       fmaxf(sm100::f2_lo(vb), sm100::f2_lo(mb)), fmaxf(sm100::f2_hi(vb), sm100::f2_hi(mb)));
+}
+/* max(v, slope * v) on a pair */
+__device__ __forceinline__ float2 act2(f32x2 v, f32x2 slope2)
+{
+    const f32x2 m = sm100::f2_mul(v, slope2);
+    return make_float2(fmaxf(sm100::f2_lo(v), sm100::f2_lo(m)), fmaxf(sm100::f2_hi(v), sm100::f2_hi(m)));
+}
+/* tf32 split of two values that are adjacent in an mma fragment: hi by integer rounding, lo = x - hi as one packed subtract */
+__device__ __forceinline__ void split_tf32x2(float x0, float x1, uint32_t &h0, uint32_t &h1, uint32_t &l0, uint32_t &l1)
+{
+    h0 = (__float_as_uint(x0) + 0x1000u) & 0xffffe000u; h1 = (__float_as_uint(x1) + 0x1000u) & 0xffffe000u;
+    const f32x2 l = sm100::f2_sub(sm100::f2_pack(x0, x1), (f32x2)h0 | ((f32x2)h1 << 32));
+    l0 = (uint32_t)l; l1 = (uint32_t)(l >> 32);
 }
 
 /* 1-D bulk copy global -> shared, completion (bytes) on an mbarrier; size multiple of 16, both addresses 16-byte aligned */
@@ -203,6 +240,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     __syncthreads();
     if (TC) sm100::tc_fence_after_sync();
     pdl_trigger(); pdl_wait();
+    const f32x2 slope1_2 = sm100::f2_pack(a.slope1, a.slope1), sloped2 = sm100::f2_pack(a.sloped, a.sloped);
     /* ---- TC: expand GEMM on tcgen05.  TMEM columns: per 128-pixel m-tile mt the A operand [x_hi (KP cols) | x_lo (KP cols)]
        at mt * 2KP, then the accumulators D[mt][buf] (16*GC cols each, double buffered over chunks) ---- */
     constexpr int KP = 8 * KS1, KC = (KS1 + 3) / 4;
@@ -280,8 +318,8 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     float4 x0 = blk_zero4(), x1 = blk_zero4();
                     if (p < XP) { x0 = *reinterpret_cast<const float4 *>(xr + 8 * ks); x1 = *reinterpret_cast<const float4 *>(xr + 8 * ks + 4); }
                     uint32_t hi[8], lo[8];
-                    split_tf32(x0.x, hi[0], lo[0]); split_tf32(x0.y, hi[1], lo[1]); split_tf32(x0.z, hi[2], lo[2]); split_tf32(x0.w, hi[3], lo[3]);
-                    split_tf32(x1.x, hi[4], lo[4]); split_tf32(x1.y, hi[5], lo[5]); split_tf32(x1.z, hi[6], lo[6]); split_tf32(x1.w, hi[7], lo[7]);
+                    split_tf32x2(x0.x, x0.y, hi[0], hi[1], lo[0], lo[1]); split_tf32x2(x0.z, x0.w, hi[2], hi[3], lo[2], lo[3]);
+                    split_tf32x2(x1.x, x1.y, hi[4], hi[5], lo[4], lo[5]); split_tf32x2(x1.z, x1.w, hi[6], hi[7], lo[6], lo[7]);
                     sm100::tmem_st8(acol + 8 * ks, hi);
                     sm100::tmem_st8(acol + KP + 8 * ks, lo);
                 }
@@ -329,18 +367,18 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                         sm100::tmem_ld16(dcol + gr * 16, r);
                         /* the group's scale / bias first, as eight independent loads under the TMEM load's latency: the stores below are
                            ordered (volatile asm), and one load pair per store made this stage a chain of exposed shared-memory latencies */
-                        float4 s1v[4], b1v[4];
+                        f4p s1v[4], b1v[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            s1v[j] = *reinterpret_cast<const float4 *>(wc + off.s1 + gr * 16 + 4 * j);
-                            b1v[j] = *reinterpret_cast<const float4 *>(wc + off.b1 + gr * 16 + 4 * j);
+                            s1v[j] = ld4p(wc + off.s1 + gr * 16 + 4 * j);
+                            b1v[j] = ld4p(wc + off.b1 + gr * 16 + 4 * j);
                         }
                         sm100::tmem_ld_wait();
                         if (mp.x >= 0) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                                v = inside ? bn_act4(v, s1v[j], b1v[j], a.slope1) : blk_zero4();
+                                f4p acc; acc.a = (f32x2)r[4 * j] | ((f32x2)r[4 * j + 1] << 32); acc.b = (f32x2)r[4 * j + 2] | ((f32x2)r[4 * j + 3] << 32);
+                                const float4 v = inside ? bn_act4p(acc, s1v[j], b1v[j], slope1_2) : blk_zero4();
                                 sm100::sts128(sE_addr + mp.x + (gr * 16 + 4 * j) * 4, v);
                             }
                         }
@@ -409,10 +447,8 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                             }
 #pragma unroll
                             for (int gr = 0; gr < GC; gr++) {
-                                const float4 s1 = *reinterpret_cast<const float4 *>(wt4 + off.s1 + gr * 16);
-                                const float4 b1 = *reinterpret_cast<const float4 *>(wt4 + off.b1 + gr * 16);
-                                float4 v = make_float4(acc[gr][m][0][2 * r], acc[gr][m][0][2 * r + 1], acc[gr][m][1][2 * r], acc[gr][m][1][2 * r + 1]);
-                                v = inside ? bn_act4(v, s1, b1, a.slope1) : blk_zero4();
+                                f4p av; av.a = sm100::f2_pack(acc[gr][m][0][2 * r], acc[gr][m][0][2 * r + 1]); av.b = sm100::f2_pack(acc[gr][m][1][2 * r], acc[gr][m][1][2 * r + 1]);
+                                const float4 v = inside ? bn_act4p(av, ld4p(wt4 + off.s1 + gr * 16), ld4p(wt4 + off.b1 + gr * 16), slope1_2) : blk_zero4();
                                 sm100::sts128(sE_addr + mp.x + (gr * 16 + 4 * t) * 4, v);
                             }
                         }
@@ -434,32 +470,31 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
             /* ---------------- stage B: depthwise 3x3 in registers -> projection GEMM ---------------- */
 #pragma unroll
             for (int grp = 0; grp < GC; grp++) {
-                float4 wd[9];
+                f4p wd[9];
 #pragma unroll
-                for (int k = 0; k < 9; k++) wd[k] = *reinterpret_cast<const float4 *>(wt4 + off.wd + (grp * 9 + k) * 16);
-                const float4 sd = *reinterpret_cast<const float4 *>(wt4 + off.sd + grp * 16);
-                const float4 bd = *reinterpret_cast<const float4 *>(wt4 + off.bd + grp * 16);
+                for (int k = 0; k < 9; k++) wd[k] = ld4p(wt4 + off.wd + (grp * 9 + k) * 16);
+                const f4p sd = ld4p(wt4 + off.sd + grp * 16), bd = ld4p(wt4 + off.bd + grp * 16);
                 uint32_t ah[MTW][2][4], al[MTW][2][4];
 #pragma unroll
                 for (int qi = 0; qi < NQ; qi++) {
                     constexpr uint32_t px = SEs * 4;
                     constexpr int NR = QUAD ? S + 3 : 3, NCOL = S + 3;             /* input rows / columns the unit touches */
-                    float4 d[2][2];                                                /* [row of the quad][pixel] */
+                    f4p d[2][2];                                                   /* [row of the quad][pixel] */
 #pragma unroll
-                    for (int h = 0; h < 2; h++) { d[h][0] = blk_zero4(); d[h][1] = blk_zero4(); }
+                    for (int h = 0; h < 2; h++) { d[h][0] = blk_zero4p(); d[h][1] = blk_zero4p(); }
                     if (qi < nq) {
 #pragma unroll
                         for (int r = 0; r < NR; r++) {
                             const uint32_t row = dwbase[qi] + grp * 64 + r * rowpitch;
-                            float4 e[NCOL];
+                            f4p e[NCOL];
 #pragma unroll
-                            for (int k = 0; k < NCOL; k++) e[k] = sm100::lds128(row + k * px);
+                            for (int k = 0; k < NCOL; k++) e[k] = lds128p(row + k * px);
 #pragma unroll
                             for (int h = 0; h < (QUAD ? 2 : 1); h++) {
                                 const int dy = r - h * S;                              /* tap row of this input row for quad row h */
                                 if (dy >= 0 && dy < 3) {
-                                    blk_fma4(d[h][0], e[0], wd[dy * 3]); blk_fma4(d[h][0], e[1], wd[dy * 3 + 1]); blk_fma4(d[h][0], e[2], wd[dy * 3 + 2]);
-                                    blk_fma4(d[h][1], e[S], wd[dy * 3]); blk_fma4(d[h][1], e[S + 1], wd[dy * 3 + 1]); blk_fma4(d[h][1], e[S + 2], wd[dy * 3 + 2]);
+                                    blk_fma4p(d[h][0], e[0], wd[dy * 3]); blk_fma4p(d[h][0], e[1], wd[dy * 3 + 1]); blk_fma4p(d[h][0], e[2], wd[dy * 3 + 2]);
+                                    blk_fma4p(d[h][1], e[S], wd[dy * 3]); blk_fma4p(d[h][1], e[S + 1], wd[dy * 3 + 1]); blk_fma4p(d[h][1], e[S + 2], wd[dy * 3 + 2]);
                                 }
                             }
                         }
@@ -467,11 +502,12 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
 #pragma unroll
                     for (int h = 0; h < (QUAD ? 2 : 1); h++) {
                         const int mi = QUAD ? 2 * qi + h : qi;
-                        const float4 d0 = bn_act4(d[h][0], sd, bd, a.sloped), d1 = bn_act4(d[h][1], sd, bd, a.sloped);
-                        split_tf32(d0.x, ah[mi][0][0], al[mi][0][0]); split_tf32(d1.x, ah[mi][0][1], al[mi][0][1]);
-                        split_tf32(d0.y, ah[mi][0][2], al[mi][0][2]); split_tf32(d1.y, ah[mi][0][3], al[mi][0][3]);
-                        split_tf32(d0.z, ah[mi][1][0], al[mi][1][0]); split_tf32(d1.z, ah[mi][1][1], al[mi][1][1]);
-                        split_tf32(d0.w, ah[mi][1][2], al[mi][1][2]); split_tf32(d1.w, ah[mi][1][3], al[mi][1][3]);
+                        const float4 d0 = bn_act4p(d[h][0], sd, bd, sloped2), d1 = bn_act4p(d[h][1], sd, bd, sloped2);
+                        /* fragment registers 0/1 and 2/3 hold the same channel of the lane's two pixels: split them as pairs */
+                        split_tf32x2(d0.x, d1.x, ah[mi][0][0], ah[mi][0][1], al[mi][0][0], al[mi][0][1]);
+                        split_tf32x2(d0.y, d1.y, ah[mi][0][2], ah[mi][0][3], al[mi][0][2], al[mi][0][3]);
+                        split_tf32x2(d0.z, d1.z, ah[mi][1][0], ah[mi][1][1], al[mi][1][0], al[mi][1][1]);
+                        split_tf32x2(d0.w, d1.w, ah[mi][1][2], ah[mi][1][3], al[mi][1][2], al[mi][1][3]);
                     }
                 }
                 if (nq > 0) {
@@ -510,6 +546,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
 
         /* ---------------- block epilogue: BN + act [+ shortcut from the resident x tile] -> y ---------------- */
         BTRACE(20);
+        const f32x2 slope3_2 = sm100::f2_pack(a.slope3, a.slope3), sloper_2 = sm100::f2_pack(a.slope_res, a.slope_res);
 #pragma unroll
         for (int mi = 0; mi < MTW; mi++) {
             const int qi = QUAD ? mi >> 1 : mi;
@@ -522,13 +559,13 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                     const int co = 8 * nt + 2 * t;
                     if (co < a.cout) {
                         const float2 s3 = *reinterpret_cast<const float2 *>(sSB3 + co), b3 = *reinterpret_cast<const float2 *>(sSB3 + COUT_P + co);
-                        float2 v0, v1;
-                        v0.x = slope_act(fmaf(pacc[mi][nt][0], s3.x, b3.x), a.slope3); v0.y = slope_act(fmaf(pacc[mi][nt][1], s3.y, b3.y), a.slope3);
-                        v1.x = slope_act(fmaf(pacc[mi][nt][2], s3.x, b3.x), a.slope3); v1.y = slope_act(fmaf(pacc[mi][nt][3], s3.y, b3.y), a.slope3);
+                        const f32x2 s3p = sm100::f2_pack(s3.x, s3.y), b3p = sm100::f2_pack(b3.x, b3.y);
+                        float2 v0 = act2(sm100::f2_fma(sm100::f2_pack(pacc[mi][nt][0], pacc[mi][nt][1]), s3p, b3p), slope3_2);
+                        float2 v1 = act2(sm100::f2_fma(sm100::f2_pack(pacc[mi][nt][2], pacc[mi][nt][3]), s3p, b3p), slope3_2);
                         if (a.res) {
                             const float2 r0 = *reinterpret_cast<const float2 *>(xc + co), r1 = *reinterpret_cast<const float2 *>(xc + SXs + co);
-                            v0.x = slope_act(v0.x + r0.x, a.slope_res); v0.y = slope_act(v0.y + r0.y, a.slope_res);
-                            v1.x = slope_act(v1.x + r1.x, a.slope_res); v1.y = slope_act(v1.y + r1.y, a.slope_res);
+                            v0 = act2(sm100::f2_add(sm100::f2_pack(v0.x, v0.y), sm100::f2_pack(r0.x, r0.y)), sloper_2);
+                            v1 = act2(sm100::f2_add(sm100::f2_pack(v1.x, v1.y), sm100::f2_pack(r1.x, r1.y)), sloper_2);
                         }
                         *reinterpret_cast<float2 *>(yp + co) = v0;
                         *reinterpret_cast<float2 *>(yp + a.ldy + co) = v1;               /* tw is even: pixel tx+1 is inside the tile */

@@ -14,6 +14,12 @@
  *
  * Arithmetic is plain fp32 FFMA in the reference's tap order (ky, then kx: conv-v0.c:16-25).  Lanes 0 and 31 (lane 0
  * only for stride 2) are halo lanes: they expand pixels for their neighbours but produce no output.
+ *
+ * The kernels are bound by instruction issue, not by the FMA pipe (ncu: 56 % of the warp instructions were FFMA, the
+ * schedulers issued on 60-67 % of their cycles with 2-3 warps each), so every channel-wise operation runs on PAIRS of
+ * adjacent channels with Blackwell's packed fp32 instructions (fma/mul/add.rn.f32x2 -> FFMA2/FMUL2/FADD2): the same IEEE
+ * operation per component -- results are bit-identical to the scalar form -- in half the issue slots.  ptxas feeds them
+ * the weight pairs straight from uniform registers (LDCU.128 = two pairs) and a pixel's scalar as a broadcast operand.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -23,14 +29,19 @@
 
 namespace ffb {
 
+using sm100::f32x2;
+using sm100::f2_pack; using sm100::f2_lo; using sm100::f2_hi; using sm100::f2_fma; using sm100::f2_mul; using sm100::f2_add;
+
 template <int CIN, int CEXP, int COUT>
-struct RegBlockW {
+struct alignas(16) RegBlockW {
     /* every matrix is stored with the OUTPUT channel innermost: consecutive FFMAs of the unrolled loops then use
        consecutive constants (one 128-bit uniform load feeds four) and independent accumulators (no dependent chains) */
     float w1[CIN][CEXP], s1[CEXP], b1[CEXP];
     float wd[9][CEXP], sd[CEXP], bd[CEXP];
     float w2[CEXP][COUT], s3[COUT], b3[COUT];
 };
+/* channel pair i (channels 2i, 2i+1) of a row of weights */
+__device__ __forceinline__ f32x2 rb_pr(const float *row, int i) { return reinterpret_cast<const f32x2 *>(row)[i]; }
 
 struct RegBlockArgs {
     const float *x; float *y;
@@ -40,23 +51,29 @@ struct RegBlockArgs {
 
 constexpr int REG_WARPS = 4;
 
-__device__ __forceinline__ float rb_act(float v, float slope) { return fmaxf(v, v * slope); }
+/* utils.h:15-23 as max(v, slope * v), on a channel pair */
+__device__ __forceinline__ f32x2 rb_act2(f32x2 v, f32x2 slope2)
+{
+    const f32x2 m = f2_mul(v, slope2);
+    return f2_pack(fmaxf(f2_lo(v), f2_lo(m)), fmaxf(f2_hi(v), f2_hi(m)));
+}
 
 constexpr int RB_CH = 8;            /* expanded channels processed at a time: bounds the transient registers of a row step */
+constexpr int RB_P = RB_CH / 2;     /* ... as channel pairs */
 
 /* expand channels [C0, C0 + RB_CH) of one pixel: e[c] = act(s1[c] * sum_k x[k] * w1[c][k] + b1[c]), or 0 outside the image
  * (the depthwise conv's zero padding) */
 template <int C0, int CIN, int CEXP, int COUT>
-__device__ __forceinline__ void rb_expand(const RegBlockW<CIN, CEXP, COUT> &w, const float (&x)[CIN], bool inside, float slope, float (&e)[RB_CH])
+__device__ __forceinline__ void rb_expand(const RegBlockW<CIN, CEXP, COUT> &w, const float (&x)[CIN], bool inside, f32x2 slope2, f32x2 (&e)[RB_P])
 {
 #pragma unroll
-    for (int c = 0; c < RB_CH; c++) e[c] = x[0] * w.w1[0][C0 + c];
+    for (int c = 0; c < RB_P; c++) e[c] = f2_mul(f2_pack(x[0], x[0]), rb_pr(w.w1[0], C0 / 2 + c));
 #pragma unroll
     for (int k = 1; k < CIN; k++)
 #pragma unroll
-        for (int c = 0; c < RB_CH; c++) e[c] = fmaf(x[k], w.w1[k][C0 + c], e[c]);
+        for (int c = 0; c < RB_P; c++) e[c] = f2_fma(f2_pack(x[k], x[k]), rb_pr(w.w1[k], C0 / 2 + c), e[c]);
 #pragma unroll
-    for (int c = 0; c < RB_CH; c++) e[c] = inside ? rb_act(fmaf(e[c], w.s1[C0 + c], w.b1[C0 + c]), slope) : 0.f;
+    for (int c = 0; c < RB_P; c++) e[c] = inside ? rb_act2(f2_fma(e[c], rb_pr(w.s1, C0 / 2 + c), rb_pr(w.b1, C0 / 2 + c)), slope2) : 0ull;
 }
 
 template <int CIN>
@@ -69,55 +86,71 @@ __device__ __forceinline__ void rb_load(const float *p, bool ok, float (&x)[CIN]
     }
 }
 
-/* d[C0 ..] (+)= taps of kernel row DY applied to the three horizontally adjacent expanded pixels l, m, r (channel chunk C0) */
-template <int DY, bool SET, int C0, int CIN, int CEXP, int COUT>
-__device__ __forceinline__ void rb_taps(const RegBlockW<CIN, CEXP, COUT> &w, float (&d)[CEXP], const float (&l)[RB_CH], const float (&m)[RB_CH], const float (&r)[RB_CH])
+/* the channel chunk of a neighbouring lane (delta = -1: the lane to the left, +1: to the right) */
+template <int DELTA>
+__device__ __forceinline__ void rb_neighbour(const f32x2 (&e)[RB_P], f32x2 (&o)[RB_P])
 {
 #pragma unroll
-    for (int c = 0; c < RB_CH; c++) d[C0 + c] = SET ? l[c] * w.wd[DY * 3][C0 + c] : fmaf(l[c], w.wd[DY * 3][C0 + c], d[C0 + c]);
+    for (int c = 0; c < RB_P; c++) {
+        const float lo = DELTA < 0 ? __shfl_up_sync(0xffffffffu, f2_lo(e[c]), 1) : __shfl_down_sync(0xffffffffu, f2_lo(e[c]), 1);
+        const float hi = DELTA < 0 ? __shfl_up_sync(0xffffffffu, f2_hi(e[c]), 1) : __shfl_down_sync(0xffffffffu, f2_hi(e[c]), 1);
+        o[c] = f2_pack(lo, hi);
+    }
+}
+
+/* d[C0 ..] (+)= taps of kernel row DY applied to the three horizontally adjacent expanded pixels l, m, r (channel chunk C0) */
+template <int DY, bool SET, int C0, int CIN, int CEXP, int COUT>
+__device__ __forceinline__ void rb_taps(const RegBlockW<CIN, CEXP, COUT> &w, f32x2 (&d)[CEXP / 2], const f32x2 (&l)[RB_P], const f32x2 (&m)[RB_P], const f32x2 (&r)[RB_P])
+{
 #pragma unroll
-    for (int c = 0; c < RB_CH; c++) d[C0 + c] = fmaf(m[c], w.wd[DY * 3 + 1][C0 + c], d[C0 + c]);
+    for (int c = 0; c < RB_P; c++) d[C0 / 2 + c] = SET ? f2_mul(l[c], rb_pr(w.wd[DY * 3], C0 / 2 + c)) : f2_fma(l[c], rb_pr(w.wd[DY * 3], C0 / 2 + c), d[C0 / 2 + c]);
 #pragma unroll
-    for (int c = 0; c < RB_CH; c++) d[C0 + c] = fmaf(r[c], w.wd[DY * 3 + 2][C0 + c], d[C0 + c]);
+    for (int c = 0; c < RB_P; c++) d[C0 / 2 + c] = f2_fma(m[c], rb_pr(w.wd[DY * 3 + 1], C0 / 2 + c), d[C0 / 2 + c]);
+#pragma unroll
+    for (int c = 0; c < RB_P; c++) d[C0 / 2 + c] = f2_fma(r[c], rb_pr(w.wd[DY * 3 + 2], C0 / 2 + c), d[C0 / 2 + c]);
 }
 
 /* finish one output pixel: BN + act of the depthwise sum, projection, BN + act, optional shortcut, store.
  * PART splits a wide block into channel slices run as consecutive launches (the projection is a sum over expanded channels):
  * 0 = whole block; 1 = first slice, store the raw partial sums; 2 = middle slice, add to them; 3 = last slice, add, BN + act. */
 template <bool RES, int PART, int CIN, int CEXP, int COUT>
-__device__ __forceinline__ void rb_finish(const RegBlockW<CIN, CEXP, COUT> &w, const RegBlockArgs &a, const float (&d)[CEXP], const float (&xc)[CIN], float *yp)
+__device__ __forceinline__ void rb_finish(const RegBlockW<CIN, CEXP, COUT> &w, const RegBlockArgs &a, const f32x2 (&d)[CEXP / 2], const float (&xc)[CIN], float *yp)
 {
-    float dd[CEXP];
+    const f32x2 sloped2 = f2_pack(a.sloped, a.sloped);
+    f32x2 dd[CEXP / 2];
 #pragma unroll
-    for (int c = 0; c < CEXP; c++) dd[c] = rb_act(fmaf(d[c], w.sd[c], w.bd[c]), a.sloped);
-    float o[COUT];
+    for (int c = 0; c < CEXP / 2; c++) dd[c] = rb_act2(f2_fma(d[c], rb_pr(w.sd, c), rb_pr(w.bd, c)), sloped2);
+    f32x2 o[COUT / 2];
     if (PART >= 2) {
 #pragma unroll
-        for (int v = 0; v < COUT / 4; v++) { const float4 t = reinterpret_cast<const float4 *>(yp)[v]; o[4 * v] = t.x; o[4 * v + 1] = t.y; o[4 * v + 2] = t.z; o[4 * v + 3] = t.w; }
+        for (int v = 0; v < COUT / 4; v++) { const float4 t = reinterpret_cast<const float4 *>(yp)[v]; o[2 * v] = f2_pack(t.x, t.y); o[2 * v + 1] = f2_pack(t.z, t.w); }
     }
     if (PART < 2) {
 #pragma unroll
-        for (int co = 0; co < COUT; co++) o[co] = 0.f;
+        for (int co = 0; co < COUT / 2; co++) o[co] = 0ull;
     }
 #pragma unroll
-    for (int c = 0; c < CEXP; c++)
+    for (int c = 0; c < CEXP; c++) {
+        const float dc = (c & 1) ? f2_hi(dd[c / 2]) : f2_lo(dd[c / 2]);
 #pragma unroll
-        for (int co = 0; co < COUT; co++) o[co] = fmaf(dd[c], w.w2[c][co], o[co]);
+        for (int co = 0; co < COUT / 2; co++) o[co] = f2_fma(f2_pack(dc, dc), rb_pr(w.w2[c], co), o[co]);
+    }
 #pragma unroll
-    for (int co = 0; co < COUT; co++) {
-        float s = o[co];
-        if (PART == 0 || PART == 3) s = rb_act(fmaf(s, w.s3[co], w.b3[co]), a.slope3);
-        if (RES) s = rb_act(s + xc[co < CIN ? co : 0], a.slope_res);
+    for (int co = 0; co < COUT / 2; co++) {
+        f32x2 s = o[co];
+        if (PART == 0 || PART == 3) s = rb_act2(f2_fma(s, rb_pr(w.s3, co), rb_pr(w.b3, co)), f2_pack(a.slope3, a.slope3));
+        if (RES) s = rb_act2(f2_add(s, f2_pack(xc[2 * co < CIN ? 2 * co : 0], xc[2 * co + 1 < CIN ? 2 * co + 1 : 0])), f2_pack(a.slope_res, a.slope_res));
         o[co] = s;
     }
 #pragma unroll
-    for (int v = 0; v < COUT / 4; v++) reinterpret_cast<float4 *>(yp)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+    for (int v = 0; v < COUT / 4; v++) reinterpret_cast<float4 *>(yp)[v] = make_float4(f2_lo(o[2 * v]), f2_hi(o[2 * v]), f2_lo(o[2 * v + 1]), f2_hi(o[2 * v + 1]));
 }
 
 /* ------------------------------------------------------------------ stride 1: two output pixels per lane, 60 per warp */
 template <int CIN, int CEXP, int COUT, bool RES>
 __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid_constant__ RegBlockW<CIN, CEXP, COUT> w, const RegBlockArgs a)
 {
+    constexpr int CP = CEXP / 2;
     const int lane = threadIdx.x & 31;
     const long strip = (long)blockIdx.x * REG_WARPS + (threadIdx.x >> 5);
     const int per_frame = a.nsx * a.nsy;
@@ -129,12 +162,13 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
     const bool writes = lane >= 1 && lane <= 30 && ix0 < a.W;                   /* W is even: ix1 is inside whenever ix0 is */
     const float *xf = a.x + (long)n * a.H * a.W * CIN;
     float *yf = a.y + (long)n * a.OH * a.OW * COUT;
+    const f32x2 slope1 = f2_pack(a.slope1, a.slope1);
     sm100::pdl_trigger(); sm100::pdl_wait();
 
-    float A0[CEXP], A1[CEXP], B0[CEXP], B1[CEXP], C0[CEXP], C1[CEXP];           /* three rolling output rows x two pixels */
+    f32x2 A0[CP], A1[CP], B0[CP], B1[CP], C0[CP], C1[CP];                       /* three rolling output rows x two pixels, channel pairs */
     float xc0[CIN], xc1[CIN], xn0[CIN], xn1[CIN], xp0[CIN], xp1[CIN];           /* x of the row in flight / the next row / the previous row */
 #pragma unroll
-    for (int c = 0; c < CEXP; c++) { A0[c] = A1[c] = B0[c] = B1[c] = C0[c] = C1[c] = 0.f; }
+    for (int c = 0; c < CP; c++) { A0[c] = A1[c] = B0[c] = B1[c] = C0[c] = C1[c] = 0ull; }
 #pragma unroll
     for (int k = 0; k < CIN; k++) xp0[k] = xp1[k] = 0.f;
     {
@@ -143,15 +177,14 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
         rb_load<CIN>(xf + ((long)max(r, 0) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
     }
     /* one input row: dm = output row r-1 (gets kernel row 2 and is finished), d0 = row r (kernel row 1), dp = row r+1 (kernel row 0, first contribution) */
-    auto step = [&](int r, float (&dm0)[CEXP], float (&dm1)[CEXP], float (&d00)[CEXP], float (&d01)[CEXP], float (&dp0)[CEXP], float (&dp1)[CEXP]) {
+    auto step = [&](int r, f32x2 (&dm0)[CP], f32x2 (&dm1)[CP], f32x2 (&d00)[CP], f32x2 (&d01)[CP], f32x2 (&dp0)[CP], f32x2 (&dp1)[CP]) {
         /* expand -> neighbour exchange -> taps, RB_CH channels at a time */
         auto chunk = [&](auto c0, bool rin) {
             constexpr int C0 = decltype(c0)::value;
-            float e0[RB_CH], e1[RB_CH], el[RB_CH], er[RB_CH];
-            rb_expand<C0>(w, xc0, rin && in0, a.slope1, e0);
-            rb_expand<C0>(w, xc1, rin && in1, a.slope1, e1);
-#pragma unroll
-            for (int c = 0; c < RB_CH; c++) { el[c] = __shfl_up_sync(0xffffffffu, e1[c], 1); er[c] = __shfl_down_sync(0xffffffffu, e0[c], 1); }
+            f32x2 e0[RB_P], e1[RB_P], el[RB_P], er[RB_P];
+            rb_expand<C0>(w, xc0, rin && in0, slope1, e0);
+            rb_expand<C0>(w, xc1, rin && in1, slope1, e1);
+            rb_neighbour<-1>(e1, el); rb_neighbour<1>(e0, er);
             rb_taps<2, false, C0>(w, dm0, el, e0, e1); rb_taps<2, false, C0>(w, dm1, e0, e1, er);
             rb_taps<1, false, C0>(w, d00, el, e0, e1); rb_taps<1, false, C0>(w, d01, e0, e1, er);
             rb_taps<0, true, C0>(w, dp0, el, e0, e1);  rb_taps<0, true, C0>(w, dp1, e0, e1, er);
@@ -189,6 +222,7 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
 template <int CIN, int CEXP, int COUT, int PART>
 __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid_constant__ RegBlockW<CIN, CEXP, COUT> w, const RegBlockArgs a)
 {
+    constexpr int CP = CEXP / 2;
     const int lane = threadIdx.x & 31;
     const long strip = (long)blockIdx.x * REG_WARPS + (threadIdx.x >> 5);
     const int per_frame = a.nsx * a.nsy;
@@ -200,19 +234,22 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
     const bool writes = lane >= 1 && ox < a.OW;
     const float *xf = a.x + (long)n * a.H * a.W * CIN;
     float *yf = a.y + (long)n * a.OH * a.OW * COUT;
+    const f32x2 slope1 = f2_pack(a.slope1, a.slope1);
     sm100::pdl_trigger(); sm100::pdl_wait();
 
-    float A[CEXP], B[CEXP];                                                     /* output rows oy and oy + 1 */
+    f32x2 A[CP], B[CP];                                                         /* output rows oy and oy + 1, channel pairs */
     float xc0[CIN], xc1[CIN], xn0[CIN], xn1[CIN];
 #pragma unroll
-    for (int c = 0; c < CEXP; c++) A[c] = B[c] = 0.f;
+    for (int c = 0; c < CP; c++) A[c] = B[c] = 0ull;
     const int r_first = 2 * oy0 - 1, r_last = 2 * (oy1 - 1) + 1;
     {
         const bool rok = r_first >= 0;
         rb_load<CIN>(xf + ((long)max(r_first, 0) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
         rb_load<CIN>(xf + ((long)max(r_first, 0) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
     }
-    const float dummy[CIN] = {};
+    float dummy[CIN];
+#pragma unroll
+    for (int k = 0; k < CIN; k++) dummy[k] = 0.f;
     auto fetch_row = [&](int r) {                                               /* xc <- row r, prefetch row r + 1 */
 #pragma unroll
         for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; }
@@ -221,27 +258,25 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
         rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
     };
     /* odd input row 2oy-1: kernel row 2 of output row oy-1 (cur) and kernel row 0 of output row oy (nxt), RB_CH channels at a time */
-    auto odd_chunk = [&](auto c0, bool rin, float (&cur)[CEXP], float (&nxt)[CEXP]) {
+    auto odd_chunk = [&](auto c0, bool rin, f32x2 (&cur)[CEXP / 2], f32x2 (&nxt)[CEXP / 2]) {
         constexpr int C0 = decltype(c0)::value;
-        float e0[RB_CH], e1[RB_CH], el[RB_CH];
-        rb_expand<C0>(w, xc0, rin && in0, a.slope1, e0);
-        rb_expand<C0>(w, xc1, rin && in1, a.slope1, e1);
-#pragma unroll
-        for (int c = 0; c < RB_CH; c++) el[c] = __shfl_up_sync(0xffffffffu, e1[c], 1);
+        f32x2 e0[RB_P], e1[RB_P], el[RB_P];
+        rb_expand<C0>(w, xc0, rin && in0, slope1, e0);
+        rb_expand<C0>(w, xc1, rin && in1, slope1, e1);
+        rb_neighbour<-1>(e1, el);
         rb_taps<2, false, C0>(w, cur, el, e0, e1);
         rb_taps<0, true, C0>(w, nxt, el, e0, e1);
     };
-    auto even_chunk = [&](auto c0, bool rin, float (&nxt)[CEXP]) {              /* even input row 2oy: kernel row 1 of output row oy */
+    auto even_chunk = [&](auto c0, bool rin, f32x2 (&nxt)[CEXP / 2]) {                /* even input row 2oy: kernel row 1 of output row oy */
         constexpr int C0 = decltype(c0)::value;
-        float e0[RB_CH], e1[RB_CH], el[RB_CH];
-        rb_expand<C0>(w, xc0, rin && in0, a.slope1, e0);
-        rb_expand<C0>(w, xc1, rin && in1, a.slope1, e1);
-#pragma unroll
-        for (int c = 0; c < RB_CH; c++) el[c] = __shfl_up_sync(0xffffffffu, e1[c], 1);
+        f32x2 e0[RB_P], e1[RB_P], el[RB_P];
+        rb_expand<C0>(w, xc0, rin && in0, slope1, e0);
+        rb_expand<C0>(w, xc1, rin && in1, slope1, e1);
+        rb_neighbour<-1>(e1, el);
         rb_taps<1, false, C0>(w, nxt, el, e0, e1);
     };
     /* rows come in (odd, even) pairs: odd row 2oy-1 closes output row oy-1 and opens row oy; even row 2oy is row oy's centre */
-    auto pair = [&](int oy, float (&cur)[CEXP], float (&nxt)[CEXP]) {
+    auto pair = [&](int oy, f32x2 (&cur)[CEXP / 2], f32x2 (&nxt)[CEXP / 2]) {
         {
             const int r = 2 * oy - 1; const bool rin = r >= 0 && r < a.H;
             fetch_row(r);

@@ -33,6 +33,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4 v)
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+/* ---------------------------------------------------------------- packed fp32 pairs (FFMA2 / FMUL2 / FADD2)
+ * sm_100 executes fma/mul/add.rn.f32x2 on a 64-bit register pair: two independent IEEE fp32 operations (bit-identical to
+ * fmaf / * / +) in ONE issue slot.  The FMA pipe's peak is unchanged (tools/micro/ffma2.cu: 70.8 vs 73.2 TFLOP/s); what
+ * they buy is issue slots, which is what the CUDA-core stages of the fused kernels run out of.  Not volatile: the compiler
+ * may schedule, CSE and fold them; ptxas turns f2_pack(s, s) into a broadcast operand and constant-bank pairs into
+ * uniform-register operands. */
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { return (f32x2)__float_as_uint(lo) | ((f32x2)__float_as_uint(hi) << 32); }
+__device__ __forceinline__ float f2_lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f2_hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 /* ---------------------------------------------------------------- mbarrier */
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
