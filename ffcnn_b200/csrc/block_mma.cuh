@@ -51,17 +51,10 @@ __device__ __forceinline__ float4 blk_zero4() { return make_float4(0.f, 0.f, 0.f
 /* Four channels as two packed fp32 pairs (sm100.cuh: FFMA2 / FMUL2 / FADD2 do two IEEE fp32 operations per issue slot, results
  * bit-identical to the scalar instructions).  The depthwise stage is bound by instruction issue on the warps that own a unit,
  * so its 9 taps, BN and the lo half of the tf32 split run on pairs. */
-using sm100::f32x2;
-struct f4p { f32x2 a, b; };                                         /* channels (0, 1) and (2, 3) */
-__device__ __forceinline__ f4p blk_zero4p() { f4p r; r.a = 0ull; r.b = 0ull; return r; }
-__device__ __forceinline__ f4p lds128p(uint32_t addr)
-{
-    f4p v;
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.a), "=l"(v.b) : "r"(addr));
-    return v;
-}
+using sm100::f32x2; using sm100::f4p; using sm100::lds128p;
+__device__ __forceinline__ f4p blk_zero4p() { return sm100::zero4p(); }
 __device__ __forceinline__ f4p ld4p(const float *p) { const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p); f4p r; r.a = t.x; r.b = t.y; return r; }
-__device__ __forceinline__ void blk_fma4p(f4p &acc, const f4p v, const f4p w) { acc.a = sm100::f2_fma(v.a, w.a, acc.a); acc.b = sm100::f2_fma(v.b, w.b, acc.b); }
+__device__ __forceinline__ void blk_fma4p(f4p &acc, const f4p v, const f4p w) { sm100::fma4p(acc, v, w); }
 
 constexpr int BLK_THREADS = 256;
 constexpr int BLK_WARPS = BLK_THREADS / 32;

@@ -27,6 +27,15 @@ namespace ffb {
 
 constexpr int DW_THREADS = 384;
 
+/* The stencil loops keep four channels as two packed fp32 pairs (sm100.cuh: FFMA2 does two IEEE fp32 FMAs per issue slot, results
+ * bit-identical to fmaf), loaded from the staged tile with explicit 128-bit shared loads. */
+using sm100::f4p; using sm100::lds128p; using sm100::ldg128p; using sm100::fma4p; using sm100::zero4p;
+__device__ __forceinline__ float4 epilogue4p(const f4p a, const f4p s, const f4p b, int act)
+{
+    const sm100::f32x2 lo = sm100::f2_fma(a.a, s.a, b.a), hi = sm100::f2_fma(a.b, s.b, b.b);
+    return make_float4(act_apply(sm100::f2_lo(lo), act), act_apply(sm100::f2_hi(lo), act), act_apply(sm100::f2_lo(hi), act), act_apply(sm100::f2_hi(hi), act));
+}
+
 struct DwArgs {
     float *out; const float *wt, *scale, *bias;     /* wt: [FS*FS][C] tap-major */
     int N, H, W, C, OH, OW;                          /* input and output geometry (OH = H, OW = W for stride 1) */
@@ -78,7 +87,7 @@ k_dw3s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
     const int srow = IWb * a.CB;                                  /* floats per staged input row */
     const int col_off = xl * a.CB + c;                            /* top-left tap of output (yl = 0, xl) inside a stage */
 
-    float4 wv[9], sc, bi;
+    f4p wv[9], sc, bi;
     int wc0 = -1;
 
     long it = 0;
@@ -92,22 +101,22 @@ k_dw3s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
         const int ox = tx * a.TW + xl, oy0 = ty * a.TH, c0 = tc * a.CB + c;
         if (worker && c0 != wc0) {                                /* weights change only when the channel block does */
 #pragma unroll
-            for (int t = 0; t < 9; t++) wv[t] = ldg4(a.wt + t * a.C + c0);
-            sc = ldg4(a.scale + c0); bi = ldg4(a.bias + c0);
+            for (int t = 0; t < 9; t++) wv[t] = ldg128p(a.wt + t * a.C + c0);
+            sc = ldg128p(a.scale + c0); bi = ldg128p(a.bias + c0);
             wc0 = c0;
         }
         sm100::mbar_wait(full + s, ph);
         if (worker && ox < a.W) {
-            const float *col = reinterpret_cast<const float *>(smem + (size_t)s * stage_stride) + col_off;
+            const uint32_t col = sm100::smem_u32(smem + (size_t)s * stage_stride) + (uint32_t)col_off * 4;
             const int yl1 = min(yl1_tile, a.H - oy0);
             const bool two = (xl + 1 < a.TW) && (ox + 1 < a.W);
             float *dst = a.out + (((long)n * a.H + oy0) * a.W + ox) * a.C + c0;
             const long orow = (long)a.W * a.C;
-            float4 win[3][4];
+            f4p win[3][4];
             auto load_row = [&](int slot, int yrow) {
-                const float *rp = col + yrow * srow;
+                const uint32_t rp = col + (uint32_t)(yrow * srow) * 4;
 #pragma unroll
-                for (int k = 0; k < 4; k++) win[slot][k] = *reinterpret_cast<const float4 *>(rp + k * a.CB);
+                for (int k = 0; k < 4; k++) win[slot][k] = lds128p(rp + (uint32_t)(k * a.CB) * 4);
             };
             load_row(0, yl0); load_row(1, yl0 + 1);
             for (int yb = yl0; yb < yl1; yb += 3) {
@@ -116,17 +125,17 @@ k_dw3s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
                     const int yl = yb + u;
                     if (yl < yl1) {
                         load_row((u + 2) % 3, yl + 2);
-                        float4 acc0 = zero4(), acc1 = zero4();
+                        f4p acc0 = zero4p(), acc1 = zero4p();
 #pragma unroll
                         for (int j = 0; j < 3; j++)
 #pragma unroll
                             for (int k = 0; k < 3; k++) {
-                                fma4(acc0, win[(u + j) % 3][k], wv[j * 3 + k]);
-                                fma4(acc1, win[(u + j) % 3][k + 1], wv[j * 3 + k]);
+                                fma4p(acc0, win[(u + j) % 3][k], wv[j * 3 + k]);
+                                fma4p(acc1, win[(u + j) % 3][k + 1], wv[j * 3 + k]);
                             }
                         float *o = dst + yl * orow;
-                        *reinterpret_cast<float4 *>(o) = epilogue4(acc0, sc, bi, a.act);
-                        if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4(acc1, sc, bi, a.act);
+                        *reinterpret_cast<float4 *>(o) = epilogue4p(acc0, sc, bi, a.act);
+                        if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4p(acc1, sc, bi, a.act);
                     }
                 }
             }
@@ -186,7 +195,7 @@ k_dw3s2_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
     const int yl0 = ch * a.RC, yl1_tile = min(a.TH, yl0 + a.RC);
     const int srow = a.IWb * a.CB;
     const int col_off = (2 * xl) * a.CB + c;                      /* input column 2*xl of box row 0 */
-    float4 wv[9], sc, bi; int wc0 = -1;
+    f4p wv[9], sc, bi; int wc0 = -1;
 
     long it = 0;
     for (long tile = first; tile < a.ntiles; tile += step, it++) {
@@ -196,36 +205,36 @@ k_dw3s2_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
         const int ox = t.tx * a.TW + xl, oy0 = t.ty * a.TH, c0 = t.tc * a.CB + c;
         if (worker && c0 != wc0) {
 #pragma unroll
-            for (int k = 0; k < 9; k++) wv[k] = ldg4(a.wt + k * a.C + c0);
-            sc = ldg4(a.scale + c0); bi = ldg4(a.bias + c0); wc0 = c0;
+            for (int k = 0; k < 9; k++) wv[k] = ldg128p(a.wt + k * a.C + c0);
+            sc = ldg128p(a.scale + c0); bi = ldg128p(a.bias + c0); wc0 = c0;
         }
         sm100::mbar_wait(full + s, ph);
         if (worker && ox < a.OW) {
-            const float *col = reinterpret_cast<const float *>(smem + (size_t)s * stage_stride) + col_off;
+            const uint32_t col = sm100::smem_u32(smem + (size_t)s * stage_stride) + (uint32_t)col_off * 4;
             const int yl1 = min(yl1_tile, a.OH - oy0);
             const bool two = (xl + 1 < a.TW) && (ox + 1 < a.OW);
             float *dst = a.out + (((long)t.n * a.OH + oy0) * a.OW + ox) * a.C + c0;
             const long orow = (long)a.OW * a.C;
-            float4 top[5], mid[5], bot[5];
-            auto load_row = [&](float4 (&r)[5], int yrow) {
-                const float *rp = col + yrow * srow;
+            f4p top[5], mid[5], bot[5];
+            auto load_row = [&](f4p (&r)[5], int yrow) {
+                const uint32_t rp = col + (uint32_t)(yrow * srow) * 4;
 #pragma unroll
-                for (int k = 0; k < 5; k++) r[k] = *reinterpret_cast<const float4 *>(rp + k * a.CB);
+                for (int k = 0; k < 5; k++) r[k] = lds128p(rp + (uint32_t)(k * a.CB) * 4);
             };
             load_row(top, 2 * yl0);
             for (int yl = yl0; yl < yl1; yl++) {
                 load_row(mid, 2 * yl + 1);
                 load_row(bot, 2 * yl + 2);
-                float4 acc0 = zero4(), acc1 = zero4();
+                f4p acc0 = zero4p(), acc1 = zero4p();
 #pragma unroll
-                for (int k = 0; k < 3; k++) { fma4(acc0, top[k], wv[k]);     fma4(acc1, top[k + 2], wv[k]); }
+                for (int k = 0; k < 3; k++) { fma4p(acc0, top[k], wv[k]);     fma4p(acc1, top[k + 2], wv[k]); }
 #pragma unroll
-                for (int k = 0; k < 3; k++) { fma4(acc0, mid[k], wv[3 + k]); fma4(acc1, mid[k + 2], wv[3 + k]); }
+                for (int k = 0; k < 3; k++) { fma4p(acc0, mid[k], wv[3 + k]); fma4p(acc1, mid[k + 2], wv[3 + k]); }
 #pragma unroll
-                for (int k = 0; k < 3; k++) { fma4(acc0, bot[k], wv[6 + k]); fma4(acc1, bot[k + 2], wv[6 + k]); }
+                for (int k = 0; k < 3; k++) { fma4p(acc0, bot[k], wv[6 + k]); fma4p(acc1, bot[k + 2], wv[6 + k]); }
                 float *o = dst + yl * orow;
-                *reinterpret_cast<float4 *>(o) = epilogue4(acc0, sc, bi, a.act);
-                if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4(acc1, sc, bi, a.act);
+                *reinterpret_cast<float4 *>(o) = epilogue4p(acc0, sc, bi, a.act);
+                if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4p(acc1, sc, bi, a.act);
 #pragma unroll
                 for (int k = 0; k < 5; k++) top[k] = bot[k];
             }
@@ -282,31 +291,31 @@ k_dw5s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
         const int ox = t.tx * a.TW + xl, oy0 = t.ty * a.TH, c0 = t.tc * a.CB + c;
         sm100::mbar_wait(full + s, ph);
         if (worker && ox < a.W) {
-            const float *col = reinterpret_cast<const float *>(smem + (size_t)s * stage_stride) + col_off;
+            const uint32_t col = sm100::smem_u32(smem + (size_t)s * stage_stride) + (uint32_t)col_off * 4;
             const int yl1 = min(yl1_tile, a.H - oy0);
             const bool two = (xl + 1 < a.TW) && (ox + 1 < a.W);
-            float4 acc[DW5_RC][2];
+            f4p acc[DW5_RC][2];
 #pragma unroll
-            for (int r = 0; r < DW5_RC; r++) { acc[r][0] = zero4(); acc[r][1] = zero4(); }
+            for (int r = 0; r < DW5_RC; r++) { acc[r][0] = zero4p(); acc[r][1] = zero4p(); }
 #pragma unroll
             for (int j = 0; j < 5; j++) {
-                float4 w[5];
+                f4p w[5];
 #pragma unroll
-                for (int k = 0; k < 5; k++) w[k] = ldg4(a.wt + (j * 5 + k) * a.C + c0);
+                for (int k = 0; k < 5; k++) w[k] = ldg128p(a.wt + (j * 5 + k) * a.C + c0);
 #pragma unroll
                 for (int r = 0; r < DW5_RC; r++) {
                     const int yl = yl0 + r;
                     if (yl < yl1 && !(j == 0 && oy0 + yl == a.skip_row0_at)) {
-                        const float *rp = col + (yl + j) * srow;
-                        float4 v[6];
+                        const uint32_t rp = col + (uint32_t)((yl + j) * srow) * 4;
+                        f4p v[6];
 #pragma unroll
-                        for (int k = 0; k < 6; k++) v[k] = *reinterpret_cast<const float4 *>(rp + k * a.CB);
+                        for (int k = 0; k < 6; k++) v[k] = lds128p(rp + (uint32_t)(k * a.CB) * 4);
 #pragma unroll
-                        for (int k = 0; k < 5; k++) { fma4(acc[r][0], v[k], w[k]); fma4(acc[r][1], v[k + 1], w[k]); }
+                        for (int k = 0; k < 5; k++) { fma4p(acc[r][0], v[k], w[k]); fma4p(acc[r][1], v[k + 1], w[k]); }
                     }
                 }
             }
-            const float4 sc = ldg4(a.scale + c0), bi = ldg4(a.bias + c0);
+            const f4p sc = ldg128p(a.scale + c0), bi = ldg128p(a.bias + c0);
             float *dst = a.out + (((long)t.n * a.H + oy0) * a.W + ox) * a.C + c0;
             const long orow = (long)a.W * a.C;
 #pragma unroll
@@ -314,8 +323,8 @@ k_dw5s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
                 const int yl = yl0 + r;
                 if (yl < yl1) {
                     float *o = dst + yl * orow;
-                    *reinterpret_cast<float4 *>(o) = epilogue4(acc[r][0], sc, bi, a.act);
-                    if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4(acc[r][1], sc, bi, a.act);
+                    *reinterpret_cast<float4 *>(o) = epilogue4p(acc[r][0], sc, bi, a.act);
+                    if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4p(acc[r][1], sc, bi, a.act);
                 }
             }
         }

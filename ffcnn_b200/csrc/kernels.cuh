@@ -82,16 +82,19 @@ __global__ void k_input_u8(const uint8_t *__restrict__ frames, float *__restrict
  *   k_stem_u8 : net_input fused in -- reads the BGR u8 frames directly (no resize: frame size == net size) and applies
  *               (px - mean) * norm while staging, the same float arithmetic as ffcnn.c:281-283, 4x fewer input bytes.
  * ---------------------------------------------------------------------------------------------- */
-struct StemW { float w[27 * 8]; float s[8]; float b[8]; };      /* w[(c*3+ky)*3+kx][oc] */
+struct alignas(16) StemW { float w[27 * 8]; float s[8]; float b[8]; };      /* w[(c*3+ky)*3+kx][oc] */
 
 template <int TX, int TY>
 __device__ __forceinline__ void stem_compute(const float4 (*tile)[2 * TX + 1], const StemW &sw, float *__restrict__ out,
                                              long f, int OH, int OW, int ox, int oy, int act)
 {
     if (ox >= OW || oy >= OH) return;
-    float acc[8];
+    /* output channels as four packed pairs (FFMA2: two fp32 FMAs per issue slot, bit-identical to fmaf; the weight pairs come
+       from the constant bank through uniform registers, the pixel value is a broadcast operand) */
+    using sm100::f32x2; using sm100::f2_pack; using sm100::f2_fma; using sm100::f2_lo; using sm100::f2_hi;
+    f32x2 acc[4];
 #pragma unroll
-    for (int o = 0; o < 8; o++) acc[o] = 0.f;
+    for (int o = 0; o < 4; o++) acc[o] = 0ull;
     float4 p[3][3];
 #pragma unroll
     for (int j = 0; j < 3; j++)
@@ -104,14 +107,17 @@ __device__ __forceinline__ void stem_compute(const float4 (*tile)[2 * TX + 1], c
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const float v = c == 0 ? p[j][k].x : c == 1 ? p[j][k].y : p[j][k].z;
+                const float *wt = sw.w + ((c * 3 + j) * 3 + k) * 8;
 #pragma unroll
-                for (int o = 0; o < 8; o++) acc[o] = fmaf(v, sw.w[((c * 3 + j) * 3 + k) * 8 + o], acc[o]);
+                for (int o = 0; o < 4; o++) acc[o] = f2_fma(f2_pack(v, v), f2_pack(wt[2 * o], wt[2 * o + 1]), acc[o]);
             }
-    float4 r0, r1;
-    r0.x = act_apply(fmaf(acc[0], sw.s[0], sw.b[0]), act); r0.y = act_apply(fmaf(acc[1], sw.s[1], sw.b[1]), act);
-    r0.z = act_apply(fmaf(acc[2], sw.s[2], sw.b[2]), act); r0.w = act_apply(fmaf(acc[3], sw.s[3], sw.b[3]), act);
-    r1.x = act_apply(fmaf(acc[4], sw.s[4], sw.b[4]), act); r1.y = act_apply(fmaf(acc[5], sw.s[5], sw.b[5]), act);
-    r1.z = act_apply(fmaf(acc[6], sw.s[6], sw.b[6]), act); r1.w = act_apply(fmaf(acc[7], sw.s[7], sw.b[7]), act);
+    float rr[8];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        const f32x2 t = f2_fma(acc[o], f2_pack(sw.s[2 * o], sw.s[2 * o + 1]), f2_pack(sw.b[2 * o], sw.b[2 * o + 1]));
+        rr[2 * o] = act_apply(f2_lo(t), act); rr[2 * o + 1] = act_apply(f2_hi(t), act);
+    }
+    const float4 r0 = make_float4(rr[0], rr[1], rr[2], rr[3]), r1 = make_float4(rr[4], rr[5], rr[6], rr[7]);
     float4 *o = reinterpret_cast<float4 *>(out + (f * (long)OH * OW + (long)oy * OW + ox) * 8);
     o[0] = r0; o[1] = r1;
 }

@@ -48,6 +48,23 @@ __device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn
 __device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
+/* four channels as two packed pairs: (0, 1) and (2, 3) -- what one 128-bit load delivers */
+struct f4p { f32x2 a, b; };
+__device__ __forceinline__ f4p zero4p() { f4p r; r.a = 0ull; r.b = 0ull; return r; }
+__device__ __forceinline__ f4p lds128p(uint32_t addr)
+{
+    f4p v;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.a), "=l"(v.b) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ f4p ldg128p(const float *p)              /* read-only global data */
+{
+    f4p v;
+    asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(v.a), "=l"(v.b) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void fma4p(f4p &acc, const f4p v, const f4p w) { acc.a = f2_fma(v.a, w.a, acc.a); acc.b = f2_fma(v.b, w.b, acc.b); }
+
 /* ---------------------------------------------------------------- mbarrier */
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
