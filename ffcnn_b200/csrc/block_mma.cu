@@ -12,6 +12,7 @@
 #include "block_mma.h"
 #include "pw_tc.h"
 #include "block_mma.cuh"
+#include "block_ws.cuh"
 
 #include "ffb_internal.h"
 
@@ -21,7 +22,8 @@ struct BlkPlan {
     int cin, cexp, cout, S, H, W, OH, OW, res;
     int KS1, NT3, MTW, MINB, G, GC, NC, TH, TW, HH, HW, SEs, xrows, chunk_floats, occ;
     int XH, XW, xo, yo, frame;
-    int tc, nmt, tmem_cols;               /* experimental tcgen05 expand (FFCNN_BLK_TC=1): m-tiles of the x tile, TMEM columns */
+    int tc, nmt, tmem_cols;               /* tcgen05 expand: m-tiles of the x tile, TMEM columns */
+    int ws, R, XB, xbuf_floats;           /* warp-specialised kernel (block_ws.cuh): weight slots, x buffers, floats per x buffer */
     float slope1, sloped, slope3, slope_res;
     size_t smem;
     float *d_chunks, *d_sb3;
@@ -56,6 +58,21 @@ static BlkInst g_inst[] = {
 #undef INST2
 #undef INST
 #undef INST_TC
+
+/* warp-specialised kernel (block_ws.cuh): one 16-channel group per chunk, 5 stage-B warps + 3 stage-A warps */
+struct WsInst { int KS1, NT3, S, MTW; BlkKernel fn; ffb_smem_cfg configured; };
+#define INST_WS(K, N, S, M) { K, N, S, M, k_block_ws<K, N, S, M, 1>, {} }
+static WsInst g_ws[] = {
+    INST_WS(1, 1, 2, 1),                                          /* 8->32->8 s2 */
+    INST_WS(1, 1, 1, 2), INST_WS(1, 2, 1, 2),                     /* 8->48->8, 8->48->16 */
+    INST_WS(2, 2, 1, 2),                                          /* 16->96->16 */
+};
+#undef INST_WS
+static WsInst *find_ws(int KS1, int NT3, int S, int MTW)          /* MTW == 0: any */
+{
+    for (WsInst &i : g_ws) if (i.KS1 == KS1 && i.NT3 == NT3 && i.S == S && (!MTW || i.MTW == MTW)) return &i;
+    return nullptr;
+}
 
 static BlkInst *find_inst(int KS1, int NT3, int S, int MTW, int GC, int tc = 0)      /* MTW / GC == 0: any */
 {
@@ -143,6 +160,55 @@ static bool plan_tile(BlkPlan *p)
     return ok;
 }
 
+/* Tile of the warp-specialised kernel: at most WS_BW stage-B units (one per B warp), two E buffers + the x buffers + the
+ * weight slots inside half an SM's shared memory, x split + accumulators of every 96-pixel m-tile inside 256 TMEM columns.
+ * Among the feasible tiles: fewest idle B-warp lanes per output pixel, then fewest halo pixels. */
+static bool plan_ws(BlkPlan *p)
+{
+    const int S = p->S, KS1 = p->KS1, NT3 = p->NT3, G = p->G, SXs = 8 * KS1 + 4, GC = 1, NC = G;
+    if (NC < 2 || !find_ws(KS1, NT3, S, 0)) return false;
+    const int SEs = 16 * GC + (S == 1 ? 8 : 4);
+    const BlkChunk off(GC, KS1, NT3, true);
+    const int R = NC <= WS_RING ? NC : WS_RING, XB = NC >= 6 ? 2 : 3;   /* a tile's x is split three chunk steps before its first stage B */
+    int fTH = 0, fTW = 0, fGC = 0;
+    char key[64]; snprintf(key, sizeof key, "FFCNN_BLK_WSTILE_%d_%d", p->OH, p->cexp);
+    if (const char *ov = getenv(key)) sscanf(ov, "%d,%d,%d", &fTH, &fTW, &fGC);
+    double best = 1e30; bool ok = false;
+    for (int TW = 2; TW <= p->OW && TW <= 80; TW += 2) {
+        if (fTW && TW != fTW) continue;
+        for (int TH = 1; TH <= p->OH && TH <= 80; TH++) {
+            if (fTH && TH != fTH) continue;
+            for (int MTW = 1; MTW <= 2; MTW++) {
+                if (MTW == 2 && (TH & 1)) continue;
+                if (!find_ws(KS1, NT3, S, MTW)) continue;
+                const int units = MTW == 2 ? (TH / 2 * TW + 15) / 16 : (TH * TW + 15) / 16;
+                if (units > WS_BW) continue;
+                const int HH = (TH - 1) * S + 3, HW = (TW - 1) * S + 3;
+                if (TH >= p->OH && TW >= p->OW) continue;             /* frame mode is k_block_mma's */
+                if (HH > 256 || HW > 256) continue;
+                const int XP = HH * HW, nmt = (XP + WS_MROWS - 1) / WS_MROWS, xrows = 4 * WS_MROWS;   /* the kernel reads map rows of m-tile pairs */
+                const int xbuf = (XP * SXs + 31) / 32 * 32;
+                const size_t smem = 4 * (size_t)(128 + 2 * xrows + R * off.total + XB * xbuf + 2 * HH * HW * SEs + SEs) + 1024 + 128;
+                if (smem > 113 * 1024) continue;
+                int tmem_cols = 32; while (tmem_cols < nmt * (16 * KS1 + 32 * GC)) tmem_cols *= 2;
+                if (tmem_cols > 256 || nmt > 4) continue;
+                const double waste = (double)((p->OH + TH - 1) / TH * TH) * ((p->OW + TW - 1) / TW * TW) / ((double)p->OH * p->OW);
+                /* a chunk step costs the longer of one B unit and the A warps' passes over the halo (about a third of a unit per m-tile) */
+                const double step = std::max(1.0, 0.35 * nmt) + 0.08;
+                const double score = step * waste / (TH * TW) * (1.0 + 0.02 * XP / (double)(TH * TW));
+                if (score < best) {
+                    best = score; ok = true;
+                    p->GC = GC; p->NC = NC; p->SEs = SEs; p->TH = TH; p->TW = TW; p->HH = HH; p->HW = HW; p->MTW = MTW; p->MINB = 2;
+                    p->xrows = xrows; p->chunk_floats = off.total; p->smem = smem; p->occ = 2;
+                    p->XH = HH; p->XW = HW; p->frame = 0; p->xo = p->yo = 0; p->nmt = nmt; p->tmem_cols = tmem_cols;
+                    p->R = R; p->XB = XB; p->xbuf_floats = xbuf;
+                }
+            }
+        }
+    }
+    return ok;
+}
+
 BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, int act1, int actd, int act3, int res, int act_res)
 {
     if (cin < 1 || cexp < 1 || cout < 1 || cin % 4 || cexp % 4 || cout % 2 || (stride != 1 && stride != 2)) return nullptr;
@@ -177,9 +243,27 @@ BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
         p->tc = 0;                              /* the tcgen05 instances cover fewer tiles */
         if (!plan_tile(p)) { delete p; return nullptr; }
     }
+    /* warp-specialised kernel (block_ws.cuh), opt-in with FFCNN_BLK_WS=1 wherever a tile exists.  Built for the blocks whose
+       regular tile leaves three of the eight warps without a stage-B unit (the 40x40 maps); parity-green, but measured SLOWER
+       than k_block_mma on every one of them (L38: 0.124 vs 0.105 ms, profiles/r2s_block_ws.txt): the fixed roles remove the
+       barrier stalls and add instructions (one 16-channel group per chunk, 96-pixel m-tiles, per-chunk GEMM issue), and what
+       binds these kernels is instructions issued per cycle at four warps per scheduler, not the idle warps. */
+    {
+        static const int env_ws = getenv("FFCNN_BLK_WS") ? atoi(getenv("FFCNN_BLK_WS")) : 0;
+        const int units = p->MTW > 1 ? ((p->TH + 1) / 2 * p->TW + 15) / 16 : (p->TH * p->TW + 15) / 16;
+        if (env_ws > 0 && units <= 2 * WS_BW) {
+            BlkPlan w = *p;
+            w.KS1 = (cin + 7) / 8; w.NT3 = (cout + 7) / 8;
+            bool found_ws = false;
+            for (int k = w.KS1; k <= 6 && !found_ws; k++)
+                for (int n = w.NT3; n <= 6 && !found_ws; n++)
+                    if (find_ws(k, n, stride, 0)) { w.KS1 = k; w.NT3 = n; found_ws = true; }
+            if (found_ws && plan_ws(&w)) { *p = w; p->ws = 1; p->tc = 1; }
+        }
+    }
     p->num_sms = ffb_num_sms();
-    snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s tile %dx%d%s gc%d mtw%d smem %zuKB occ%d%s", cin, cexp, cout, stride, res ? "+res" : "",
-             p->TH, p->TW, p->frame ? " (frame)" : "", p->GC, p->MTW, p->smem >> 10, p->occ, p->tc ? " tcgen05-expand" : "");
+    snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s tile %dx%d%s gc%d mtw%d smem %zuKB occ%d%s%s", cin, cexp, cout, stride, res ? "+res" : "",
+             p->TH, p->TW, p->frame ? " (frame)" : "", p->GC, p->MTW, p->smem >> 10, p->occ, p->tc ? " tcgen05-expand" : "", p->ws ? " warp-specialised" : "");
     return p;
 }
 
@@ -207,9 +291,18 @@ int blk_prepare(BlkPlan *p, const float *p1, const float *pd, const float *p3, c
 
 int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st)
 {
-    BlkInst *inst = find_inst(p->KS1, p->NT3, p->S, p->MTW, p->GC, p->tc);
-    if (!inst) { ffb_set_error("block_mma: no kernel instance"); return -1; }
-    if (ffb_ensure_smem((const void *)inst->fn, p->smem, &inst->configured) != 0) return -1;
+    BlkKernel fn = nullptr;
+    if (p->ws) {
+        WsInst *wi = find_ws(p->KS1, p->NT3, p->S, p->MTW);
+        if (!wi) { ffb_set_error("block_ws: no kernel instance"); return -1; }
+        if (ffb_ensure_smem((const void *)wi->fn, p->smem, &wi->configured) != 0) return -1;
+        fn = wi->fn;
+    } else {
+        BlkInst *inst = find_inst(p->KS1, p->NT3, p->S, p->MTW, p->GC, p->tc);
+        if (!inst) { ffb_set_error("block_mma: no kernel instance"); return -1; }
+        if (ffb_ensure_smem((const void *)inst->fn, p->smem, &inst->configured) != 0) return -1;
+        fn = inst->fn;
+    }
     BlkArgs a;
     a.x = x; a.y = y; a.wchunks = p->d_chunks; a.sb3 = p->d_sb3;
     a.N = n; a.H = p->H; a.W = p->W; a.OH = p->OH; a.OW = p->OW; a.ldx = ldx; a.ldy = ldy; a.cout = p->cout;
@@ -218,6 +311,7 @@ int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
     a.NC = p->NC; a.xrows = p->xrows;
     a.nmt = p->nmt; a.tmem_cols = (uint32_t)p->tmem_cols;
     a.XH = p->XH; a.XW = p->XW; a.xo = p->xo; a.yo = p->yo; a.frame = p->frame;
+    a.R = p->R; a.XB = p->XB; a.xbuf_floats = p->xbuf_floats;
     a.inv_tpf = 1.0f / (float)(a.ntx * a.nty); a.inv_ntx = 1.0f / (float)a.ntx;
     CUtensorMap tm;
     const int SXs = 8 * p->KS1 + 4;
@@ -232,7 +326,7 @@ int blk_run(BlkPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
         a.trace = (g_blk_trace && p->cexp == tc && p->S == ts) ? g_blk_trace : nullptr;
     }
     const int grid = (int)std::min<long>(a.ntiles, (long)p->num_sms * p->occ);
-    cudaError_t e = sm100::launch_pdl(inst->fn, dim3(grid), dim3(BLK_THREADS), p->smem, st, tm, a);
+    cudaError_t e = sm100::launch_pdl(fn, dim3(grid), dim3(BLK_THREADS), p->smem, st, tm, a);
     if (e != cudaSuccess) { ffb_set_error("block_mma launch failed: %s (grid %d smem %zu)", cudaGetErrorString(e), grid, p->smem); return -1; }
     return 0;
 }

@@ -68,6 +68,7 @@ struct BlkArgs {
     int NC, xrows;
     int nmt; uint32_t tmem_cols;          /* TC: 128-pixel m-tiles of the x tile, TMEM columns to allocate (power of 2) */
     int XH, XW, xo, yo, frame;            /* x-tile box and its offset inside the halo; frame: one tile covers the whole image */
+    int R, XB, xbuf_floats;               /* k_block_ws: weight slots (all chunks resident when NC <= R), x buffers, floats per x buffer */
     float inv_tpf, inv_ntx;
     float slope1, sloped, slope3, slope_res; int res;
     long long *trace;                     /* developer timeline (-DFFB_BLK_TRACE, tools/blk_trace.py): CTA 0, warps 0 and 7 stamp clock64 per stage */
@@ -368,10 +369,14 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                         }
                         sm100::tmem_ld_wait();
                         if (mp.x >= 0) {
+                            /* pixels outside the image are zeroed with a mask, not a branch: the four float4 stay independent streams */
+                            const uint32_t msk = inside ? 0xffffffffu : 0u;
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
                                 f4p acc; acc.a = (f32x2)r[4 * j] | ((f32x2)r[4 * j + 1] << 32); acc.b = (f32x2)r[4 * j + 2] | ((f32x2)r[4 * j + 3] << 32);
-                                const float4 v = inside ? bn_act4p(acc, s1v[j], b1v[j], slope1_2) : blk_zero4();
+                                float4 v = bn_act4p(acc, s1v[j], b1v[j], slope1_2);
+                                v.x = __uint_as_float(__float_as_uint(v.x) & msk); v.y = __uint_as_float(__float_as_uint(v.y) & msk);
+                                v.z = __uint_as_float(__float_as_uint(v.z) & msk); v.w = __uint_as_float(__float_as_uint(v.w) & msk);
                                 sm100::sts128(sE_addr + mp.x + (gr * 16 + 4 * j) * 4, v);
                             }
                         }
