@@ -220,10 +220,10 @@ BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
     p->KS1 = (cin + 7) / 8; p->NT3 = (cout + 7) / 8; p->G = (cexp + 15) / 16;
     /* measured on a B200 at batch 256 (profiles/r2a_block_tc.txt, r2r_block_tc_policy.txt): with the MMAs issued from the warp
        that has no depthwise unit, the tcgen05 expand stage wins on the 96- and 224-channel blocks (L38-L57 -10 %, L58 -17 %,
-       L84-L108 -14 % against mma.sync) and on the stride-1 32-channel blocks (L12, L17 -3 %); it ties at 136 channels and
-       loses where its TMEM budget forces one CTA per SM (L22, L35) */
+       L84-L108 -14 % against mma.sync) and on the stride-1 32-channel blocks (L12, L17 -3 %); at 136 channels it tied until the
+       stage-A stores lost their branches (r2s: 0.0661 vs 0.0703 ms); it loses on the 48-channel blocks and on L22 */
     static const int env_tc = getenv("FFCNN_BLK_TC") ? atoi(getenv("FFCNN_BLK_TC")) : 0;
-    p->tc = env_tc > 0 ? 1 : env_tc < 0 ? 0 : (cexp == 96 || cexp == 224 || (cexp == 32 && stride == 1)) ? 1 : 0;
+    p->tc = env_tc > 0 ? 1 : env_tc < 0 ? 0 : (cexp == 96 || cexp == 224 || (cexp == 136 && stride == 1) || (cexp == 32 && stride == 1)) ? 1 : 0;
     /* round up to an instantiated (KS1, NT3) pair: zero-padded K / N lanes cost tensor work, not correctness */
     bool found = false;
     for (int k = p->KS1; k <= 6 && !found; k++)

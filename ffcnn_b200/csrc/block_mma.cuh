@@ -443,10 +443,13 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
                                 const int iy = q.iy0 + (mp.y & 0xffff), ix = q.ix0 + (mp.y >> 16);
                                 inside = (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W;
                             }
+                            const uint32_t msk = inside ? 0xffffffffu : 0u;        /* a mask, not a branch: the groups stay independent streams */
 #pragma unroll
                             for (int gr = 0; gr < GC; gr++) {
                                 f4p av; av.a = sm100::f2_pack(acc[gr][m][0][2 * r], acc[gr][m][0][2 * r + 1]); av.b = sm100::f2_pack(acc[gr][m][1][2 * r], acc[gr][m][1][2 * r + 1]);
-                                const float4 v = inside ? bn_act4p(av, ld4p(wt4 + off.s1 + gr * 16), ld4p(wt4 + off.b1 + gr * 16), slope1_2) : blk_zero4();
+                                float4 v = bn_act4p(av, ld4p(wt4 + off.s1 + gr * 16), ld4p(wt4 + off.b1 + gr * 16), slope1_2);
+                                v.x = __uint_as_float(__float_as_uint(v.x) & msk); v.y = __uint_as_float(__float_as_uint(v.y) & msk);
+                                v.z = __uint_as_float(__float_as_uint(v.z) & msk); v.w = __uint_as_float(__float_as_uint(v.w) & msk);
                                 sm100::sts128(sE_addr + mp.x + (gr * 16 + 4 * t) * 4, v);
                             }
                         }

@@ -993,7 +993,7 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         if (in.c % 4)
             CK(launch_pdl(k_upsample_scalar, dim3(grid_for((long)n * o.h * o.w * o.c, 256, 64)), dim3(256), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride));
         else
-        CK(launch_pdl(k_upsample, dim3(grid_for((long)n * o.h * o.w * (o.c / 4), 128, 64)), dim3(128), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride));
+        CK(launch_pdl(k_upsample, dim3(std::min(n * in.h, g_num_sms * 16)), dim3(std::min(256, (in.w * (in.c / 4) + 31) / 32 * 32)), 0, st, (const float *)in.p, o.p, n, in.h, in.w, in.c, in.ld, o.ld, 0, il->stride));
         (*launches)++;
         break;
     case LAYER_TYPE_SHORTCUT: {
