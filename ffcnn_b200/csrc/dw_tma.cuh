@@ -243,14 +243,30 @@ k_dw3s2_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
     }
 }
 
-/* Depthwise 5x5, stride 1, pad 2 (conv-v6.c:291-465).  25 weight vectors do not fit the register budget next to a 5-row
- * window, so the loop is kernel-row outer: for each kernel row j the thread keeps that row's 5 weight vectors and adds
- * its contribution to the RC x 2 output accumulators it owns (6 LDS.128 per output row and kernel row).  Accumulation
- * order stays kernel-row -> kernel-column.  skip_row0_at: conv-v6 drops kernel row 0 on output row oh-2 (422-441). */
+/* Depthwise 5x5, stride 1, pad 2 (conv-v6.c:291-465).  A work item is 2 adjacent output pixels x 2 channels (one packed fp32
+ * pair) x DW5_RC output rows; the threads of the CTA loop over the items of a tile.  Two channels instead of four is what lets
+ * the item keep ALL 25 weight pairs in registers (50) and walk the INPUT rows once: each of the DW5_RC + 4 rows is read with
+ * six 64-bit shared loads and feeds every output row it belongs to, 12 loads per output pixel pair instead of the 30 of the
+ * first version (kernel-row outer loop over a 4-channel item, which re-read every row five times and was bound by
+ * shared-memory wavefronts: 29 % of the HBM roofline).  Per output the taps are still added in the reference's order, kernel row
+ * -> kernel column (conv-v0.c:17-24).  skip_row0_at: conv-v6 drops kernel row 0 on output row oh-2 (422-441). */
 constexpr int DW5_RC = 4;
+__device__ __forceinline__ sm100::f32x2 dw5_lds64(uint32_t addr)
+{
+    sm100::f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ sm100::f32x2 dw5_ldg64(const float *p)
+{
+    sm100::f32x2 v;
+    asm("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
 __global__ void __launch_bounds__(DW_THREADS)
 k_dw5s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
 {
+    using sm100::f32x2; using sm100::f2_fma; using sm100::f2_lo; using sm100::f2_hi;
     extern __shared__ uint8_t dw_smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
     const int S = a.stages;
@@ -274,57 +290,58 @@ k_dw5s1_tma(const __grid_constant__ CUtensorMap tmIn, const DwArgs a)
     if (tid == 0)
         for (int s = 0; s < S - 1; s++) if (first + s * step < a.ntiles) issue(first + s * step, s);
 
-    const int cb4 = a.CB / 4, pairs = (a.TW + 1) / 2, per_chunk = pairs * cb4;
-    const bool worker = tid < per_chunk * a.nch;
-    const int ch = tid / per_chunk, jj0 = tid - ch * per_chunk;
-    const int xp = jj0 / cb4, c = (jj0 - xp * cb4) * 4;
-    const int xl = 2 * xp;
-    const int yl0 = ch * a.RC, yl1_tile = min(a.TH, yl0 + a.RC);   /* a.RC <= DW5_RC */
-    const int srow = a.IWb * a.CB;
-    const int col_off = xl * a.CB + c;
+    const int cb2 = a.CB / 2, pairs = (a.TW + 1) / 2;
+    const int nitems = a.nch * pairs * cb2;                       /* a.RC == DW5_RC rows per item */
+    const uint32_t srow = (uint32_t)a.IWb * a.CB * 4, spx = (uint32_t)a.CB * 4;   /* bytes per staged row / pixel */
 
     long it = 0;
     for (long tile = first; tile < a.ntiles; tile += step, it++) {
         const int s = (int)(it % S); const uint32_t ph = (uint32_t)((it / S) & 1);
         if (tid == 0) { const long nx = tile + (long)(S - 1) * step; if (nx < a.ntiles) issue(nx, (int)((it + S - 1) % S)); }
         const DwTile t = dw_decode(tile, a);
-        const int ox = t.tx * a.TW + xl, oy0 = t.ty * a.TH, c0 = t.tc * a.CB + c;
+        const int oy0 = t.ty * a.TH;
+        const uint32_t stage = sm100::smem_u32(smem + (size_t)s * stage_stride);
         sm100::mbar_wait(full + s, ph);
-        if (worker && ox < a.W) {
-            const uint32_t col = sm100::smem_u32(smem + (size_t)s * stage_stride) + (uint32_t)col_off * 4;
-            const int yl1 = min(yl1_tile, a.H - oy0);
+        for (int item = tid; item < nitems; item += DW_THREADS) {
+            const int c2 = item % cb2, rest = item / cb2, xp = rest % pairs, ch = rest / pairs;
+            const int xl = 2 * xp, ox = t.tx * a.TW + xl, c0 = t.tc * a.CB + 2 * c2;
+            const int yl0 = ch * DW5_RC, yl1 = min(min(a.TH, yl0 + DW5_RC), a.H - oy0);
+            if (ox >= a.W || yl0 >= yl1) continue;
             const bool two = (xl + 1 < a.TW) && (ox + 1 < a.W);
-            f4p acc[DW5_RC][2];
+            f32x2 w[25];
 #pragma unroll
-            for (int r = 0; r < DW5_RC; r++) { acc[r][0] = zero4p(); acc[r][1] = zero4p(); }
+            for (int k = 0; k < 25; k++) w[k] = dw5_ldg64(a.wt + k * a.C + c0);
+            const uint32_t col = stage + (uint32_t)(yl0 * a.IWb + xl) * spx + (uint32_t)c2 * 8;
+            f32x2 acc[DW5_RC][2];
 #pragma unroll
-            for (int j = 0; j < 5; j++) {
-                f4p w[5];
+            for (int r = 0; r < DW5_RC; r++) { acc[r][0] = 0ull; acc[r][1] = 0ull; }
 #pragma unroll
-                for (int k = 0; k < 5; k++) w[k] = ldg128p(a.wt + (j * 5 + k) * a.C + c0);
+            for (int iy = 0; iy < DW5_RC + 4; iy++) {             /* input row yl0 + iy of the staged box */
+                if (yl0 + (iy > 4 ? iy - 4 : 0) < yl1) {          /* some valid output row of the item uses it */
+                    f32x2 v[6];
 #pragma unroll
-                for (int r = 0; r < DW5_RC; r++) {
-                    const int yl = yl0 + r;
-                    if (yl < yl1 && !(j == 0 && oy0 + yl == a.skip_row0_at)) {
-                        const uint32_t rp = col + (uint32_t)((yl + j) * srow) * 4;
-                        f4p v[6];
+                    for (int k = 0; k < 6; k++) v[k] = dw5_lds64(col + iy * srow + k * spx);
 #pragma unroll
-                        for (int k = 0; k < 6; k++) v[k] = lds128p(rp + (uint32_t)(k * a.CB) * 4);
+                    for (int r = 0; r < DW5_RC; r++) {
+                        const int j = iy - r;                     /* kernel row of this input row for output row r (compile time) */
+                        if (j >= 0 && j < 5) {
+                            if (yl0 + r < yl1 && !(j == 0 && oy0 + yl0 + r == a.skip_row0_at)) {
 #pragma unroll
-                        for (int k = 0; k < 5; k++) { fma4p(acc[r][0], v[k], w[k]); fma4p(acc[r][1], v[k + 1], w[k]); }
+                                for (int k = 0; k < 5; k++) { acc[r][0] = f2_fma(v[k], w[j * 5 + k], acc[r][0]); acc[r][1] = f2_fma(v[k + 1], w[j * 5 + k], acc[r][1]); }
+                            }
+                        }
                     }
                 }
             }
-            const f4p sc = ldg128p(a.scale + c0), bi = ldg128p(a.bias + c0);
-            float *dst = a.out + (((long)t.n * a.H + oy0) * a.W + ox) * a.C + c0;
+            const f32x2 sc = dw5_ldg64(a.scale + c0), bi = dw5_ldg64(a.bias + c0);
+            float *dst = a.out + (((long)t.n * a.H + oy0 + yl0) * a.W + ox) * a.C + c0;
             const long orow = (long)a.W * a.C;
 #pragma unroll
             for (int r = 0; r < DW5_RC; r++) {
-                const int yl = yl0 + r;
-                if (yl < yl1) {
-                    float *o = dst + yl * orow;
-                    *reinterpret_cast<float4 *>(o) = epilogue4p(acc[r][0], sc, bi, a.act);
-                    if (two) *reinterpret_cast<float4 *>(o + a.C) = epilogue4p(acc[r][1], sc, bi, a.act);
+                if (yl0 + r < yl1) {
+                    const f32x2 o0 = f2_fma(acc[r][0], sc, bi), o1 = f2_fma(acc[r][1], sc, bi);
+                    *reinterpret_cast<float2 *>(dst + r * orow) = make_float2(act_apply(f2_lo(o0), a.act), act_apply(f2_hi(o0), a.act));
+                    if (two) *reinterpret_cast<float2 *>(dst + r * orow + a.C) = make_float2(act_apply(f2_lo(o1), a.act), act_apply(f2_hi(o1), a.act));
                 }
             }
         }

@@ -193,6 +193,42 @@ static bool dw_plan(int C, int OH, int OW, int FS, int stride, int max_rc, DwPla
     return true;
 }
 
+/* 5x5 kernel (k_dw5s1_tma): the CTA's threads loop over items of 2 px x 2 ch x DW5_RC rows, so any tile whose stage fits is
+ * legal; minimise  halo re-read  x  idle thread slots in the last pass  x  the thin-row penalty of a partial channel block. */
+static bool dw5_plan(int C, int OH, int OW, DwPlan *p)
+{
+    static const int env_kb = getenv("FFCNN_DW_STAGE_KB") ? atoi(getenv("FFCNN_DW_STAGE_KB")) : 0;
+    const size_t stage_limit = (size_t)(env_kb ? env_kb : 108) * 1024;
+    double best = 1e30; bool ok = false;
+    for (int CB = 4; CB <= C && CB <= 256; CB += 4) {
+        if (C % CB) continue;
+        for (int ntx = 1; ntx <= OW; ntx++) {
+            const int TW = (OW + ntx - 1) / ntx, pairs = (TW + 1) / 2, IWb = 2 * pairs + 4;
+            if (IWb > 256) continue;
+            for (int nty = 1; nty <= OH; nty++) {
+                const int TH = (OH + nty - 1) / nty, IHb = TH + 4;
+                if (IHb > 256 || (size_t)IWb * IHb * CB * 4 > stage_limit) continue;
+                const int nch = (TH + DW5_RC - 1) / DW5_RC, items = nch * pairs * (CB / 2);
+                const double halo = (double)IWb * IHb / ((double)TW * TH);
+                const double passes = (double)((items + DW_THREADS - 1) / DW_THREADS) * DW_THREADS / items;
+                const double rows = (double)nch * DW5_RC / TH;                   /* ragged last row chunk */
+                const double thin = (CB < C && CB * 4 < 256) ? 1.0 + 0.25 * (256.0 / (CB * 4) - 1.0) : 1.0;
+                const double score = (halo + 0.5) * (0.5 + 0.5 * passes * rows) * thin;
+                if (score < best) {
+                    best = score; ok = true;
+                    p->CB = CB; p->TW = TW; p->TH = TH; p->RC = DW5_RC; p->nch = nch; p->IWb = IWb; p->IHb = IHb;
+                    p->ntx = (OW + TW - 1) / TW; p->nty = (OH + TH - 1) / TH; p->ntc = C / CB;
+                }
+            }
+        }
+    }
+    if (!ok) return false;
+    p->stages = 2;
+    const size_t stage = (((size_t)p->IHb * p->IWb * p->CB * 4) + 127) & ~(size_t)127;
+    p->smem = p->stages * stage + 64 + 256;
+    return true;
+}
+
 typedef void (*DwKernel)(const CUtensorMap, const DwArgs);
 
 static int dw_launch(DwKernel kernel, ffb_smem_cfg *configured, const float *in, DwArgs &a, const DwPlan &pl, cudaStream_t st)
@@ -327,7 +363,7 @@ static int conv_run(ffb_conv *op, const float *in, int ldi, float *out, int ldo,
             a.act = op->act; a.skip_row0_at = skip;
             if (kind == CK_DW_S1_3 && dw_plan(op->ic, oh, ow, 3, 1, 1 << 20, &pl)) return dw_launch(k_dw3s1_tma, &cfg_s1, in, a, pl, st);
             if (kind == CK_DW3_S2 && dw_plan(op->ic, oh, ow, 3, 2, 1 << 20, &pl)) return dw_launch(k_dw3s2_tma, &cfg_s2, in, a, pl, st);
-            if (kind == CK_DW_S1_5 && dw_plan(op->ic, oh, ow, 5, 1, DW5_RC, &pl)) return dw_launch(k_dw5s1_tma, &cfg_5, in, a, pl, st);
+            if (kind == CK_DW_S1_5 && dw5_plan(op->ic, oh, ow, &pl)) return dw_launch(k_dw5s1_tma, &cfg_5, in, a, pl, st);
         }
         if (kind == CK_DW3_S2) {
             const int R = oh >= 40 ? 10 : oh;
