@@ -171,10 +171,13 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
     for (int c = 0; c < CP; c++) { A0[c] = A1[c] = B0[c] = B1[c] = C0[c] = C1[c] = 0ull; }
 #pragma unroll
     for (int k = 0; k < CIN; k++) xp0[k] = xp1[k] = 0.f;
+    float xm0[CIN], xm1[CIN];                                                   /* x of the row after next: the loads run two rows ahead of their use */
     {
         const int r = oy0 - 1; const bool rok = r >= 0;
         rb_load<CIN>(xf + ((long)max(r, 0) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
         rb_load<CIN>(xf + ((long)max(r, 0) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
+        rb_load<CIN>(xf + ((long)min(oy0, a.H - 1) * a.W + max(ix0, 0)) * CIN, in0, xm0);
+        rb_load<CIN>(xf + ((long)min(oy0, a.H - 1) * a.W + max(ix1, 0)) * CIN, in1, xm1);
     }
     /* one input row: dm = output row r-1 (gets kernel row 2 and is finished), d0 = row r (kernel row 1), dp = row r+1 (kernel row 0, first contribution) */
     auto step = [&](int r, f32x2 (&dm0)[CP], f32x2 (&dm1)[CP], f32x2 (&d00)[CP], f32x2 (&d01)[CP], f32x2 (&dp0)[CP], f32x2 (&dp1)[CP]) {
@@ -190,11 +193,11 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
             rb_taps<0, true, C0>(w, dp0, el, e0, e1);  rb_taps<0, true, C0>(w, dp1, e0, e1, er);
         };
 #pragma unroll
-        for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; }
-        {   /* prefetch the next row's x while this one is being expanded */
-            const int rn = r + 1; const bool rok = rn < a.H && rn <= oy1;
-            rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
-            rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
+        for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; xn0[k] = xm0[k]; xn1[k] = xm1[k]; }
+        {   /* prefetch x two rows ahead (ncu: with one row of lookahead a quarter of the warp samples waited for these loads) */
+            const int rn = r + 2; const bool rok = rn < a.H && rn <= oy1;
+            rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xm0);
+            rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xm1);
         }
         const bool rin = r >= 0 && r < a.H;
         chunk(std::integral_constant<int, 0>(), rin);
@@ -242,20 +245,24 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
 #pragma unroll
     for (int c = 0; c < CP; c++) A[c] = B[c] = 0ull;
     const int r_first = 2 * oy0 - 1, r_last = 2 * (oy1 - 1) + 1;
+    float xm0[CIN], xm1[CIN];                                                   /* the row after next: the loads run two rows ahead of their use */
     {
         const bool rok = r_first >= 0;
         rb_load<CIN>(xf + ((long)max(r_first, 0) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
         rb_load<CIN>(xf + ((long)max(r_first, 0) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
+        const int r2 = r_first + 1; const bool rok2 = r2 < a.H && r2 <= r_last;
+        rb_load<CIN>(xf + ((long)min(r2, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok2 && in0, xm0);
+        rb_load<CIN>(xf + ((long)min(r2, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok2 && in1, xm1);
     }
     float dummy[CIN];
 #pragma unroll
     for (int k = 0; k < CIN; k++) dummy[k] = 0.f;
-    auto fetch_row = [&](int r) {                                               /* xc <- row r, prefetch row r + 1 */
+    auto fetch_row = [&](int r) {                                               /* xc <- row r, prefetch row r + 2 */
 #pragma unroll
-        for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; }
-        const int rn = r + 1; const bool rok = rn < a.H && rn <= r_last;
-        rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
-        rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
+        for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; xn0[k] = xm0[k]; xn1[k] = xm1[k]; }
+        const int rn = r + 2; const bool rok = rn < a.H && rn <= r_last;
+        rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xm0);
+        rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xm1);
     };
     /* odd input row 2oy-1: kernel row 2 of output row oy-1 (cur) and kernel row 0 of output row oy (nxt), RB_CH channels at a time */
     auto odd_chunk = [&](auto c0, bool rin, f32x2 (&cur)[CEXP / 2], f32x2 (&nxt)[CEXP / 2]) {
