@@ -52,7 +52,7 @@ static BlkInst g_inst[] = {
        TMEM one chunk ahead of the depthwise stage): the (tile, group) shapes the plan of yolo-fastest-1.1 uses.  Selected per
        block shape where it measured faster (tc_wanted below); FFCNN_BLK_TC=1 forces it wherever an instance exists, -1 disables it. */
     INST_TC(1, 1, 1, 2, 2), INST_TC(1, 1, 2, 1, 2), INST_TC(1, 1, 1, 2, 3), INST_TC(1, 2, 1, 2, 3),
-    INST_TC(2, 2, 1, 2, 2), INST_TC(2, 3, 2, 1, 3), INST_TC(3, 3, 1, 2, 3), INST_TC(6, 6, 1, 1, 1), INST_TC(6, 6, 1, 1, 2),
+    INST_TC(2, 2, 1, 2, 2), INST_TC(2, 3, 2, 1, 3), INST_TC(3, 3, 1, 2, 3), INST_TC(3, 6, 2, 1, 1), INST_TC(3, 6, 2, 1, 3), INST_TC(6, 6, 1, 1, 1), INST_TC(6, 6, 1, 1, 2),
 };
 #undef INST3
 #undef INST2
@@ -223,7 +223,7 @@ BlkPlan *blk_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
        L84-L108 -14 % against mma.sync) and on the stride-1 32-channel blocks (L12, L17 -3 %); at 136 channels it tied until the
        stage-A stores lost their branches (r2s: 0.0661 vs 0.0703 ms); it loses on the 48-channel blocks and on L22 */
     static const int env_tc = getenv("FFCNN_BLK_TC") ? atoi(getenv("FFCNN_BLK_TC")) : 0;
-    p->tc = env_tc > 0 ? 1 : env_tc < 0 ? 0 : (cexp == 96 || cexp == 224 || (cexp == 136 && stride == 1) || (cexp == 32 && stride == 1)) ? 1 : 0;
+    p->tc = env_tc > 0 ? 1 : env_tc < 0 ? 0 : (cexp == 96 || cexp == 224 || cexp == 136 || (cexp == 32 && stride == 1)) ? 1 : 0;
     /* round up to an instantiated (KS1, NT3) pair: zero-padded K / N lanes cost tensor work, not correctness */
     bool found = false;
     for (int k = p->KS1; k <= 6 && !found; k++)

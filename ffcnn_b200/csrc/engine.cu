@@ -552,8 +552,9 @@ static int engine_find_blocks(ffb_engine *e)
         }
         /* two fused kernels: the register-resident one (block_reg.cu) for the 160x160 blocks with <= 24 expanded channels,
            the shared-memory / tensor-core one (block_mma.cu) for the rest.  fuse_block 1 (default) uses the latter only for
-           the block shapes where it beats the three separate layers on a B200 (measured, profiles/r1k_block_fusion.txt: it
-           loses on the stride-2 136-channel block); 2: every supported block; 3: block_mma only */
+           the block shapes where it beats the three separate layers on a B200 (measured: every inverted-residual chain of
+           yolo-fastest-1.1 since round 2s -- the stride-2 136-channel block L81-L83 lost by 10 % in round 1 and wins by 3 % now,
+           0.0518 vs 0.0533 ms); 2: every supported block; 3: block_mma only */
         BlkPlan *plan = nullptr; RegPlan *reg = nullptr; Blk2Plan *tc2 = nullptr;
         if (e->fuse_block != 3)
             reg = reg_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res,
@@ -564,7 +565,7 @@ static int engine_find_blocks(ffb_engine *e)
             if (tc2 && blk2_prepare(tc2, e->convs[i]->d_packed, e->convs[i + 1]->d_packed, e->convs[i + 2]->d_packed, e->stream) != 0) { blk2_plan_destroy(tc2); return -1; }
         }
         if (!reg && !tc2) {
-            const bool wanted = e->fuse_block >= 2 || a->fn == 32 || a->fn == 48 || a->fn == 96 || (a->fn == 136 && d->stride == 1) || a->fn == 224;
+            const bool wanted = e->fuse_block >= 2 || a->fn == 32 || a->fn == 48 || a->fn == 96 || a->fn == 136 || a->fn == 224;
             if (!wanted) continue;
             plan = blk_plan_create(a->c, a->fn, p->fn, d->stride, a->h, a->w, a->activation, d->activation, p->activation, sc >= 0, act_res);
             if (!plan) continue;
