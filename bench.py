@@ -343,7 +343,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     cfg, wts = fb.default_model()
-    net = fb.Net(cfg, wts if rank == 0 else None, 0, 0, device=local, max_batch=B)
+    # N > 1: the end-to-end leg may give a rank up to 1.5 x its equal shard (rate-proportional shards, see run_e2e below)
+    balance = world > 1 and os.environ.get("FFCNN_E2E_BALANCE", "1") == "1"
+    BE = (B * 3 // 2 + 7) // 8 * 8 if balance else B
+    net = fb.Net(cfg, wts if rank == 0 else None, 0, 0, device=local, max_batch=BE)
     stream = torch.cuda.Stream()            # a real (non-legacy) stream shared by torch's events and the library's launches
     torch.cuda.set_stream(stream)
     net.set_stream(stream.cuda_stream)
@@ -370,28 +373,28 @@ def main():
     NB = 4
     lo, _ = shard.shard_range(B * world, rank, world)
     if os.environ.get("BENCH_PINNED", "") == "wc":          # developer knob: write-combined pinned frames (profiles/r2h_e2e_8gpu.txt)
-        wc_ptr = fb.lib().ffb_host_alloc_pinned_wc(NB * B * NET_H * PITCH)
+        wc_ptr = fb.lib().ffb_host_alloc_pinned_wc(NB * BE * NET_H * PITCH)
         if not wc_ptr:
             raise SystemExit("bench.py: write-combined pinned allocation failed")
-        hv = np.ctypeslib.as_array((fb.C.c_uint8 * (NB * B * NET_H * PITCH)).from_address(wc_ptr)).reshape(NB, B, NET_H, PITCH)
+        hv = np.ctypeslib.as_array((fb.C.c_uint8 * (NB * BE * NET_H * PITCH)).from_address(wc_ptr)).reshape(NB, BE, NET_H, PITCH)
 
         class _HostView:                                  # host[i].data_ptr() as the pinned torch tensor offers it
             def __init__(self, base, stride): self.base, self.stride = base, stride
             def __getitem__(self, i):
                 p = self.base + i * self.stride
                 return type("P", (), {"data_ptr": staticmethod(lambda p=p: p)})
-        host = _HostView(wc_ptr, B * NET_H * PITCH)
+        host = _HostView(wc_ptr, BE * NET_H * PITCH)
         host_t = None
     else:
-        host = torch.empty((NB, B, NET_H, PITCH), dtype=torch.uint8).pin_memory()
+        host = torch.empty((NB, BE, NET_H, PITCH), dtype=torch.uint8).pin_memory()
         hv = host.numpy()
         host_t = host
     base = synth.frames_u8(16, NET_W, NET_H, seed0=0xFFC0 + 16 * rank)
     for b in range(NB):
-        for f in range(B):
+        for f in range(BE):
             hv[b, f] = base[(b * 5 + f) % 16]
             hv[b, f, f % NET_H, :8] = (lo + f + b) & 0xFF          # every frame distinct
-    dev = (host_t if host_t is not None else torch.from_numpy(np.ascontiguousarray(hv))).cuda(non_blocking=False)
+    dev = torch.from_numpy(np.ascontiguousarray(hv[:, :B])).cuda(non_blocking=False)      # the resident leg: equal shards of B frames
     frame_bytes = B * NET_H * PITCH
 
     def step_resident(i):
@@ -427,29 +430,55 @@ def main():
 
     # end to end through the public calls: pinned host frames -> decoded boxes on the host, every batch's H2D copy and
     # D2H read inside the timed region (ffb_submit_u8 / ffb_collect: the copy of batch i+1 overlaps the work on batch i)
-    def run_e2e(steps):
+    def run_e2e(steps, n=B):
         moved = 0
-        net.submit_u8(host[0].data_ptr(), B, NET_W, NET_H, PITCH)
+        net.submit_u8(host[0].data_ptr(), n, NET_W, NET_H, PITCH)
         for i in range(steps):
             if i + 1 < steps:
-                net.submit_u8(host[(i + 1) % NB].data_ptr(), B, NET_W, NET_H, PITCH)
+                net.submit_u8(host[(i + 1) % NB].data_ptr(), n, NET_W, NET_H, PITCH)
             net.collect()
             moved += net.last_d2h_bytes()
         return moved
 
+    def timed_e2e(steps, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.time()
+        e0.record(stream)
+        moved = run_e2e(steps, n)
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1), time.time() - t_wall, moved
+
     run_e2e(W)                      # W untimed warm-up steps of the same pipelined path (copy stream, staging slots, graph)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     KE = K
-    d2h = 0
-    t_wall = time.time()
-    e0.record(stream)
-    d2h = run_e2e(KE)
-    e1.record(stream)
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    wall_e2e = time.time() - t_wall
-    nboxes = sum(len(net.boxes(f)) for f in range(B))
+    ms_e2e, wall_e2e, d2h = timed_e2e(KE, B)                    # equal shards: every rank B frames per step
+    n_e2e, shards, equal_e2e = B, None, None
+    if balance:
+        # Rate-proportional shards (ffcnn_b200/shard.py::weighted_shards): on a box whose GPUs do not get equal shares of the host's
+        # memory path, equal shards run at the pace of the slowest copy.  Each rank's measured end-to-end rate with everybody
+        # running (the equal-shard loop just timed) sizes its contiguous shard of the same world x B frames; frames stay where
+        # they are, nothing goes on the wire.  Both results are reported: `e2e` = proportional shards, `e2e.equal_shards`.
+        rate = torch.tensor([B * KE / ms_e2e], dtype=torch.float64, device="cuda")
+        rates = [torch.zeros_like(rate) for _ in range(world)]
+        dist.all_gather(rates, rate)
+        shards = shard.weighted_shards(B * world, [float(r[0]) for r in rates], quantum=8, max_per_rank=BE)
+        n_e2e = shards[rank][1] - shards[rank][0]
+        t_eq = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_eq, op=dist.ReduceOp.MAX)
+        equal_e2e = {"value": world * B * KE / (float(t_eq[0]) * 1e-3), "unit": "frames/s", "ms_per_step": float(t_eq[0]) / KE,
+                     "ms_per_step_rank0": ms_e2e / KE}
+        run_e2e(max(2, W // 2), n_e2e)                          # graph + staging for the new batch size
+        # one refinement: the rates move when the shares do (a rank that copies less leaves bandwidth to its neighbours)
+        ms_c, _, _ = timed_e2e(max(5, KE // 3), n_e2e)
+        rate = torch.tensor([n_e2e * max(5, KE // 3) / ms_c], dtype=torch.float64, device="cuda")
+        dist.all_gather(rates, rate)
+        shards = shard.weighted_shards(B * world, [float(r[0]) for r in rates], quantum=8, max_per_rank=BE)
+        if shards[rank][1] - shards[rank][0] != n_e2e:
+            n_e2e = shards[rank][1] - shards[rank][0]
+        run_e2e(max(2, W // 2), n_e2e)                          # every rank takes the same path whether or not its own share moved
+        ms_e2e, wall_e2e, d2h = timed_e2e(KE, n_e2e)
+    nboxes = sum(len(net.boxes(f)) for f in range(n_e2e))
     clocks = sampler.summary() if rank == 0 else None
 
     pic_result = None
@@ -574,6 +603,14 @@ def main():
                          "by_kernel": {k: {"ms": round(v["ms"], 4), "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
                                            "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3), "layers": v["layers"]} for k, v in sorted(groups.items())}},
         }
+        if shards is not None:
+            sizes = [hi - lo for lo, hi in shards]
+            line["e2e"]["shards"] = sizes
+            line["e2e"]["h2d_bytes_per_step_by_rank"] = [n * NET_H * PITCH for n in sizes]
+            line["e2e"]["sharding"] = ("the same %d frames per step, contiguous shards sized in proportion to each rank's measured end-to-end rate "
+                                       "(ffcnn_b200/shard.py::weighted_shards; the GPUs of this box do not share the host memory path equally); "
+                                       "h2d_bytes_per_step is the mean over ranks; equal_shards = the same loop with %d frames on every rank" % (B * world, B))
+            line["e2e"]["equal_shards"] = equal_e2e
         line["parity_check"] = pc
         if pic_result is not None:
             line["e2e"]["picture_frames"] = pic_result

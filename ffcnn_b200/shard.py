@@ -14,6 +14,43 @@ def shard_range(n_frames: int, rank: int, world: int) -> tuple[int, int]:
     return rank * n_frames // world, (rank + 1) * n_frames // world
 
 
+def weighted_shards(n_frames: int, rates, quantum: int = 8, max_per_rank: int | None = None) -> list[tuple[int, int]]:
+    """Contiguous shards [lo, hi) per rank, sized in proportion to each rank's measured ingest rate (frames per unit time).
+
+    The end-to-end path of a multi-GPU box is bounded by the host->device copies, and the GPUs of one box do not all get
+    the same share of the host's memory path (profiles/r2h_e2e_8gpu.txt: GPUs 0-3 of the 8 x B200 box get 23 GB/s each when
+    all eight copy, GPUs 4-7 get 36).  Equal shards then finish at the pace of the slowest rank; shards proportional to the
+    measured rates finish together.  Frames stay contiguous and nothing goes on the wire.  Sizes are multiples of `quantum`
+    (except that the last rank absorbs n_frames % quantum), never exceed `max_per_rank`, and always sum to n_frames."""
+    world = len(rates)
+    if world < 1 or n_frames < 0 or quantum < 1 or any(not (r > 0) for r in rates):
+        raise ValueError((n_frames, list(rates), quantum))
+    cap = n_frames if max_per_rank is None else max_per_rank
+    if cap * world < n_frames:
+        raise ValueError("max_per_rank too small for n_frames")
+    units, tail = divmod(n_frames, quantum)
+    cap_u = [(cap - (tail if i == world - 1 else 0)) // quantum for i in range(world)]   # the last rank also carries the tail
+    total = float(sum(rates))
+    want = [units * r / total for r in rates]
+    size = [min(int(w), cap_u[i]) for i, w in enumerate(want)]
+    left = units - sum(size)
+    # largest remainders first; a rank at its cap passes its turn
+    order = sorted(range(world), key=lambda i: (-(want[i] - int(want[i])), i))
+    while left > 0:
+        progressed = False
+        for i in order:
+            if left > 0 and size[i] < cap_u[i]:
+                size[i] += 1; left -= 1; progressed = True
+        if not progressed:
+            raise ValueError("cannot place every frame under max_per_rank")
+    out, lo = [], 0
+    for i in range(world):
+        n = size[i] * quantum + (tail if i == world - 1 else 0)
+        out.append((lo, lo + n)); lo += n
+    assert lo == n_frames
+    return out
+
+
 class _CudaArrayView:
     """Wraps a raw device pointer so torch can view it (``__cuda_array_interface__`` v2)."""
 

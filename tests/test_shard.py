@@ -70,3 +70,35 @@ def test_bind_near_gpu_is_best_effort():
         assert os.sched_getaffinity(0) == (before if got is None else set(got))
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_weighted_shards_properties():
+    """Rate-proportional contiguous shards (the end-to-end frontend of a box whose GPUs do not share the host path equally):
+    contiguous cover of [0, n), multiples of the quantum, the cap respected, equal rates = the equal shards of shard_range,
+    faster ranks never get fewer frames, bad arguments refused."""
+    import random
+    from ffcnn_b200.shard import shard_range, weighted_shards
+    assert weighted_shards(2048, [1.0] * 8) == [shard_range(2048, r, 8) for r in range(8)]
+    got = weighted_shards(2048, [23.4] * 4 + [35.7] * 4, quantum=8, max_per_rank=384)
+    assert [hi - lo for lo, hi in got] == [200] * 4 + [312] * 4
+    rng = random.Random(7)
+    for _ in range(200):
+        world = rng.randint(1, 8)
+        q = rng.choice([1, 4, 8])
+        n = rng.randint(0, 4096)
+        rates = [rng.uniform(0.5, 4.0) for _ in range(world)]
+        cap = rng.choice([None, (n + world - 1) // world + 8 * q + q])
+        sh = weighted_shards(n, rates, quantum=q, max_per_rank=cap)
+        assert sh[0][0] == 0 and sh[-1][1] == n and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+        sizes = [hi - lo for lo, hi in sh]
+        assert all(s % q == 0 for s in sizes[:-1]) and (sizes[-1] - n % q) % q == 0
+        if cap is not None:
+            assert max(sizes) <= cap
+        else:                                            # without a cap a rank is within one quantum (+ the tail) of its exact share
+            tot = sum(rates)
+            assert all(abs(s - n * r / tot) <= q + n % q for s, r in zip(sizes, rates))
+    for bad in ((10, [], 8), (10, [1.0, 0.0], 8), (-1, [1.0], 8), (10, [1.0], 0)):
+        with pytest.raises(ValueError):
+            weighted_shards(bad[0], bad[1], quantum=bad[2])
+    with pytest.raises(ValueError):
+        weighted_shards(100, [1.0, 1.0], quantum=1, max_per_rank=40)
