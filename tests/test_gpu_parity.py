@@ -18,6 +18,7 @@ Tolerances (written here as the contract):
   * integer/byte:  net_input's u8 -> fp32 conversion is bit-exact.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -301,6 +302,18 @@ def test_dw5_quirk_on_the_smallest_maps():
         if quirk:
             exact = orc.conv_raw(x, f, iw, ih, ic, ic, 2, 1, 5, ic, 2, False)
             assert float(np.abs(got - exact).max() / np.abs(exact).max()) > 1e-3
+
+
+@pytest.mark.gpu
+def test_warp_specialised_block_kernel_opt_in():
+    """k_block_ws (block_ws.cuh: fixed stage-A / stage-B warp roles, opt-in because it measured slower) must stay correct: the fused-block
+    parity test in a child process with FFCNN_BLK_WS=1 -- the planner reads the variable once per process -- and the kernel really selected."""
+    import subprocess
+    env = dict(os.environ, FFCNN_BLK_WS="1", FFCNN_BLK_VERBOSE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-s", "-k", "test_fused_blocks_against_oracle"],
+                       capture_output=True, text=True, env=env, timeout=280, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "2 passed" in r.stdout and "warp-specialised" in (r.stdout + r.stderr)
 
 
 @pytest.mark.parametrize("fuse_block", [1, 2])
