@@ -55,6 +55,7 @@ using sm100::f32x2; using sm100::f4p; using sm100::lds128p;
 __device__ __forceinline__ f4p blk_zero4p() { return sm100::zero4p(); }
 __device__ __forceinline__ f4p ld4p(const float *p) { const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p); f4p r; r.a = t.x; r.b = t.y; return r; }
 __device__ __forceinline__ void blk_fma4p(f4p &acc, const f4p v, const f4p w) { sm100::fma4p(acc, v, w); }
+__device__ __forceinline__ f4p blk_mul4p(const f4p v, const f4p w) { f4p r; r.a = sm100::f2_mul(v.a, w.a); r.b = sm100::f2_mul(v.b, w.b); return r; }
 
 constexpr int BLK_THREADS = 256;
 constexpr int BLK_WARPS = BLK_THREADS / 32;
@@ -493,7 +494,11 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
 #pragma unroll
                             for (int h = 0; h < (QUAD ? 2 : 1); h++) {
                                 const int dy = r - h * S;                              /* tap row of this input row for quad row h */
-                                if (dy >= 0 && dy < 3) {
+                                if (dy == 0) {            /* first tap: a product, not 0 + product -- no accumulator clearing */
+                                    d[h][0] = blk_mul4p(e[0], wd[0]); d[h][1] = blk_mul4p(e[S], wd[0]);
+                                    blk_fma4p(d[h][0], e[1], wd[1]); blk_fma4p(d[h][0], e[2], wd[2]);
+                                    blk_fma4p(d[h][1], e[S + 1], wd[1]); blk_fma4p(d[h][1], e[S + 2], wd[2]);
+                                } else if (dy > 0 && dy < 3) {
                                     blk_fma4p(d[h][0], e[0], wd[dy * 3]); blk_fma4p(d[h][0], e[1], wd[dy * 3 + 1]); blk_fma4p(d[h][0], e[2], wd[dy * 3 + 2]);
                                     blk_fma4p(d[h][1], e[S], wd[dy * 3]); blk_fma4p(d[h][1], e[S + 1], wd[dy * 3 + 1]); blk_fma4p(d[h][1], e[S + 2], wd[dy * 3 + 2]);
                                 }

@@ -430,6 +430,12 @@ struct ffb_engine {
     std::vector<int> spp_at, up_into;       /* per layer: index into spps (route layers) / the route an upsample writes into, else -1 */
     std::vector<char> in_spp;               /* pool layers computed by the SPP kernel */
     int fuse_tail = 1, cand_cap = 0;
+    /* side branch (option fork_tail): the chain of convs that ends in a yolo head which is not the graph's last layer (L116-L121 of
+       yolo-fastest-1.1: five small kernels on 10x10 maps, each a single under-filled wave) runs on a second stream next to the layers
+       that follow it in program order (the upsample -> ... -> second head chain), forked after the layer both read and joined at the
+       end of the forward pass; inside the captured graph that is a fork / join of two kernel chains */
+    int fork_tail = 1, side_a = -1, side_b = -1;
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
     Tens input;
     std::vector<Buf> bufs;
     float *d_arena = nullptr; size_t arena_floats = 0;
@@ -501,6 +507,9 @@ void ffb_engine_destroy(ffb_engine *e)
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->copy_stream2) cudaStreamDestroy(e->copy_stream2);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side_stream) cudaStreamDestroy(e->side_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_side) cudaEventDestroy(e->ev_side);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -705,6 +714,36 @@ static int engine_plan(ffb_engine *e)
         }
         if (o.buf >= 0) touch(o, i);
     }
+    /* side branch: walk back from the first yolo head that has layers after it, through plain convs whose output nobody else reads;
+       the layer where the walk stops because its output has a second reader is the fork point.  Its layers run concurrently with
+       everything after the head in program order, so none of the buffers they touch may be recycled before the pass ends. */
+    e->side_a = e->side_b = -1;
+    if (fuse && e->fork_tail) {
+        const std::vector<int> readers = count_readers(net);
+        for (int y = 2; y + 1 < L && e->side_a < 0; y++) {
+            if (net->layer_list[y].type != LAYER_TYPE_YOLO || net->layer_list[y + 1].type != LAYER_TYPE_ROUTE) continue;
+            auto plain = [&](int k) {
+                return k >= 1 && net->layer_list[k].type == LAYER_TYPE_CONV && e->blk_at[k] < 0 && !e->in_block[k] && e->fuse_sc[k] < 0 &&
+                       net->layer_list[k - 1].type != LAYER_TYPE_ROUTE && net->layer_list[k - 1].type != LAYER_TYPE_DROPOUT;
+            };
+            int a = y;
+            while (plain(a - 1) && (a == y || readers[a - 1] == 1)) a--;       /* layer a - 1 joins while its output feeds only layer a (the head feeds the yolo layer) */
+            if (a < y && plain(a) && readers[a - 1] > 1 && y - a >= 2) {
+                bool closed = true;                                              /* nothing after the head reads a tensor of the branch */
+                for (int j = y + 1; j < L && closed; j++) {
+                    const LAYER *jl = net->layer_list + j;
+                    if (jl->type != LAYER_TYPE_ROUTE && j > 0) { const int q = producer_of(net, j - 1); if (q >= a && q < y) closed = false; }
+                    for (int d = 0; d < jl->depend_num; d++) { const int q = producer_of(net, jl->depend_list[d]); if (q >= a && q < y) closed = false; }
+                }
+                if (closed) { e->side_a = a; e->side_b = y; }
+            }
+        }
+        if (e->side_a >= 0)
+            for (int i = e->side_a; i <= e->side_b; i++) {
+                if (e->outs[i].buf >= 0) bufs[e->outs[i].buf].last = 1 << 30;
+                if (in_of(i).buf >= 0) bufs[in_of(i).buf].last = 1 << 30;
+            }
+    }
     if (e->keep_all) for (Buf &b : bufs) b.last = 1 << 30;
     /* greedy best-fit over a free list, in creation order */
     struct Free { size_t off, len; };
@@ -787,6 +826,8 @@ int ffb_net_attach(NET *net, int device, int max_batch)
     e = new ffb_engine(); e->net = fn; e->device = device; e->max_batch = max_batch;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; ffb_set_error("cudaStreamCreate failed"); return -1; }
     e->stream = e->own_stream;
+    if (cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming) != cudaSuccess) { ffb_engine_destroy(e); ffb_set_error("side stream / events: creation failed"); return -1; }
     fn->engine = e;
     if (engine_attach_body(e, net) != 0) {                   /* never leave a half-initialised engine behind */
         ffb_engine_destroy(e); fn->engine = nullptr;
@@ -805,6 +846,7 @@ static int engine_attach_body(ffb_engine *e, NET *net)
     if ((env = getenv("FFCNN_DW_MODE")))   e->dw_mode = atoi(env);
     if ((env = getenv("FFCNN_PDL")))       sm100::g_ffb_pdl = atoi(env);
     if ((env = getenv("FFCNN_FUSE_BLOCK"))) e->fuse_block = atoi(env);
+    if ((env = getenv("FFCNN_FORK_TAIL"))) e->fork_tail = atoi(env);
     if ((env = getenv("FFCNN_BLK2")))      e->blk2 = atoi(env);
     CK(cudaMalloc(&e->d_packed, std::max(1, net->weight_size) * sizeof(float)));
     CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
@@ -869,6 +911,7 @@ int ffb_set_option(NET *net, const char *name, int value)
     else if (!strcmp(name, "fuse_block")) { reweight = e->fuse_block != value; e->fuse_block = value; }
     else if (!strcmp(name, "blk2"))      { reweight = e->blk2 != value; e->blk2 = value; }
     else if (!strcmp(name, "fuse_tail")) { if (e->fuse_tail != value) e->plan_dirty = true; e->fuse_tail = value; }
+    else if (!strcmp(name, "fork_tail")) { if (e->fork_tail != value) e->plan_dirty = true; e->fork_tail = value; }
     else if (!strcmp(name, "cand_cap")) { e->cand_cap = value; for (ffb_engine::DetSet &d : e->det) d.want = 0; }   /* test hook: initial candidate capacity */
     else { ffb_set_error("unknown option '%s'", name); return -1; }
     if (reweight) {
@@ -895,6 +938,8 @@ int ffb_get_option(NET *net, const char *name)
     if (!strcmp(name, "fuse_block")) return e->fuse_block;
     if (!strcmp(name, "blk2")) return e->blk2;
     if (!strcmp(name, "fuse_tail")) return e->fuse_tail;
+    if (!strcmp(name, "fork_tail")) return e->fork_tail;
+    if (!strcmp(name, "side_branch")) return e->side_a >= 0 ? e->side_a * 1000 + e->side_b : -1;
     if (!strcmp(name, "blocks")) return (int)e->blocks.size();
     if (!strcmp(name, "max_batch")) return e->max_batch;
     if (!strcmp(name, "batch")) return e->batch;
@@ -1076,7 +1121,16 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
 static int run_all(ffb_engine *e, cudaStream_t st, int first = 0)
 {
     int launches = first;
-    for (int i = first; i < e->net->pub.layer_num; i++) if (run_layer(e, i, st, &launches) != 0) return -1;
+    const bool side = e->side_a > first && e->side_stream;
+    for (int i = first; i < e->net->pub.layer_num; i++) {
+        cudaStream_t s = st;
+        if (side && i >= e->side_a && i <= e->side_b) {
+            if (i == e->side_a) { CK(cudaEventRecord(e->ev_fork, st)); CK(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0)); }
+            s = e->side_stream;
+        }
+        if (run_layer(e, i, s, &launches) != 0) return -1;
+    }
+    if (side) { CK(cudaEventRecord(e->ev_side, e->side_stream)); CK(cudaStreamWaitEvent(st, e->ev_side, 0)); }
     e->launches = launches;
     return 0;
 }
