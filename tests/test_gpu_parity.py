@@ -242,6 +242,30 @@ def test_liveness_arena_gives_same_heads_as_keep_all(assets):
     assert res[0] == res[1]
 
 
+def test_forked_tail_is_found_and_changes_nothing(assets):
+    """fork_tail: the conv chain of the first yolo head (L116-L121) runs on a second stream beside the layers that follow it, inside
+    the captured graph and in eager mode.  Same kernels, same operands: boxes and heads must be bit-identical with the fork off,
+    over several replays of the graph (a buffer recycled too early between the two chains would show up as a difference)."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    s2f = synth.shifted_frames_from(img, w, h, 16)
+    res = []
+    for fork in (1, 0):
+        for graph in (1, 0):
+            net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=16)
+            net.set_option("fork_tail", fork)
+            net.set_option("graph", graph)
+            out = []
+            for rep in range(3):
+                net.detect_batch_u8(s2f, 16, 320, 320, 960)
+                out.append([net.boxes(f).tobytes() for f in range(16)] + [net.layer_output(120, f).tobytes() for f in (0, 15)] + [net.layer_output(129, f).tobytes() for f in (0, 15)])
+            assert out[0] == out[1] == out[2]
+            assert (net.get_option("side_branch") == 116 * 1000 + 121) == bool(fork)
+            res.append(out[0])
+            net.close()
+    assert res[0] == res[1] == res[2] == res[3]
+
+
 def test_dw5_exact_mode_matches_conv_v0(assets, oracle_layers):
     cfg, wts, bmp = assets
     img, w, h = ref.load_bmp(bmp)
