@@ -51,7 +51,8 @@ static BlkInst g_inst[] = {
     /* expand GEMM on tcgen05 (x split hi/lo into TMEM as the A operand, W1 chunk as SWIZZLE_128B B sub-tiles, accumulators in
        TMEM one chunk ahead of the depthwise stage): the (tile, group) shapes the plan of yolo-fastest-1.1 uses.  Selected per
        block shape where it measured faster (tc_wanted below); FFCNN_BLK_TC=1 forces it wherever an instance exists, -1 disables it. */
-    INST_TC(1, 1, 1, 2, 2), INST_TC(1, 1, 2, 1, 2), INST_TC(1, 1, 1, 2, 3), INST_TC(1, 2, 1, 2, 3),
+    INST_TC(1, 1, 1, 2, 2), INST_TC(1, 1, 1, 2, 1), INST_TC(1, 1, 1, 4, 2), INST_TC(1, 1, 2, 1, 2), INST_TC(1, 1, 1, 2, 3), INST_TC(1, 2, 1, 2, 3),
+    INST_TC(2, 2, 1, 2, 1), INST_TC(2, 2, 1, 2, 3), INST_TC(2, 2, 1, 1, 2), INST_TC(3, 3, 1, 2, 1), INST_TC(3, 3, 1, 1, 3),
     INST_TC(2, 2, 1, 2, 2), INST_TC(2, 3, 2, 1, 3), INST_TC(3, 3, 1, 2, 3), INST_TC(3, 6, 2, 1, 1), INST_TC(3, 6, 2, 1, 3), INST_TC(6, 6, 1, 1, 1), INST_TC(6, 6, 1, 1, 2),
 };
 #undef INST3
@@ -99,7 +100,7 @@ static bool plan_tile(BlkPlan *p)
            model below covers every other shape */
         static const struct { int oh, ow, cexp, s, th, tw, gc; } best_tiles[] = {
             { 80, 80, 32, 1, 16, 16, 2 }, { 40, 40, 32, 2, 4, 20, 2 }, { 40, 40, 48, 1, 8, 20, 3 }, { 40, 40, 96, 1, 8, 20, 2 },
-            { 20, 20, 96, 2, 10, 10, 3 }, { 20, 20, 136, 1, 10, 20, 3 },
+            { 20, 20, 96, 2, 10, 10, 3 }, { 20, 20, 136, 1, 10, 20, 1 },     /* r2v sweep: one group per chunk fits two CTAs per SM (0.0597 vs 0.0638 ms) */
         };
         for (const auto &b : best_tiles)
             if (b.oh == p->OH && b.ow == p->OW && b.cexp == p->cexp && b.s == S) { fTH = b.th; fTW = b.tw; fGC = b.gc; }

@@ -394,6 +394,15 @@ static int stem_run_u8(ffb_conv *op, const unsigned char *frames, int pitch, flo
                        const float *mean, const float *norm, cudaStream_t st)
 {
     const int oh = conv_out_dim(ih, 3, 1, 2), ow = conv_out_dim(iw, 3, 1, 2);
+    /* two output pixels per thread with word-wise staging when rows can be read as aligned 32-bit words (FFCNN_STEM_X2=0: the
+       one-pixel kernel) */
+    static const int x2 = getenv("FFCNN_STEM_X2") ? atoi(getenv("FFCNN_STEM_X2")) : 1;
+    if (x2 && iw % 4 == 0 && pitch % 4 == 0 && ((uintptr_t)frames & 3) == 0) {
+        /* tile sweep (r2v, batch 256, ms): 16x8 threads 0.111 | 40x4 0.113 | 20x8 0.118 | 40x2 0.124 | 20x4 0.126 | 40x8 0.135; one-pixel kernel 0.140 */
+        dim3 grid((ow + 31) / 32, (oh + 7) / 8, n), block(16, 8);
+        CK(launch_pdl(k_stem_u8x2<16, 8>, grid, block, 0, st, (const uint8_t *)frames, pitch, out, op->stemw, ih, iw, oh, ow, op->act, mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]));
+        return 0;
+    }
     dim3 grid((ow + 31) / 32, (oh + 7) / 8, n), block(32, 8);
     CK(launch_pdl(k_stem_u8<32, 8>, grid, block, 0, st, (const uint8_t *)frames, pitch, out, op->stemw, ih, iw, oh, ow, op->act, mean[0], mean[1], mean[2], norm[0], norm[1], norm[2]));
     return 0;

@@ -183,6 +183,113 @@ k_stem_u8(const uint8_t *__restrict__ frames, int pitch, float *__restrict__ out
     stem_compute<TX, TY>(tile, sw, out, f, OH, OW, ox0 + threadIdx.x, oy0 + threadIdx.y, act);
 }
 
+/* k_stem_u8x2: the u8 stem with two output pixels per thread and word-wise staging (round 2v).  ncu on k_stem_u8 (r2t): 590
+ * instructions per output pixel, issue-bound, 40 % of them the staging -- three byte loads, three I2F and ~10 index / predicate
+ * instructions per input pixel, 4.3 input pixels per output.  Here
+ *   - a tile row is fetched as aligned 32-bit words (the row of input pixels 2*ox0-1 ... starts one byte after a 4-byte boundary
+ *     whenever the tile's first output column is even, which the launcher guarantees together with a 4-byte aligned frame pointer
+ *     and pitch); a byte becomes a float by PRMT into the mantissa of 2^23 and one subtraction (exact, = (float)byte, no
+ *     conversion pipe), then (f - mean) * norm exactly as ffcnn.c:281-283;
+ *   - a thread produces two adjacent output pixels: every weight pair fetched from the constant bank feeds two FFMA2, the 3x5 input
+ *     window is 15 shared loads for two pixels instead of 18.
+ * Accumulation order per output stays channel -> ky -> kx (conv-v0.c:16-25): results are bit-identical to k_stem_u8. */
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY, TX * TY <= 160 ? 5 : 2)
+k_stem_u8x2(const uint8_t *__restrict__ frames, int pitch, float *__restrict__ out, const __grid_constant__ StemW sw,
+            int H, int W, int OH, int OW, int act, float m0, float m1, float m2, float n0, float n1, float n2)
+{
+    using sm100::f32x2; using sm100::f2_pack; using sm100::f2_fma; using sm100::f2_lo; using sm100::f2_hi;
+    pdl_trigger(); pdl_wait();
+    constexpr int OWT = 2 * TX, IW = 2 * OWT + 1, IH = 2 * TY + 1, NT = TX * TY;
+    constexpr int GPR = (IW - 1) / 4, NG = GPR * IH;                /* 4-pixel groups per tile row (tile pixels 1 .. IW-1), per tile */
+    /* tile pixel px of row ty lives at tile[ty][px & 3][px >> 2]: a thread stages / reads pixels 4 apart, so consecutive threads touch
+       consecutive float4 of one plane (with a plain [IH][IW] tile every 128-bit access was a 4-way bank conflict and the kernel lost 40 %) */
+    __shared__ float4 tile[IH][4][GPR + 1];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int ox0 = blockIdx.x * OWT, oy0 = blockIdx.y * TY;
+    const long f = blockIdx.z;
+    const uint8_t *img = frames + f * (long)H * pitch;
+    const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+    /* tile pixel 1 = image pixel 2*ox0 starts at byte 6*ox0 of its row: 4-byte aligned (ox0 is a multiple of 2*TX), so tile pixels
+       1+4g .. 4+4g are three aligned words [B0 G0 R0 B1][G1 R1 B2 G2][R2 B3 G3 R3]; W % 4 == 0 puts a group wholly inside or outside */
+    constexpr int NIT = (NG + NT - 1) / NT;
+    uint32_t w0[NIT], w1[NIT], w2[NIT]; bool ok[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {                              /* all loads of this thread are issued before the first is consumed */
+        const int g = tid + it * NT, ty = g / GPR, gx = g - ty * GPR, iy = iy0 + ty, ix = ix0 + 1 + 4 * gx;
+        ok[it] = g < NG && (unsigned)iy < (unsigned)H && ix + 3 < W;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (long)(ok[it] ? iy : 0) * pitch + 3 * (ok[it] ? ix : 0));
+        w0[it] = ok[it] ? __ldg(src) : 0u; w1[it] = ok[it] ? __ldg(src + 1) : 0u; w2[it] = ok[it] ? __ldg(src + 2) : 0u;
+    }
+    /* a byte becomes a float by PRMT into the mantissa of 2^23 and one subtraction: exact, = (float)byte, no conversion pipe */
+    auto cvt = [&](uint32_t word, int k, float mean, float norm) {
+        return (__uint_as_float(__byte_perm(word, 0x4b000000u, 0x7540 + k)) - 8388608.0f - mean) * norm;
+    };
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int g = tid + it * NT, ty = g / GPR, gx = g - ty * GPR;
+        if (g < NG) {
+            if (ok[it]) {
+                tile[ty][1][gx] = make_float4(cvt(w0[it], 2, m0, n0), cvt(w0[it], 1, m1, n1), cvt(w0[it], 0, m2, n2), 0.f);
+                tile[ty][2][gx] = make_float4(cvt(w1[it], 1, m0, n0), cvt(w1[it], 0, m1, n1), cvt(w0[it], 3, m2, n2), 0.f);
+                tile[ty][3][gx] = make_float4(cvt(w2[it], 0, m0, n0), cvt(w1[it], 3, m1, n1), cvt(w1[it], 2, m2, n2), 0.f);
+                tile[ty][0][gx + 1] = make_float4(cvt(w2[it], 3, m0, n0), cvt(w2[it], 2, m1, n1), cvt(w2[it], 1, m2, n2), 0.f);
+            } else {
+                tile[ty][1][gx] = tile[ty][2][gx] = tile[ty][3][gx] = tile[ty][0][gx + 1] = zero4();
+            }
+        }
+    }
+    if (tid < IH) {                                                 /* tile pixel 0 = image pixel 2*ox0 - 1, the left halo column */
+        const int iy = iy0 + tid;
+        float4 v = zero4();
+        if ((unsigned)iy < (unsigned)H && ix0 >= 0) {
+            const uint8_t *px = img + (long)iy * pitch + 3 * ix0;
+            v.x = ((float)__ldg(px + 2) - m0) * n0; v.y = ((float)__ldg(px + 1) - m1) * n1; v.z = ((float)__ldg(px) - m2) * n2;
+        }
+        tile[tid][0][0] = v;
+    }
+    __syncthreads();
+    const int ox = ox0 + 2 * threadIdx.x, oy = oy0 + threadIdx.y;
+    if (ox >= OW || oy >= OH) return;
+    f32x2 acc[2][4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) { acc[0][o] = 0ull; acc[1][o] = 0ull; }
+    float4 p[3][5];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int k = 0; k < 5; k++) p[j][k] = tile[2 * threadIdx.y + j][k & 3][threadIdx.x + (k >> 2)];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float v0 = c == 0 ? p[j][k].x : c == 1 ? p[j][k].y : p[j][k].z;
+                const float v1 = c == 0 ? p[j][k + 2].x : c == 1 ? p[j][k + 2].y : p[j][k + 2].z;
+                const float *wt = sw.w + ((c * 3 + j) * 3 + k) * 8;
+#pragma unroll
+                for (int o = 0; o < 4; o++) {
+                    const f32x2 wp = f2_pack(wt[2 * o], wt[2 * o + 1]);
+                    acc[0][o] = f2_fma(f2_pack(v0, v0), wp, acc[0][o]);
+                    acc[1][o] = f2_fma(f2_pack(v1, v1), wp, acc[1][o]);
+                }
+            }
+    float4 *dst = reinterpret_cast<float4 *>(out + (f * (long)OH * OW + (long)oy * OW + ox) * 8);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        if (ox + q < OW) {
+            float rr[8];
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                const f32x2 t = f2_fma(acc[q][o], f2_pack(sw.s[2 * o], sw.s[2 * o + 1]), f2_pack(sw.b[2 * o], sw.b[2 * o + 1]));
+                rr[2 * o] = act_apply(f2_lo(t), act); rr[2 * o + 1] = act_apply(f2_hi(t), act);
+            }
+            dst[2 * q] = make_float4(rr[0], rr[1], rr[2], rr[3]); dst[2 * q + 1] = make_float4(rr[4], rr[5], rr[6], rr[7]);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Depthwise FSxFS, stride 1, pad FS/2 (conv-v6.c:96-229 for 3x3, 291-465 for 5x5).
  * Thread = one float4 of the flattened row (pixel x, channels c..c+3); it walks R output rows downwards
