@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
     if (TC) sm100::tc_fence_before_sync();
     __syncthreads();
     if (TC) sm100::tc_fence_after_sync();
-    pdl_trigger(); pdl_wait();
+    pdl_trigger();                                    /* the wait comes after the first weight chunk is requested (weights do not depend on the previous kernel) */
     const f32x2 slope1_2 = sm100::f2_pack(a.slope1, a.slope1), sloped2 = sm100::f2_pack(a.sloped, a.sloped);
     /* ---- TC: expand GEMM on tcgen05.  TMEM columns: per 128-pixel m-tile mt the A operand [x_hi (KP cols) | x_lo (KP cols)]
        at mt * 2KP, then the accumulators D[mt][buf] (16*GC cols each, double buffered over chunks) ---- */
@@ -274,7 +274,9 @@ __global__ void __launch_bounds__(BLK_THREADS, MINB) k_block_mma(const __grid_co
         sm100::mbar_arrive_expect_tx(full_w + wb, w_bytes);
         bulk_load(sW_addr + (uint32_t)wb * w_bytes, a.wchunks + (long)c * off.total, w_bytes, full_w + wb);
     };
-    if (tid == 0 && (long)blockIdx.x < a.ntiles) { load_x(blockIdx.x, 0); load_chunk(0, 0); }
+    if (tid == 0 && (long)blockIdx.x < a.ntiles) load_chunk(0, 0);
+    pdl_wait();                                       /* from here on the kernel touches the previous layer's output */
+    if (tid == 0 && (long)blockIdx.x < a.ntiles) load_x(blockIdx.x, 0);
     /* weights: with a single chunk they stay resident for the whole kernel; otherwise the two-slot ring runs continuously
        across tiles (chunk (c+1) % NC is requested while chunk c is being used), so no tile ever waits for L2 */
     const bool w_resident = a.NC == 1;

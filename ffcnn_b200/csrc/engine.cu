@@ -72,7 +72,7 @@ int ffb_ensure_smem(const void *func, size_t smem, ffb_smem_cfg *cfg)
     return 0;
 }
 #define g_num_sms (ffb_num_sms())
-namespace sm100 { int g_ffb_pdl = 0; }     /* programmatic dependent launch between the kernels of a forward pass: FFCNN_PDL=1 enables. Measured (r1g): back-to-back launches of one layer gain 6 %, the captured graph gains nothing (3.44 vs 3.40 ms) -- the big CTAs (>= 120 KB smem) cannot co-reside with their predecessor -- so it stays off by default. */
+namespace sm100 { int g_ffb_pdl = 1; }     /* programmatic dependent launch between the kernels of a forward pass (FFCNN_PDL=0 disables): every kernel triggers at its top and waits after its prologue (barrier init, TMEM allocation, clearing E, weight prefetch), so the prologue of kernel n+1 runs under the tail of kernel n wherever an SM has room.  Round 1 measured nothing in the captured graph (3.44 vs 3.40 ms) and left it off; with 41 shorter launches it is worth 1.6 % (r2v: 2.213 -> 2.177 ms).  ffb_layer_times switches it off: per-kernel times are those of isolated kernels. */
 using sm100::launch_pdl;
 
 static inline int grid_for(long total, int block, int waves = 8)
@@ -1486,6 +1486,7 @@ int ffb_layer_times(NET *net, float *ms, int nlayers, int reps, int flush_l2)
     if (flush_l2 && !e->d_flush) { e->flush_floats = (size_t)64 << 20; CK(cudaMalloc(&e->d_flush, e->flush_floats * sizeof(float))); }
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     const int L = std::min(nlayers, net->layer_num);
+    struct PdlOff { int saved; PdlOff() : saved(sm100::g_ffb_pdl) { sm100::g_ffb_pdl = 0; } ~PdlOff() { sm100::g_ffb_pdl = saved; } } pdl_off;   /* isolated-kernel times */
     for (int i = 0; i < L; i++) {
         int launches = 0;
         if (run_layer(e, i, e->stream, &launches) != 0) return -1;          /* untimed warm-up */
