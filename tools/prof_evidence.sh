@@ -15,6 +15,7 @@ for spec in "k_block_mma:6:blockmma_L38" "k_block_mma:0:blockmma_L12" "k_block_m
   bash tools/ncu_any.sh $k $s ${TAG}_ncu_$name > /dev/null 2>&1
   (python tools/ncu_raw.py gpurun_out/${TAG}_ncu_$name.ncu-rep; python tools/ncu_hot.py gpurun_out/${TAG}_ncu_$name.ncu-rep 12) > gpurun_out/${TAG}_ncu_$name.txt 2>&1
   head -3 gpurun_out/${TAG}_ncu_$name.txt
+  rm -f gpurun_out/${TAG}_ncu_$name.ncu-rep          # gpurun copies back at most 64 MiB: the text summaries travel, the reports do not
 done
 rm -f gpurun_out/${TAG}_ncu_*.log
 ls gpurun_out | head -60
