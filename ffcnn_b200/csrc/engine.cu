@@ -200,13 +200,16 @@ static bool dw5_plan(int C, int OH, int OW, DwPlan *p)
     static const int env_kb = getenv("FFCNN_DW_STAGE_KB") ? atoi(getenv("FFCNN_DW_STAGE_KB")) : 0;
     const size_t stage_limit = (size_t)(env_kb ? env_kb : 108) * 1024;
     double best = 1e30; bool ok = false;
+    int fCB = 0, fTW = 0, fTH = 0;                                   /* developer override for tile sweeps: FFCNN_DW5_TILE_<C>="CB,TW,TH" */
+    { char key[48]; snprintf(key, sizeof key, "FFCNN_DW5_TILE_%d", C); if (const char *ov = getenv(key)) sscanf(ov, "%d,%d,%d", &fCB, &fTW, &fTH); }
     for (int CB = 4; CB <= C && CB <= 256; CB += 4) {
-        if (C % CB) continue;
+        if (C % CB || (fCB && CB != fCB)) continue;
         for (int ntx = 1; ntx <= OW; ntx++) {
             const int TW = (OW + ntx - 1) / ntx, pairs = (TW + 1) / 2, IWb = 2 * pairs + 4;
             if (IWb > 256) continue;
             for (int nty = 1; nty <= OH; nty++) {
                 const int TH = (OH + nty - 1) / nty, IHb = TH + 4;
+                if ((fTW && TW != fTW) || (fTH && TH != fTH)) continue;
                 if (IHb > 256 || (size_t)IWb * IHb * CB * 4 > stage_limit) continue;
                 const int nch = (TH + DW5_RC - 1) / DW5_RC, items = nch * pairs * (CB / 2);
                 const double halo = (double)IWb * IHb / ((double)TW * TH);
