@@ -8,8 +8,9 @@
 #include <cuda_runtime.h>
 #include "block_reg.h"
 #include "block_reg.cuh"
+#include "stem_block.cuh"
+#include "ffb_internal.h"
 
-extern "C" void ffb_set_error(const char *fmt, ...);
 
 using namespace ffb;
 
@@ -83,5 +84,27 @@ int reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
         if (e == cudaSuccess) e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 3>, grid, block, 0, st, p->u.w488[2], a);
     }
     if (e != cudaSuccess) { ffb_set_error("block_reg launch failed: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+
+/* ---- stem + first block as one kernel (stem_block.cuh) ---- */
+int reg_stem_ok(const RegPlan *p, int ih, int iw, int pitch, const void *frames)
+{
+    return p && p->kind == 0 && p->H == (ih - 3 + 2) / 2 + 1 && p->W == (iw - 3 + 2) / 2 + 1 && iw % 4 == 0 && pitch % 4 == 0 && ((uintptr_t)frames & 3) == 0;
+}
+
+int reg_run_stem(RegPlan *p, const void *stemw, int act0, const unsigned char *frames, int pitch, float *y, int ldy, int n, int ih, int iw,
+                 const float *mean, const float *norm, cudaStream_t st)
+{
+    if (!reg_stem_ok(p, ih, iw, pitch, frames) || ldy != 4) { ffb_set_error("stem_block: shape not supported"); return -1; }
+    static ffb_smem_cfg configured;
+    if (ffb_ensure_smem((const void *)k_stem_block, SB_SMEM, &configured) != 0) return -1;
+    StemBlockArgs a;
+    a.frames = frames; a.pitch = pitch; a.y = y; a.H = ih; a.W = iw; a.OH = p->H; a.OW = p->W;
+    a.act0 = act0; a.m0 = mean[0]; a.m1 = mean[1]; a.m2 = mean[2]; a.n0 = norm[0]; a.n1 = norm[1]; a.n2 = norm[2];
+    a.slope1 = p->slope1; a.sloped = p->sloped; a.slope3 = p->slope3;
+    const dim3 grid((unsigned)((p->W + SB_TXO - 1) / SB_TXO), (unsigned)((p->H + SB_TYO - 1) / SB_TYO), (unsigned)n);
+    cudaError_t e = sm100::launch_pdl(k_stem_block, grid, dim3(SB_THREADS), SB_SMEM, st, *reinterpret_cast<const StemW *>(stemw), p->u.w884, a);
+    if (e != cudaSuccess) { ffb_set_error("stem_block launch failed: %s", cudaGetErrorString(e)); return -1; }
     return 0;
 }

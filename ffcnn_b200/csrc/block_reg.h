@@ -12,3 +12,9 @@ void     reg_plan_destroy(RegPlan *p);
 int      reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st);
 const char *reg_describe(const RegPlan *p);
 int      reg_launches(const RegPlan *p);          /* kernels one reg_run enqueues (3 for the sliced 24-channel block) */
+
+/* The stem (3x3 s2 conv on the u8 frames, net_input fused) and the 8->8->4 block as one kernel (stem_block.cuh): `stemw` points to the
+ * stem's StemW parameter block, y is the block's output tensor.  reg_stem_ok: the plan is that block and the frames qualify. */
+int      reg_stem_ok(const RegPlan *p, int ih, int iw, int pitch, const void *frames);
+int      reg_run_stem(RegPlan *p, const void *stemw, int act0, const unsigned char *frames, int pitch, float *y, int ldy, int n, int ih, int iw,
+                      const float *mean, const float *norm, cudaStream_t st);

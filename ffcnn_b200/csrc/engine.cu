@@ -447,6 +447,8 @@ struct ffb_engine {
        that follow it in program order (the upsample -> ... -> second head chain), forked after the layer both read and joined at the
        end of the forward pass; inside the captured graph that is a fork / join of two kernel chains */
     int fork_tail = 1, side_a = -1, side_b = -1;
+    /* stem + first block as one kernel (stem_block.cuh) when net_input is fused into the stem and L1-L3 is the 8->8->4 register block */
+    int fuse_stem = 1; bool stem_block_ok = false;
     cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
     Tens input;
     std::vector<Buf> bufs;
@@ -756,6 +758,12 @@ static int engine_plan(ffb_engine *e)
                 if (in_of(i).buf >= 0) bufs[in_of(i).buf].last = 1 << 30;
             }
     }
+    e->stem_block_ok = false;
+    if (use_blocks && e->fuse_stem && L > 4 && e->blk_at[1] >= 0 && e->blocks[e->blk_at[1]].reg && e->blocks[e->blk_at[1]].sc < 0 &&
+        net->layer_list[0].type == LAYER_TYPE_CONV && e->convs[0] && e->convs[0]->kind == CK_STEM && e->outs[0].ld == 8 && e->outs[3].ld == 4) {
+        const std::vector<int> readers = count_readers(net);
+        e->stem_block_ok = readers[0] == 1;                     /* nobody but the block reads the stem's output */
+    }
     if (e->keep_all) for (Buf &b : bufs) b.last = 1 << 30;
     /* greedy best-fit over a free list, in creation order */
     struct Free { size_t off, len; };
@@ -859,6 +867,7 @@ static int engine_attach_body(ffb_engine *e, NET *net)
     if ((env = getenv("FFCNN_PDL")))       sm100::g_ffb_pdl = atoi(env);
     if ((env = getenv("FFCNN_FUSE_BLOCK"))) e->fuse_block = atoi(env);
     if ((env = getenv("FFCNN_FORK_TAIL"))) e->fork_tail = atoi(env);
+    if ((env = getenv("FFCNN_FUSE_STEM"))) e->fuse_stem = atoi(env);
     if ((env = getenv("FFCNN_BLK2")))      e->blk2 = atoi(env);
     CK(cudaMalloc(&e->d_packed, std::max(1, net->weight_size) * sizeof(float)));
     CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
@@ -908,6 +917,8 @@ int ffb_commit_weights(NET *net)
     return 0;
 }
 
+static bool stem_block_active(const ffb_engine *e);
+
 int ffb_set_option(NET *net, const char *name, int value)
 {
     ffb_engine *e = engine_of(net);
@@ -924,6 +935,7 @@ int ffb_set_option(NET *net, const char *name, int value)
     else if (!strcmp(name, "blk2"))      { reweight = e->blk2 != value; e->blk2 = value; }
     else if (!strcmp(name, "fuse_tail")) { if (e->fuse_tail != value) e->plan_dirty = true; e->fuse_tail = value; }
     else if (!strcmp(name, "fork_tail")) { if (e->fork_tail != value) e->plan_dirty = true; e->fork_tail = value; }
+    else if (!strcmp(name, "fuse_stem")) { if (e->fuse_stem != value) e->plan_dirty = true; e->fuse_stem = value; }
     else if (!strcmp(name, "cand_cap")) { e->cand_cap = value; for (ffb_engine::DetSet &d : e->det) d.want = 0; }   /* test hook: initial candidate capacity */
     else { ffb_set_error("unknown option '%s'", name); return -1; }
     if (reweight) {
@@ -951,6 +963,8 @@ int ffb_get_option(NET *net, const char *name)
     if (!strcmp(name, "blk2")) return e->blk2;
     if (!strcmp(name, "fuse_tail")) return e->fuse_tail;
     if (!strcmp(name, "fork_tail")) return e->fork_tail;
+    if (!strcmp(name, "fuse_stem")) return e->fuse_stem;
+    if (!strcmp(name, "stem_block")) return stem_block_active(e) ? 1 : 0;
     if (!strcmp(name, "side_branch")) return e->side_a >= 0 ? e->side_a * 1000 + e->side_b : -1;
     if (!strcmp(name, "blocks")) return (int)e->blocks.size();
     if (!strcmp(name, "max_batch")) return e->max_batch;
@@ -1048,6 +1062,13 @@ int ffb_input_chw(NET *net, const float *chw, int n, int s1, int s2)
     return 0;
 }
 
+/* stem + first block in one kernel: the plan allows it and this batch's frames are read by the stem directly */
+static bool stem_block_active(const ffb_engine *e)
+{
+    return e->stem_block_ok && e->input_fused && e->keep_all != 1 && e->fuse_block && e->blk_at.size() > 1 && e->blk_at[1] >= 0 &&
+           reg_stem_ok(e->blocks[e->blk_at[1]].reg, e->input.h, e->input.w, e->u8_pitch, e->u8_src);
+}
+
 /* ---- the layer loop ---- */
 static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
 {
@@ -1058,6 +1079,7 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
         if (e->in_block[i]) return 0;                          /* computed by the block kernel launched in an earlier slot */
         if (e->blk_at[i] >= 0) {
             const ffb_engine::Block &b = e->blocks[e->blk_at[i]]; const Tens &y = e->outs[i + 2];
+            if (i == 1 && stem_block_active(e)) return 0;      /* computed together with the stem in layer 0's slot */
             if ((b.tc2 ? blk2_run(b.tc2, in.p, in.ld, y.p, y.ld, n, st) : b.plan ? blk_run(b.plan, in.p, in.ld, y.p, y.ld, n, st) : reg_run(b.reg, in.p, in.ld, y.p, y.ld, n, st)) != 0) return -1;
             *launches += b.reg ? reg_launches(b.reg) : 1;
             return 0;
@@ -1065,7 +1087,10 @@ static int run_layer(ffb_engine *e, int i, cudaStream_t st, int *launches)
     }
     switch (il->type) {
     case LAYER_TYPE_CONV:
-        if (i == 0 && e->input_fused) {
+        if (i == 0 && stem_block_active(e)) {
+            const ffb_engine::Block &b = e->blocks[e->blk_at[1]]; const Tens &y = e->outs[3];
+            if (reg_run_stem(b.reg, &e->convs[0]->stemw, e->convs[0]->act, e->u8_src, e->u8_pitch, y.p, y.ld, n, in.h, in.w, e->in_mean, e->in_norm, st) != 0) return -1;
+        } else if (i == 0 && e->input_fused) {
             if (stem_run_u8(e->convs[0], e->u8_src, e->u8_pitch, o.p, n, in.h, in.w, e->in_mean, e->in_norm, st) != 0) return -1;
         } else if (e->fuse_sc[i] >= 0) {
             const LAYER *sl = net->layer_list + e->fuse_sc[i]; const Tens &r = e->outs[sl->depend_list[0]];
@@ -1464,7 +1489,13 @@ int ffb_layer_cost(NET *net, int i, double *bytes, double *flops, char *kname, i
     if (fn->engine && fn->engine->keep_all != 1 && fn->engine->fuse_block && (int)fn->engine->blk_at.size() > i && !g_cost_recursing) {
         /* a fused block is reported in its first layer's slot with the summed (unfused) algorithmic cost of its layers */
         ffb_engine *e = fn->engine;
-        if (e->in_block[i]) { by = 0; fl = 0; nm = "in_block"; }
+        if (e->in_block[i] || (i == 1 && stem_block_active(e))) { by = 0; fl = 0; nm = "in_block"; }
+        else if (i == 0 && stem_block_active(e)) {             /* stem + block L1-L3: reported in the stem's slot */
+            g_cost_recursing = true;
+            for (int k = 1; k <= 3; k++) { double b2 = 0, f2 = 0; ffb_layer_cost(net, k, &b2, &f2, NULL, 0); by += b2; fl += f2; }
+            g_cost_recursing = false;
+            nm = "block_stem_reg_fp32";
+        }
         else if (e->blk_at[i] >= 0) {
             const ffb_engine::Block &b = e->blocks[e->blk_at[i]];
             g_cost_recursing = true;

@@ -17,16 +17,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "sm100.cuh"
+#include "stem_common.cuh"
 
 namespace ffb {
 
 using sm100::pdl_trigger;
 using sm100::pdl_wait;
 
-__device__ __forceinline__ float act_apply(float v, int act)
-{
-    return act == 2 ? (v > 0.f ? v : 0.1f * v) : act == 1 ? fmaxf(v, 0.f) : v;
-}
 
 __device__ __forceinline__ float4 epilogue4(float4 a, float4 s, float4 b, int act)
 {
@@ -43,7 +40,6 @@ __device__ __forceinline__ void fma4(float4 &acc, const float4 v, const float4 w
 }
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 /* ------------------------------------------------------------------------------------------------
  * net_input, batched (ffcnn.c:259-289): BGR u8 frames -> NHWC fp32 [n][H][W][ld=4] (channel 3 = 0),
@@ -82,7 +78,6 @@ __global__ void k_input_u8(const uint8_t *__restrict__ frames, float *__restrict
  *   k_stem_u8 : net_input fused in -- reads the BGR u8 frames directly (no resize: frame size == net size) and applies
  *               (px - mean) * norm while staging, the same float arithmetic as ffcnn.c:281-283, 4x fewer input bytes.
  * ---------------------------------------------------------------------------------------------- */
-struct alignas(16) StemW { float w[27 * 8]; float s[8]; float b[8]; };      /* w[(c*3+ky)*3+kx][oc] */
 
 template <int TX, int TY>
 __device__ __forceinline__ void stem_compute(const float4 (*tile)[2 * TX + 1], const StemW &sw, float *__restrict__ out,

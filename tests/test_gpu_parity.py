@@ -266,6 +266,37 @@ def test_forked_tail_is_found_and_changes_nothing(assets):
     assert res[0] == res[1] == res[2] == res[3]
 
 
+def test_stem_block_fusion_is_bit_identical(assets):
+    """fuse_stem: the stem (net_input + 3x3 s2 conv on the u8 frames) and the first 8->8->4 block run as one kernel (stem_block.cuh)
+    whenever the frames are read by the stem directly.  It performs the two kernels' arithmetic in their order, so the block's output
+    (layer 3), the heads and the boxes must be bit-identical with the fusion off -- on seeded frames, on picture frames, on a batch
+    that is not a multiple of anything, and on a net whose width is not a multiple of the 32-pixel tile."""
+    cfg, wts, bmp = assets
+    img, w, h = ref.load_bmp(bmp)
+    for (nw, nh, n) in ((320, 320, 11), (416, 256, 3)):
+        fr = synth.frames_u8(n, nw, nh)
+        pitch = fr.shape[-1] if fr.ndim == 3 else (3 * nw + 3) & ~3
+        res = []
+        for fuse in (1, 0):
+            net = fb.Net(cfg, wts, nw, nh, device=0, max_batch=n)
+            net.set_option("fuse_stem", fuse)
+            net.set_option("keep_all", 2)
+            net.detect_batch_u8(fr, n, nw, nh, pitch)
+            assert net.get_option("stem_block") == fuse
+            res.append([net.layer_output(3, f).tobytes() for f in range(n)] + [net.layer_output(129, f).tobytes() for f in (0, n - 1)] + [net.boxes(f).tobytes() for f in range(n)])
+            net.close()
+        assert res[0] == res[1]
+    s2f = synth.shifted_frames_from(img, w, h, 8)
+    out = []
+    for fuse in (1, 0):
+        net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=8)
+        net.set_option("fuse_stem", fuse)
+        net.detect_batch_u8(s2f, 8, 320, 320, 960)
+        out.append([net.boxes(f).tobytes() for f in range(8)])
+        net.close()
+    assert out[0] == out[1] and any(len(b) for b in out[0])
+
+
 def test_dw5_exact_mode_matches_conv_v0(assets, oracle_layers):
     cfg, wts, bmp = assets
     img, w, h = ref.load_bmp(bmp)
