@@ -9,6 +9,7 @@
 #include "block_reg.h"
 #include "block_reg.cuh"
 #include "stem_block.cuh"
+#include "block_s2.cuh"
 #include "ffb_internal.h"
 
 
@@ -18,6 +19,8 @@ struct RegPlan {
     int cin, cexp, cout, S, H, W, OH, OW, res, R, kind;
     float slope1, sloped, slope3, slope_res;
     union { RegBlockW<8, 8, 4> w884; RegBlockW<4, 8, 4> w484; RegBlockW<4, 8, 8> w488[3]; } u;     /* 4->24->8: three 8-channel slices */
+    RegBlockW<4, 24, 8> w4248;              /* 4->24->8 as one shared-memory-tiled kernel (block_s2.cuh) */
+    int s2_tile;
     char desc[96];
 };
 
@@ -58,13 +61,21 @@ RegPlan *reg_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
     p->R = env ? atoi(env) : (kind == 2 ? 9 : 16);      /* measured: 16 rows per strip is best for the stride-1 kernels, 9 for the stride-2 slices (3.9 waves of CTAs instead of 2.2) */
     if (p->R < 1) p->R = 16;
     if (kind == 0) fill(p->u.w884, h1, hd, h3); else if (kind == 1) fill(p->u.w484, h1, hd, h3); else for (int i = 0; i < 3; i++) fill(p->u.w488[i], h1, hd, h3, 8 * i, 24);
-    snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s register-resident, %d rows per warp strip", cin, cexp, cout, stride, res ? "+res" : "", p->R);
+    if (kind == 2) {
+        fill(p->w4248, h1, hd, h3);
+        /* FFCNN_S2_TILE=1: the shared-memory-tiled kernel (block_s2.cuh) instead of the three register-resident slices.  Bit-identical,
+           a third fewer instructions, and measured SLOWER (0.228 vs 0.214 ms; 16x8 / 16x4 tiles at 3-6 CTAs per SM all within 0.222-0.228):
+           kept as an option and as the record of the experiment */
+        p->s2_tile = getenv("FFCNN_S2_TILE") ? atoi(getenv("FFCNN_S2_TILE")) : 0;
+    }
+    if (kind == 2 && p->s2_tile) snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d shared-memory tiles %dx%d", cin, cexp, cout, stride, S2_TXO, S2_TYO);
+    else snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s register-resident, %d rows per warp strip", cin, cexp, cout, stride, res ? "+res" : "", p->R);
     return p;
 }
 
 void reg_plan_destroy(RegPlan *p) { delete p; }
 const char *reg_describe(const RegPlan *p) { return p ? p->desc : ""; }
-int reg_launches(const RegPlan *p) { return p && p->kind == 2 ? 3 : 1; }
+int reg_launches(const RegPlan *p) { return p && p->kind == 2 && !p->s2_tile ? 3 : 1; }
 
 int reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaStream_t st)
 {
@@ -78,6 +89,13 @@ int reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
     cudaError_t e;
     if (p->kind == 0)      e = sm100::launch_pdl(k_block_reg_s1<8, 8, 4, false>, grid, block, 0, st, p->u.w884, a);
     else if (p->kind == 1) e = sm100::launch_pdl(k_block_reg_s1<4, 8, 4, true>, grid, block, 0, st, p->u.w484, a);
+    else if (p->s2_tile) {
+        static ffb_smem_cfg configured;
+        if (ffb_ensure_smem((const void *)k_block_s2_tile, S2_SMEM, &configured) != 0) return -1;
+        S2Args s; s.x = x; s.y = y; s.N = n; s.H = p->H; s.W = p->W; s.OH = p->OH; s.OW = p->OW; s.slope1 = p->slope1; s.sloped = p->sloped; s.slope3 = p->slope3;
+        const dim3 g2((unsigned)((p->OW + S2_TXO - 1) / S2_TXO), (unsigned)((p->OH + S2_TYO - 1) / S2_TYO), (unsigned)n);
+        e = sm100::launch_pdl(k_block_s2_tile, g2, dim3(S2_THREADS), S2_SMEM, st, p->w4248, s);
+    }
     else {                 /* three 8-channel slices of the expanded tensor, accumulated through y (which stays in L2) */
         e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 1>, grid, block, 0, st, p->u.w488[0], a);
         if (e == cudaSuccess) e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 2>, grid, block, 0, st, p->u.w488[1], a);

@@ -297,6 +297,38 @@ def test_stem_block_fusion_is_bit_identical(assets):
     assert out[0] == out[1] and any(len(b) for b in out[0])
 
 
+def test_tiled_stride2_block_is_bit_identical_to_the_sliced_kernel(assets):
+    """block_s2.cuh: the 4->24->8 stride-2 block (L9-L11) as one shared-memory-tiled kernel performs the arithmetic of the three
+    8-channel slices of k_block_reg_s2 in their order; the block's output (layer 11), the heads and the boxes must be bit-identical
+    (child process: the choice is read from FFCNN_S2_TILE when the plan is made)."""
+    import subprocess
+    code = r"""
+import sys, hashlib
+sys.path.insert(0, %r)
+import numpy as np
+import ffcnn_b200 as fb
+from ffcnn_b200 import synth
+cfg, wts = fb.default_model()
+h = hashlib.sha256()
+for (nw, nh, n) in ((320, 320, 7), (416, 256, 3)):
+    fr = synth.frames_u8(n, nw, nh)
+    net = fb.Net(cfg, wts, nw, nh, device=0, max_batch=n)
+    net.set_option("keep_all", 2)
+    net.detect_batch_u8(fr, n, nw, nh, fr.shape[-1])
+    for f in range(n):
+        h.update(net.layer_output(11, f).tobytes()); h.update(net.layer_output(129, f).tobytes()); h.update(net.boxes(f).tobytes())
+    net.close()
+print("DIGEST", h.hexdigest())
+""" % REPO
+    digests = []
+    for tile in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, FFCNN_S2_TILE=tile, FFCNN_BLK_VERBOSE="1"), timeout=280)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        assert ("shared-memory tiles" in r.stderr) == (tile == "1")
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
+
+
 def test_dw5_exact_mode_matches_conv_v0(assets, oracle_layers):
     cfg, wts, bmp = assets
     img, w, h = ref.load_bmp(bmp)
