@@ -20,7 +20,7 @@ struct RegPlan {
     float slope1, sloped, slope3, slope_res;
     union { RegBlockW<8, 8, 4> w884; RegBlockW<4, 8, 4> w484; RegBlockW<4, 8, 8> w488[3]; } u;     /* 4->24->8: three 8-channel slices */
     RegBlockW<4, 24, 8> w4248;              /* 4->24->8 as one shared-memory-tiled kernel (block_s2.cuh) */
-    int s2_tile;
+    int s2_tile, ring;
     char desc[96];
 };
 
@@ -60,6 +60,8 @@ RegPlan *reg_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
     const char *env = getenv("FFCNN_REG_ROWS");
     p->R = env ? atoi(env) : (kind == 2 ? 9 : 16);      /* measured: 16 rows per strip is best for the stride-1 kernels, 9 for the stride-2 slices (3.9 waves of CTAs instead of 2.2) */
     if (p->R < 1) p->R = 16;
+    /* x rows through a per-lane cp.async ring in shared memory (block_reg.cuh "row ring") instead of register loads two rows ahead; FFCNN_REG_RING=0 restores the latter */
+    p->ring = getenv("FFCNN_REG_RING") ? atoi(getenv("FFCNN_REG_RING")) : 1;
     if (kind == 0) fill(p->u.w884, h1, hd, h3); else if (kind == 1) fill(p->u.w484, h1, hd, h3); else for (int i = 0; i < 3; i++) fill(p->u.w488[i], h1, hd, h3, 8 * i, 24);
     if (kind == 2) {
         fill(p->w4248, h1, hd, h3);
@@ -69,7 +71,7 @@ RegPlan *reg_plan_create(int cin, int cexp, int cout, int stride, int h, int w, 
         p->s2_tile = getenv("FFCNN_S2_TILE") ? atoi(getenv("FFCNN_S2_TILE")) : 0;
     }
     if (kind == 2 && p->s2_tile) snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d shared-memory tiles %dx%d", cin, cexp, cout, stride, S2_TXO, S2_TYO);
-    else snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s register-resident, %d rows per warp strip", cin, cexp, cout, stride, res ? "+res" : "", p->R);
+    else snprintf(p->desc, sizeof p->desc, "%d->%d->%d s%d%s register-resident, %d rows per warp strip%s", cin, cexp, cout, stride, res ? "+res" : "", p->R, p->ring ? ", cp.async row ring" : "");
     return p;
 }
 
@@ -87,8 +89,10 @@ int reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
     const long strips = (long)n * a.nsx * a.nsy;
     const dim3 grid((unsigned)((strips + REG_WARPS - 1) / REG_WARPS)), block(REG_WARPS * 32);
     cudaError_t e;
-    if (p->kind == 0)      e = sm100::launch_pdl(k_block_reg_s1<8, 8, 4, false>, grid, block, 0, st, p->u.w884, a);
-    else if (p->kind == 1) e = sm100::launch_pdl(k_block_reg_s1<4, 8, 4, true>, grid, block, 0, st, p->u.w484, a);
+    if (p->kind == 0)      e = p->ring ? sm100::launch_pdl(k_block_reg_s1<8, 8, 4, false, true>, grid, block, 0, st, p->u.w884, a)
+                                       : sm100::launch_pdl(k_block_reg_s1<8, 8, 4, false>, grid, block, 0, st, p->u.w884, a);
+    else if (p->kind == 1) e = p->ring ? sm100::launch_pdl(k_block_reg_s1<4, 8, 4, true, true>, grid, block, 0, st, p->u.w484, a)
+                                       : sm100::launch_pdl(k_block_reg_s1<4, 8, 4, true>, grid, block, 0, st, p->u.w484, a);
     else if (p->s2_tile) {
         static ffb_smem_cfg configured;
         if (ffb_ensure_smem((const void *)k_block_s2_tile, S2_SMEM, &configured) != 0) return -1;
@@ -96,7 +100,12 @@ int reg_run(RegPlan *p, const float *x, int ldx, float *y, int ldy, int n, cudaS
         const dim3 g2((unsigned)((p->OW + S2_TXO - 1) / S2_TXO), (unsigned)((p->OH + S2_TYO - 1) / S2_TYO), (unsigned)n);
         e = sm100::launch_pdl(k_block_s2_tile, g2, dim3(S2_THREADS), S2_SMEM, st, p->w4248, s);
     }
-    else {                 /* three 8-channel slices of the expanded tensor, accumulated through y (which stays in L2) */
+    else if (p->ring) {    /* three 8-channel slices of the expanded tensor, accumulated through y (which stays in L2) */
+        e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 1, true>, grid, block, 0, st, p->u.w488[0], a);
+        if (e == cudaSuccess) e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 2, true>, grid, block, 0, st, p->u.w488[1], a);
+        if (e == cudaSuccess) e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 3, true>, grid, block, 0, st, p->u.w488[2], a);
+    }
+    else {
         e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 1>, grid, block, 0, st, p->u.w488[0], a);
         if (e == cudaSuccess) e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 2>, grid, block, 0, st, p->u.w488[1], a);
         if (e == cudaSuccess) e = sm100::launch_pdl(k_block_reg_s2<4, 8, 8, 3>, grid, block, 0, st, p->u.w488[2], a);

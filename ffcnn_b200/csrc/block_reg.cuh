@@ -86,6 +86,43 @@ __device__ __forceinline__ void rb_load(const float *p, bool ok, float (&x)[CIN]
     }
 }
 
+/* ---- row ring (RING variants): x rows travel global -> shared memory by cp.async, several rows ahead of their use, into slots
+ * that are PRIVATE to a lane (a lane reads back only the 2 pixels it copied itself, so cp.async.wait_group is the only
+ * synchronisation).  Why not plain register loads two rows ahead (the non-RING variants): ncu showed a fifth of all warp samples
+ * waiting at the first use of a row that had been requested ~400 instructions earlier -- the consumer waits on a scoreboard
+ * that the NEWEST row's loads (issued just before it) also count on, so every row paid a full DRAM latency regardless of the
+ * lookahead.  cp.async groups complete in order and wait_group<D> names exactly the row that is needed. ---- */
+__device__ __forceinline__ void rb_cp16(uint32_t dst, const float *src, bool ok)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void rb_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void rb_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ float4 rb_lds(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+/* the lane's two adjacent pixels (2 * CIN contiguous floats at p) of one row -> ring slot; !ok writes zeros (rows / columns outside the image) */
+template <int CIN>
+__device__ __forceinline__ void rb_ring_issue(uint32_t slot_addr, const float *p, bool ok)
+{
+#pragma unroll
+    for (int v = 0; v < CIN / 2; v++) rb_cp16(slot_addr + v * 512, p + 4 * v, ok);
+    rb_commit();
+}
+template <int CIN>
+__device__ __forceinline__ void rb_ring_take(uint32_t slot_addr, float (&x0)[CIN], float (&x1)[CIN])
+{
+#pragma unroll
+    for (int v = 0; v < CIN / 4; v++) {
+        const float4 t = rb_lds(slot_addr + v * 512), u = rb_lds(slot_addr + (CIN / 4 + v) * 512);
+        x0[4 * v] = t.x; x0[4 * v + 1] = t.y; x0[4 * v + 2] = t.z; x0[4 * v + 3] = t.w;
+        x1[4 * v] = u.x; x1[4 * v + 1] = u.y; x1[4 * v + 2] = u.z; x1[4 * v + 3] = u.w;
+    }
+}
+
 /* the channel chunk of a neighbouring lane (delta = -1: the lane to the left, +1: to the right) */
 template <int DELTA>
 __device__ __forceinline__ void rb_neighbour(const f32x2 (&e)[RB_P], f32x2 (&o)[RB_P])
@@ -147,11 +184,15 @@ __device__ __forceinline__ void rb_finish(const RegBlockW<CIN, CEXP, COUT> &w, c
 }
 
 /* ------------------------------------------------------------------ stride 1: two output pixels per lane, 60 per warp */
-template <int CIN, int CEXP, int COUT, bool RES>
+template <int CIN, int CEXP, int COUT, bool RES, bool RING = false>
 __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid_constant__ RegBlockW<CIN, CEXP, COUT> w, const RegBlockArgs a)
 {
     constexpr int CP = CEXP / 2;
+    constexpr int ST = 3, D = ST - 1;                  /* RING: slots per warp, rows of lookahead (the row loop is unrolled by ST: slot numbers are constants) */
+    constexpr uint32_t SLOT = (2 * CIN / 4) * 512;      /* bytes per slot: 2 pixels x CIN floats per lane, stored as planes of 32 float4 (conflict-free) */
+    __shared__ float4 ring_s[RING ? REG_WARPS * ST * (2 * CIN / 4) * 32 : 1];
     const int lane = threadIdx.x & 31;
+    [[maybe_unused]] const uint32_t ring = sm100::smem_u32(ring_s) + (threadIdx.x >> 5) * ST * SLOT + lane * 16;
     const long strip = (long)blockIdx.x * REG_WARPS + (threadIdx.x >> 5);
     const int per_frame = a.nsx * a.nsy;
     if (strip >= (long)a.N * per_frame) return;
@@ -172,7 +213,15 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
 #pragma unroll
     for (int k = 0; k < CIN; k++) xp0[k] = xp1[k] = 0.f;
     float xm0[CIN], xm1[CIN];                                                   /* x of the row after next: the loads run two rows ahead of their use */
-    {
+    /* RING: row rn -> slot; ix0 is even and W is even, so the lane's two pixels are inside or outside together and contiguous */
+    auto ring_issue = [&](int rn, int slot) {
+        const bool rok = rn >= 0 && rn < a.H && rn <= oy1;
+        rb_ring_issue<CIN>(ring + slot * SLOT, xf + ((long)min(max(rn, 0), a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0);
+    };
+    if constexpr (RING) {
+#pragma unroll
+        for (int k = 0; k < D; k++) ring_issue(oy0 - 1 + k, k);
+    } else {
         const int r = oy0 - 1; const bool rok = r >= 0;
         rb_load<CIN>(xf + ((long)max(r, 0) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
         rb_load<CIN>(xf + ((long)max(r, 0) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
@@ -180,7 +229,8 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
         rb_load<CIN>(xf + ((long)min(oy0, a.H - 1) * a.W + max(ix1, 0)) * CIN, in1, xm1);
     }
     /* one input row: dm = output row r-1 (gets kernel row 2 and is finished), d0 = row r (kernel row 1), dp = row r+1 (kernel row 0, first contribution) */
-    auto step = [&](int r, f32x2 (&dm0)[CP], f32x2 (&dm1)[CP], f32x2 (&d00)[CP], f32x2 (&d01)[CP], f32x2 (&dp0)[CP], f32x2 (&dp1)[CP]) {
+    auto step = [&](int r, auto slot_c, f32x2 (&dm0)[CEXP / 2], f32x2 (&dm1)[CEXP / 2], f32x2 (&d00)[CEXP / 2], f32x2 (&d01)[CEXP / 2], f32x2 (&dp0)[CEXP / 2], f32x2 (&dp1)[CEXP / 2]) {   /* CEXP / 2 spelled out: cicc crashes on a generic lambda whose parameter type names a local constexpr */
+        constexpr int slot = decltype(slot_c)::value;
         /* expand -> neighbour exchange -> taps, RB_CH channels at a time */
         auto chunk = [&](auto c0, bool rin) {
             constexpr int C0 = decltype(c0)::value;
@@ -192,9 +242,15 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
             rb_taps<1, false, C0>(w, d00, el, e0, e1); rb_taps<1, false, C0>(w, d01, e0, e1, er);
             rb_taps<0, true, C0>(w, dp0, el, e0, e1);  rb_taps<0, true, C0>(w, dp1, e0, e1, er);
         };
+        if constexpr (RING) {
+            /* request row r + D into the slot whose row (r - 1) was consumed by the previous step, then take row r: at most the D newer rows stay in flight */
+            ring_issue(r + D, (slot + D) % ST);
+            rb_wait<D>();
+            rb_ring_take<CIN>(ring + slot * SLOT, xc0, xc1);
+        } else {
 #pragma unroll
-        for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; xn0[k] = xm0[k]; xn1[k] = xm1[k]; }
-        {   /* prefetch x two rows ahead (ncu: with one row of lookahead a quarter of the warp samples waited for these loads) */
+            for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; xn0[k] = xm0[k]; xn1[k] = xm1[k]; }
+            /* prefetch x two rows ahead (ncu: with one row of lookahead a quarter of the warp samples waited for these loads) */
             const int rn = r + 2; const bool rok = rn < a.H && rn <= oy1;
             rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xm0);
             rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xm1);
@@ -215,18 +271,22 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 2) k_block_reg_s1(const __grid
     /* rows are taken three at a time with no branch around the steps (a warp shuffle under a branch the compiler cannot
        prove uniform costs four extra synchronisation instructions each); rows past the strip load zeros and write nothing */
     for (int r = oy0 - 1; r <= oy1; r += 3) {
-        step(r, A0, A1, B0, B1, C0, C1);
-        step(r + 1, B0, B1, C0, C1, A0, A1);
-        step(r + 2, C0, C1, A0, A1, B0, B1);
+        step(r, std::integral_constant<int, 0>(), A0, A1, B0, B1, C0, C1);
+        step(r + 1, std::integral_constant<int, 1>(), B0, B1, C0, C1, A0, A1);
+        step(r + 2, std::integral_constant<int, 2>(), C0, C1, A0, A1, B0, B1);
     }
 }
 
 /* ------------------------------------------------------------------ stride 2: one output pixel per lane, 31 per warp */
-template <int CIN, int CEXP, int COUT, int PART>
+template <int CIN, int CEXP, int COUT, int PART, bool RING = false>
 __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid_constant__ RegBlockW<CIN, CEXP, COUT> w, const RegBlockArgs a)
 {
     constexpr int CP = CEXP / 2;
+    constexpr int ST = 4, D = ST - 1;                  /* RING: slots per warp, rows of lookahead (four rows per trip of the row loop: slot numbers are constants) */
+    constexpr uint32_t SLOT = (2 * CIN / 4) * 512;
+    __shared__ float4 ring_s[RING ? REG_WARPS * ST * (2 * CIN / 4) * 32 : 1];
     const int lane = threadIdx.x & 31;
+    [[maybe_unused]] const uint32_t ring = sm100::smem_u32(ring_s) + (threadIdx.x >> 5) * ST * SLOT + lane * 16;
     const long strip = (long)blockIdx.x * REG_WARPS + (threadIdx.x >> 5);
     const int per_frame = a.nsx * a.nsy;
     if (strip >= (long)a.N * per_frame) return;
@@ -246,7 +306,14 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
     for (int c = 0; c < CP; c++) A[c] = B[c] = 0ull;
     const int r_first = 2 * oy0 - 1, r_last = 2 * (oy1 - 1) + 1;
     float xm0[CIN], xm1[CIN];                                                   /* the row after next: the loads run two rows ahead of their use */
-    {
+    auto ring_issue = [&](int rn, int slot) {                                   /* ix0 and W are even: both pixels are inside or outside together, and contiguous */
+        const bool rok = rn >= 0 && rn < a.H && rn <= r_last;
+        rb_ring_issue<CIN>(ring + slot * SLOT, xf + ((long)min(max(rn, 0), a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0);
+    };
+    if constexpr (RING) {
+#pragma unroll
+        for (int k = 0; k < D; k++) ring_issue(r_first + k, k);
+    } else {
         const bool rok = r_first >= 0;
         rb_load<CIN>(xf + ((long)max(r_first, 0) * a.W + max(ix0, 0)) * CIN, rok && in0, xn0);
         rb_load<CIN>(xf + ((long)max(r_first, 0) * a.W + max(ix1, 0)) * CIN, rok && in1, xn1);
@@ -257,12 +324,19 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
     float dummy[CIN];
 #pragma unroll
     for (int k = 0; k < CIN; k++) dummy[k] = 0.f;
-    auto fetch_row = [&](int r) {                                               /* xc <- row r, prefetch row r + 2 */
+    auto fetch_row = [&](int r, auto slot_c) {                                  /* xc <- row r, prefetch row r + 2 (RING: request row r + D) */
+        constexpr int slot = decltype(slot_c)::value;
+        if constexpr (RING) {
+            ring_issue(r + D, (slot + D) % ST);
+            rb_wait<D>();
+            rb_ring_take<CIN>(ring + slot * SLOT, xc0, xc1);
+        } else {
 #pragma unroll
-        for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; xn0[k] = xm0[k]; xn1[k] = xm1[k]; }
-        const int rn = r + 2; const bool rok = rn < a.H && rn <= r_last;
-        rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xm0);
-        rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xm1);
+            for (int k = 0; k < CIN; k++) { xc0[k] = xn0[k]; xc1[k] = xn1[k]; xn0[k] = xm0[k]; xn1[k] = xm1[k]; }
+            const int rn = r + 2; const bool rok = rn < a.H && rn <= r_last;
+            rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0, xm0);
+            rb_load<CIN>(xf + ((long)min(rn, a.H - 1) * a.W + max(ix1, 0)) * CIN, rok && in1, xm1);
+        }
     };
     /* odd input row 2oy-1: kernel row 2 of output row oy-1 (cur) and kernel row 0 of output row oy (nxt), RB_CH channels at a time */
     auto odd_chunk = [&](auto c0, bool rin, f32x2 (&cur)[CEXP / 2], f32x2 (&nxt)[CEXP / 2]) {
@@ -283,10 +357,11 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
         rb_taps<1, false, C0>(w, nxt, el, e0, e1);
     };
     /* rows come in (odd, even) pairs: odd row 2oy-1 closes output row oy-1 and opens row oy; even row 2oy is row oy's centre */
-    auto pair = [&](int oy, f32x2 (&cur)[CEXP / 2], f32x2 (&nxt)[CEXP / 2]) {
+    auto pair = [&](int oy, auto slot_c, f32x2 (&cur)[CEXP / 2], f32x2 (&nxt)[CEXP / 2]) {
+        constexpr int slot = decltype(slot_c)::value;
         {
             const int r = 2 * oy - 1; const bool rin = r >= 0 && r < a.H;
-            fetch_row(r);
+            fetch_row(r, std::integral_constant<int, slot>());
             /* the closing taps of `cur` must be complete before it is finished, the opening taps of `nxt` are independent:
                chunks are run for both, then `cur` is finished */
             odd_chunk(std::integral_constant<int, 0>(), rin, cur, nxt);
@@ -296,15 +371,15 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
         }
         {
             const int r = 2 * oy; const bool rin = r < a.H && oy < oy1;
-            fetch_row(r);
+            fetch_row(r, std::integral_constant<int, slot + 1>());
             even_chunk(std::integral_constant<int, 0>(), rin, nxt);
             if constexpr (CEXP > 8)  even_chunk(std::integral_constant<int, 8>(), rin, nxt);
             if constexpr (CEXP > 16) even_chunk(std::integral_constant<int, 16>(), rin, nxt);
         }
     };
     for (int oy = oy0; oy <= oy1; oy += 2) {                                   /* no branch around the pairs: see k_block_reg_s1 */
-        pair(oy, A, B);
-        pair(oy + 1, B, A);
+        pair(oy, std::integral_constant<int, 0>(), A, B);
+        pair(oy + 1, std::integral_constant<int, 2>(), B, A);
     }
 }
 

@@ -329,6 +329,42 @@ print("DIGEST", h.hexdigest())
     assert digests[0] == digests[1]
 
 
+def test_row_ring_register_blocks_are_bit_identical_to_register_prefetch(assets):
+    """block_reg.cuh "row ring": the register-resident block kernels fetch x rows through a per-lane cp.async ring in shared memory
+    (default) instead of register loads two rows ahead (FFCNN_REG_RING=0).  Only the way x arrives changes, so every block output
+    (layers 3, 8, 11 -- the stem fusion is switched off so that the 8->8->4 block runs on the register kernel too), the heads and the
+    boxes must be bit-identical; frames whose strips end on ragged rows / columns are included (child process: the choice is read
+    from FFCNN_REG_RING when the plan is made)."""
+    import subprocess
+    code = r"""
+import sys, hashlib
+sys.path.insert(0, %r)
+import numpy as np
+import ffcnn_b200 as fb
+from ffcnn_b200 import synth
+cfg, wts = fb.default_model()
+h = hashlib.sha256()
+for (nw, nh, n) in ((320, 320, 7), (416, 256, 3), (352, 288, 2)):
+    fr = synth.frames_u8(n, nw, nh)
+    net = fb.Net(cfg, wts, nw, nh, device=0, max_batch=n)
+    net.set_option("keep_all", 2)
+    net.set_option("fuse_stem", 0)
+    net.detect_batch_u8(fr, n, nw, nh, fr.shape[-1])
+    for f in range(n):
+        for l in (3, 8, 11, 120, 129): h.update(net.layer_output(l, f).tobytes())
+        h.update(net.boxes(f).tobytes())
+    net.close()
+print("DIGEST", h.hexdigest())
+""" % REPO
+    digests = []
+    for ring in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, FFCNN_REG_RING=ring, FFCNN_BLK_VERBOSE="1"), timeout=280)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        assert ("cp.async row ring" in r.stderr) == (ring == "1"), r.stderr[-1500:]
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
+
+
 def test_dw5_exact_mode_matches_conv_v0(assets, oracle_layers):
     cfg, wts, bmp = assets
     img, w, h = ref.load_bmp(bmp)
