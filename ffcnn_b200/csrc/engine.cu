@@ -463,20 +463,20 @@ struct ffb_engine {
     unsigned char *d_frames = nullptr; size_t d_frames_cap = 0;
     float *h_stage = nullptr; size_t h_stage_cap = 0;
     /* detection */
-    /* two candidate sets: while the host decodes batch i from one, the GPU may already be filtering batch i+1 into the other */
+    /* one candidate set per pipeline slot: while the host decodes batch i from one, the GPU may already be filtering the batches queued behind it into the others */
     struct DetSet { Candidate *d_cand = nullptr, *h_cand = nullptr; int *d_count = nullptr, *h_count = nullptr; int cap = 0, n = 0, s1 = 1, s2 = 1; long want = 0;
-                    cudaEvent_t done = nullptr; } det[2];
+                    cudaEvent_t done = nullptr; } det[FFB_SLOTS];
     int det_cur = 0;
     cudaStream_t d2h_stream = nullptr;      /* candidate read-back must not queue behind the next batch's forward pass */
-    bool slot_enqueued[2] = { false, false };
+    bool slot_enqueued[FFB_SLOTS] = {};
     std::vector<std::vector<BBOX>> boxes, raw;
     int s1 = 1, s2 = 1; size_t d2h_bytes = 0;
-    /* submit/collect pipeline: two device frame slots filled on a copy stream while the previous batch computes */
+    /* submit/collect pipeline: FFB_SLOTS device frame slots filled on a copy stream while the earlier batches compute */
     cudaStream_t copy_stream2 = nullptr; cudaEvent_t ev_join = nullptr; int h2d_chunks = 1;    /* FFCNN_H2D_CHUNKS: split each batch copy over two copy streams */
-    cudaStream_t copy_stream = nullptr; unsigned char *d_slot[2] = { nullptr, nullptr }; size_t slot_cap[2] = { 0, 0 };
-    cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr };
+    cudaStream_t copy_stream = nullptr; unsigned char *d_slot[FFB_SLOTS] = {}; size_t slot_cap[FFB_SLOTS] = {};
+    cudaEvent_t ev_copied[FFB_SLOTS] = {}, ev_free[FFB_SLOTS] = {};
     long submitted = 0, collected = 0;
-    struct SlotMeta { int n, w, h, pitch; float mean[3], norm[3]; bool has_mean, has_norm; } slot_meta[2];
+    struct SlotMeta { int n, w, h, pitch; float mean[3], norm[3]; bool has_mean, has_norm; } slot_meta[FFB_SLOTS];
     /* L2 flush scratch for ffb_layer_times */
     float *d_flush = nullptr; size_t flush_floats = 0;
 };
@@ -517,7 +517,7 @@ void ffb_engine_destroy(ffb_engine *e)
     cudaFreeHost(e->h_stage);
     for (ffb_engine::DetSet &d : e->det) { cudaFree(d.d_cand); cudaFree(d.d_count); cudaFreeHost(d.h_cand); cudaFreeHost(d.h_count); if (d.done) cudaEventDestroy(d.done); }
     if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
-    for (int i = 0; i < 2; i++) { cudaFree(e->d_slot[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]); }
+    for (int i = 0; i < FFB_SLOTS; i++) { cudaFree(e->d_slot[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]); }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->copy_stream2) cudaStreamDestroy(e->copy_stream2);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -1349,27 +1349,27 @@ int ffb_submit_u8(NET *net, const unsigned char *frames_host, int n, int w, int 
     ffb_engine *e = engine_of(net);
     if (!e) return -1;
     if (!frames_host || n < 1 || w < 1 || h < 1 || pitch < 3 * w) { ffb_set_error("ffb_submit_u8: bad arguments"); return -1; }
-    if (e->submitted - e->collected >= 2) { ffb_set_error("ffb_submit_u8: two batches already in flight, call ffb_collect first"); return -1; }
+    if (e->submitted - e->collected >= FFB_SLOTS) { ffb_set_error("ffb_submit_u8: %d batches already in flight, call ffb_collect first", FFB_SLOTS); return -1; }
     CK(cudaSetDevice(e->device));
     if (!e->copy_stream) {
         CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming)); }
+        for (int i = 0; i < FFB_SLOTS; i++) { CK(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming)); }
         const char *ch = getenv("FFCNN_H2D_CHUNKS");
         e->h2d_chunks = ch ? std::max(1, std::min(64, atoi(ch))) : 1;
         if (e->h2d_chunks > 1) { CK(cudaStreamCreateWithFlags(&e->copy_stream2, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming)); }
     }
-    const int slot = (int)(e->submitted & 1);
+    const int slot = (int)(e->submitted % FFB_SLOTS);
     const size_t bytes = (size_t)n * h * pitch;
     if (bytes > e->slot_cap[slot]) {
         CK(cudaStreamSynchronize(e->stream)); CK(cudaStreamSynchronize(e->copy_stream));
         cudaFree(e->d_slot[slot]); e->d_slot[slot] = nullptr; e->slot_cap[slot] = 0;
         CK(cudaMalloc(&e->d_slot[slot], bytes)); e->slot_cap[slot] = bytes;
     }
-    if (e->submitted >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->ev_free[slot], 0));     /* the batch that used this slot has consumed it */
+    if (e->submitted >= FFB_SLOTS) CK(cudaStreamWaitEvent(e->copy_stream, e->ev_free[slot], 0));     /* the batch that used this slot has consumed it */
     if (e->h2d_chunks > 1) {
         /* several smaller copies alternating over two streams keep two DMA transfers in flight (developer knob; measured in
            profiles/r2h_e2e_8gpu.txt) */
-        if (e->submitted >= 2) CK(cudaStreamWaitEvent(e->copy_stream2, e->ev_free[slot], 0));
+        if (e->submitted >= FFB_SLOTS) CK(cudaStreamWaitEvent(e->copy_stream2, e->ev_free[slot], 0));
         const size_t chunk = ((bytes + e->h2d_chunks - 1) / e->h2d_chunks + 4095) & ~(size_t)4095;
         int k = 0;
         for (size_t off = 0; off < bytes; off += chunk, k++)
@@ -1406,11 +1406,15 @@ int ffb_collect(NET *net)
     if (!e) return -1;
     if (e->collected >= e->submitted) { ffb_set_error("ffb_collect: nothing submitted"); return -1; }
     CK(cudaSetDevice(e->device));
-    const int slot = (int)(e->collected & 1);
-    if (!e->slot_enqueued[slot] && collect_enqueue(net, e, slot) != 0) return -1;
-    /* look-ahead: the next submitted batch is queued behind this one before the host blocks, so the GPU goes straight from
-       batch i to batch i+1 while the host decodes batch i (its candidates sit in the other detection set) */
-    if (e->submitted - e->collected >= 2 && !e->slot_enqueued[slot ^ 1] && collect_enqueue(net, e, slot ^ 1) != 0) return -1;
+    const int slot = (int)(e->collected % FFB_SLOTS);
+    /* look-ahead: every submitted batch is queued (in order) before the host blocks on the oldest one, so the GPU goes straight
+       from batch i to batch i+1 while the host decodes batch i (each batch's candidates sit in its own detection set).  With
+       FFB_SLOTS = 3 the caller can keep two batches queued behind the one it collects: a host hiccup of up to one whole step
+       (a scheduler tick, an NVML query taking the driver lock) no longer drains the GPU */
+    for (long k = e->collected; k < e->submitted; k++) {
+        const int s = (int)(k % FFB_SLOTS);
+        if (!e->slot_enqueued[s] && collect_enqueue(net, e, s) != 0) return -1;
+    }
     e->det_cur = slot;
     e->slot_enqueued[slot] = false;
     e->collected++;

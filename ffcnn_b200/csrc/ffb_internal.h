@@ -19,6 +19,7 @@ extern "C" {
 enum { FFB_ACT_LINEAR = 0, FFB_ACT_RELU = 1, FFB_ACT_LEAKY = 2 };
 
 struct ffb_engine;                      /* CUDA side, engine.cu */
+#define FFB_SLOTS 3                     /* batches ffb_submit_u8 accepts before ffb_collect must be called (frame slots, detection sets) */
 
 /* The object net_load returns: the ABI-visible NET first, private state after it. */
 typedef struct ffb_net {

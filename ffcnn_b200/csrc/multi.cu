@@ -232,7 +232,7 @@ extern "C" int ffb_multi_detect_u8(ffb_multi *m, const unsigned char *frames_hos
 extern "C" int ffb_multi_submit_u8(ffb_multi *m, const unsigned char *frames_host, int n, int w, int h, int pitch, const float *mean, const float *norm)
 {
     if (!m || !frames_host || n < 1) { ffb_set_error("ffb_multi_submit_u8: bad arguments"); return -1; }
-    if (m->inflight_total.size() >= 2) { ffb_set_error("ffb_multi_submit_u8: two batches already in flight, call ffb_multi_collect first"); return -1; }
+    if (m->inflight_total.size() >= FFB_SLOTS) { ffb_set_error("ffb_multi_submit_u8: %d batches already in flight, call ffb_multi_collect first", FFB_SLOTS); return -1; }
     shard(m, frames_host, n, w, h, pitch, mean, norm);
     const int rc = run_all(m, OP_SUBMIT);
     if (rc == 0) m->inflight_total.push_back(n);

@@ -95,7 +95,7 @@ int  ffb_detect_batch_u8(NET *net, const unsigned char *frames_host, int n, int 
                          const float *mean, const float *norm);
 
 /* Pipelined form of the same call for streams of batches: ffb_submit_u8 starts the H2D copy of a batch on a copy
- * stream (at most two batches in flight); ffb_collect runs forward + detect for the oldest submitted batch and leaves its
+ * stream (at most three batches in flight); ffb_collect runs forward + detect for the oldest submitted batch and leaves its
  * boxes readable with ffb_boxes.  submit(b0); loop { submit(b_next); collect(); read boxes; } overlaps the PCIe copy of
  * the next batch with the GPU work and the host decode of the current one.  frames_host must stay valid (and should be
  * pinned) until the matching ffb_collect returns. */

@@ -181,6 +181,24 @@ def test_pipelined_submit_collect_equals_blocking_call(assets):
     assert got == want and any(len(x) for x in got[0])
     with pytest.raises(fb.FfcnnError):
         net.collect()                                   # nothing in flight
+    # three batches in flight (the pipeline's depth): all are queued on the GPU before the host blocks on the first; a fourth is refused
+    for b in batches:
+        net.submit_u8(b, 6, 320, 320, 960)
+    with pytest.raises(fb.FfcnnError):
+        net.submit_u8(batches[0], 6, 320, 320, 960)
+    got3 = []
+    for i in range(3):
+        net.collect()
+        got3.append([net.boxes(f).tobytes() for f in range(6)])
+    assert got3 == want
+    # steady state with two batches queued behind the collected one, batch sizes changing on the way
+    sizes = [6, 4, 6, 2, 5, 6, 6]
+    net.submit_u8(batches[0], sizes[0], 320, 320, 960); net.submit_u8(batches[1], sizes[1], 320, 320, 960)
+    for i in range(len(sizes)):
+        if i + 2 < len(sizes):
+            net.submit_u8(batches[(i + 2) % 3], sizes[i + 2], 320, 320, 960)
+        net.collect()
+        assert [net.boxes(f).tobytes() for f in range(sizes[i])] == want[i % 3][:sizes[i]]
     net.close()
 
 
