@@ -24,7 +24,16 @@ namespace ffb {
 constexpr int SB_TXO = 32, SB_TYO = 8;                  /* output tile.  Sweep (B200, batch 256, ms for L0-L3): 32x8 at five CTAs per SM 0.199 | 32x16 (3) 0.205 |
                                                            32x12 (4) 0.208 | 32x20 (2) 0.229; the two-kernel path 0.224 */
 constexpr int SB_THREADS = 192;                         /* 170 position pairs in phase B, 128 output-pixel pairs in phase C */
-constexpr size_t SB_SMEM = ((size_t)(2 * SB_TYO + 5) * 4 * ((2 * SB_TXO + 6 + 3) / 4) + (size_t)(SB_TYO + 2) * 2 * 2 * ((SB_TXO + 2) / 2)) * 16;
+/* Shared-memory geometry (float4 units).  Bank conflicts decide this kernel (l1tex is its busiest unit), so both arrays are skewed:
+ *  - staged row r starts at r * 4 * IWG + SB_TILE_SKEW(r): phase B's threads walk 17 position pairs per row of positions, a quarter-warp
+ *    that straddles two position rows (= two staged rows apart) needs those rows 1 float4 apart mod 8 to stay conflict-free, phase A's
+ *    stores (18 groups per staged row) want consecutive rows 2 apart: rows alternate +2 / +7 (sum 9 = 1 mod 8);
+ *  - a row of e is padded from 68 to 73 float4 (1 mod 8) for phase B's stores; phase C reads whole quarter-warps inside one row. */
+constexpr int SB_IWG = (2 * SB_TXO + 6 + 3) / 4, SB_IH = 2 * SB_TYO + 5, SB_HXN = SB_TXO + 2, SB_HYN = SB_TYO + 2;
+__host__ __device__ constexpr int SB_TILE_SKEW(int r) { return (r >> 1) * 9 + (r & 1) * 2; }
+constexpr int SB_TILE_F4 = SB_IH * 4 * SB_IWG + SB_TILE_SKEW(SB_IH);
+constexpr int SB_E_ROW = ((4 * (SB_HXN / 2) + 7) / 8) * 8 + 1;
+constexpr size_t SB_SMEM = ((size_t)SB_TILE_F4 + (size_t)SB_HYN * SB_E_ROW) * 16;
 
 struct StemBlockArgs {
     const uint8_t *frames; int pitch;
@@ -34,7 +43,10 @@ struct StemBlockArgs {
     float slope1, sloped, slope3;
 };
 
-__global__ void __launch_bounds__(SB_THREADS, 5)
+#ifndef SB_MINB
+#define SB_MINB 4      /* 80 registers, no spills: 0.1763 ms against 0.1808 at five CTAs per SM of 64 registers (28 B of spills, a tenth of the stream MOVs) */
+#endif
+__global__ void __launch_bounds__(SB_THREADS, SB_MINB)
 k_stem_block(const __grid_constant__ StemW sw, const __grid_constant__ RegBlockW<8, 8, 4> w, const StemBlockArgs a)
 {
     sm100::pdl_trigger(); sm100::pdl_wait();
@@ -46,8 +58,10 @@ k_stem_block(const __grid_constant__ StemW sw, const __grid_constant__ RegBlockW
        lives at E[hy][h][hx & 1][hx >> 1]: the threads of both phases walk pixels 4 (positions 2) apart, so consecutive threads
        touch consecutive float4 of one plane */
     extern __shared__ float4 sb_smem[];
-    float4 (*tile)[4][IWG] = reinterpret_cast<float4 (*)[4][IWG]>(sb_smem);
-    float4 (*E)[2][2][HXN / 2] = reinterpret_cast<float4 (*)[2][2][HXN / 2]>(sb_smem + IH * 4 * IWG);
+    static_assert(IWG == SB_IWG && IH == SB_IH && HXN == SB_HXN && HYN == SB_HYN, "geometry");
+    auto tile = [&](int r, int plane, int gx) -> float4 & { return sb_smem[r * (4 * IWG) + SB_TILE_SKEW(r) + plane * IWG + gx]; };
+    float4 *Eb = sb_smem + SB_TILE_F4;
+    auto E = [&](int hy, int h, int q, int i) -> float4 & { return Eb[hy * SB_E_ROW + (h * 2 + q) * (HXN / 2) + i]; };
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * SB_TXO, oy0 = blockIdx.y * SB_TYO;
     const long f = blockIdx.z;
@@ -72,12 +86,12 @@ k_stem_block(const __grid_constant__ StemW sw, const __grid_constant__ RegBlockW
         const int g = tid + it * SB_THREADS, ty = g / IWG, gx = g - ty * IWG;
         if (g < NG) {
             if (ok[it]) {
-                tile[ty][0][gx] = make_float4(cvt(w0[it], 2, a.m0, a.n0), cvt(w0[it], 1, a.m1, a.n1), cvt(w0[it], 0, a.m2, a.n2), 0.f);
-                tile[ty][1][gx] = make_float4(cvt(w1[it], 1, a.m0, a.n0), cvt(w1[it], 0, a.m1, a.n1), cvt(w0[it], 3, a.m2, a.n2), 0.f);
-                tile[ty][2][gx] = make_float4(cvt(w2[it], 0, a.m0, a.n0), cvt(w1[it], 3, a.m1, a.n1), cvt(w1[it], 2, a.m2, a.n2), 0.f);
-                tile[ty][3][gx] = make_float4(cvt(w2[it], 3, a.m0, a.n0), cvt(w2[it], 2, a.m1, a.n1), cvt(w2[it], 1, a.m2, a.n2), 0.f);
+                tile(ty, 0, gx) = make_float4(cvt(w0[it], 2, a.m0, a.n0), cvt(w0[it], 1, a.m1, a.n1), cvt(w0[it], 0, a.m2, a.n2), 0.f);
+                tile(ty, 1, gx) = make_float4(cvt(w1[it], 1, a.m0, a.n0), cvt(w1[it], 0, a.m1, a.n1), cvt(w0[it], 3, a.m2, a.n2), 0.f);
+                tile(ty, 2, gx) = make_float4(cvt(w2[it], 0, a.m0, a.n0), cvt(w1[it], 3, a.m1, a.n1), cvt(w1[it], 2, a.m2, a.n2), 0.f);
+                tile(ty, 3, gx) = make_float4(cvt(w2[it], 3, a.m0, a.n0), cvt(w2[it], 2, a.m1, a.n1), cvt(w2[it], 1, a.m2, a.n2), 0.f);
             } else {
-                tile[ty][0][gx] = tile[ty][1][gx] = tile[ty][2][gx] = tile[ty][3][gx] = zero4();
+                tile(ty, 0, gx) = tile(ty, 1, gx) = tile(ty, 2, gx) = tile(ty, 3, gx) = zero4();
             }
         }
     }
@@ -94,7 +108,7 @@ k_stem_block(const __grid_constant__ StemW sw, const __grid_constant__ RegBlockW
 #pragma unroll
         for (int j = 0; j < 3; j++)
 #pragma unroll
-            for (int k = 0; k < 5; k++) p[j][k] = tile[2 * hy + j][(1 + k) & 3][i + ((1 + k) >> 2)];
+            for (int k = 0; k < 5; k++) p[j][k] = tile(2 * hy + j, (1 + k) & 3, i + ((1 + k) >> 2));
 #pragma unroll
         for (int c = 0; c < 3; c++)
 #pragma unroll
@@ -125,8 +139,8 @@ k_stem_block(const __grid_constant__ StemW sw, const __grid_constant__ RegBlockW
             }
             f32x2 e[4];                                  /* rb_expand<0> of block_reg.cuh */
             rb_expand<0>(w, x, inside, slope1, e);
-            E[hy][0][q][i] = make_float4(f2_lo(e[0]), f2_hi(e[0]), f2_lo(e[1]), f2_hi(e[1]));
-            E[hy][1][q][i] = make_float4(f2_lo(e[2]), f2_hi(e[2]), f2_lo(e[3]), f2_hi(e[3]));
+            E(hy, 0, q, i) = make_float4(f2_lo(e[0]), f2_hi(e[0]), f2_lo(e[1]), f2_hi(e[1]));
+            E(hy, 1, q, i) = make_float4(f2_lo(e[2]), f2_hi(e[2]), f2_lo(e[3]), f2_hi(e[3]));
         }
     }
     __syncthreads();
@@ -145,8 +159,10 @@ k_stem_block(const __grid_constant__ StemW sw, const __grid_constant__ RegBlockW
                 for (int c = 0; c < 4; c++)
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        const float4 t = E[ty + r][h][c & 1][j + (c >> 1)];
-                        v[c][2 * h] = f2_pack(t.x, t.y); v[c][2 * h + 1] = f2_pack(t.z, t.w);
+                        /* one 128-bit load as two channel pairs: left to itself the compiler fetched the pairs with two 64-bit loads, and
+                           64-bit loads of lanes 16 bytes apart are 2-way bank conflicts (half of this kernel's shared-memory wavefronts) */
+                        const sm100::f4p t = sm100::lds128p(sm100::smem_u32(&E(ty + r, h, c & 1, j + (c >> 1))));
+                        v[c][2 * h] = t.a; v[c][2 * h + 1] = t.b;
                     }
                 if (r == 0) { rb_taps<0, true, 0>(w, d0, v[0], v[1], v[2]); rb_taps<0, true, 0>(w, d1, v[1], v[2], v[3]); }
                 if (r == 1) { rb_taps<1, false, 0>(w, d0, v[0], v[1], v[2]); rb_taps<1, false, 0>(w, d1, v[1], v[2], v[3]); }

@@ -25,6 +25,12 @@ print('hottest SASS by samples:')
 for r in sorted(data, key=lambda r: -f(r, '# Samples'))[:int(sys.argv[2]) if len(sys.argv) > 2 else 14]:
     tops = sorted(((h, f(r, h)) for h in st), key=lambda x: -x[1])[:2]
     print('  %5.1f%%  %-70s %s' % (100 * f(r, '# Samples') / tot_s, r[ix['Source']].strip()[:70], ' '.join('%s=%d' % (h[6:], v) for h, v in tops if v)))
+ex = sorted(data, key=lambda r: -(f(r, 'L1 Wavefronts Shared') - f(r, 'L1 Wavefronts Shared Ideal')))[:int(__import__("os").environ.get("NCU_HOT_CONFLICTS", 6))]
+if wf > wfi:
+    print('shared-memory bank conflicts by SASS line (wavefronts, ideal):')
+    for r in ex:
+        if f(r, 'L1 Wavefronts Shared') > f(r, 'L1 Wavefronts Shared Ideal'):
+            print('  %9d %9d  %s' % (f(r, 'L1 Wavefronts Shared'), f(r, 'L1 Wavefronts Shared Ideal'), r[ix['Source']].strip()[:80]))
 # CUDA-C view
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
