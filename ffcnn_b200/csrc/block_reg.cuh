@@ -151,7 +151,8 @@ __device__ __forceinline__ void rb_taps(const RegBlockW<CIN, CEXP, COUT> &w, f32
  * PART splits a wide block into channel slices run as consecutive launches (the projection is a sum over expanded channels):
  * 0 = whole block; 1 = first slice, store the raw partial sums; 2 = middle slice, add to them; 3 = last slice, add, BN + act. */
 template <bool RES, int PART, int CIN, int CEXP, int COUT>
-__device__ __forceinline__ void rb_finish(const RegBlockW<CIN, CEXP, COUT> &w, const RegBlockArgs &a, const f32x2 (&d)[CEXP / 2], const float (&xc)[CIN], float *yp)
+__device__ __forceinline__ void rb_finish(const RegBlockW<CIN, CEXP, COUT> &w, const RegBlockArgs &a, const f32x2 (&d)[CEXP / 2], const float (&xc)[CIN], float *yp,
+                                          uint32_t ypre = 0)           /* PART >= 2: shared-memory address of the prefetched partial sums (planes of 32 float4), 0 = read y */
 {
     const f32x2 sloped2 = f2_pack(a.sloped, a.sloped);
     f32x2 dd[CEXP / 2];
@@ -160,7 +161,10 @@ __device__ __forceinline__ void rb_finish(const RegBlockW<CIN, CEXP, COUT> &w, c
     f32x2 o[COUT / 2];
     if (PART >= 2) {
 #pragma unroll
-        for (int v = 0; v < COUT / 4; v++) { const float4 t = reinterpret_cast<const float4 *>(yp)[v]; o[2 * v] = f2_pack(t.x, t.y); o[2 * v + 1] = f2_pack(t.z, t.w); }
+        for (int v = 0; v < COUT / 4; v++) {
+            const float4 t = ypre ? rb_lds(ypre + v * 512) : reinterpret_cast<const float4 *>(yp)[v];
+            o[2 * v] = f2_pack(t.x, t.y); o[2 * v + 1] = f2_pack(t.z, t.w);
+        }
     }
     if (PART < 2) {
 #pragma unroll
@@ -285,8 +289,14 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
     constexpr int ST = 4, D = ST - 1;                  /* RING: slots per warp, rows of lookahead (four rows per trip of the row loop: slot numbers are constants) */
     constexpr uint32_t SLOT = (2 * CIN / 4) * 512;
     __shared__ float4 ring_s[RING ? REG_WARPS * ST * (2 * CIN / 4) * 32 : 1];
+    /* PART >= 2 (a later channel slice adds to the partial sums in y): the y row an odd input row closes travels in that row's
+       cp.async group -- the read-modify-write no longer starts with an exposed L2 round trip per output row */
+    constexpr bool YPRE = RING && PART >= 2;
+    constexpr uint32_t YSLOT = (COUT / 4) * 512;
+    __shared__ float4 yring_s[YPRE ? REG_WARPS * 2 * (COUT / 4) * 32 : 1];
     const int lane = threadIdx.x & 31;
     [[maybe_unused]] const uint32_t ring = sm100::smem_u32(ring_s) + (threadIdx.x >> 5) * ST * SLOT + lane * 16;
+    [[maybe_unused]] const uint32_t yring = sm100::smem_u32(yring_s) + (threadIdx.x >> 5) * 2 * YSLOT + lane * 16;
     const long strip = (long)blockIdx.x * REG_WARPS + (threadIdx.x >> 5);
     const int per_frame = a.nsx * a.nsy;
     if (strip >= (long)a.N * per_frame) return;
@@ -308,6 +318,14 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
     float xm0[CIN], xm1[CIN];                                                   /* the row after next: the loads run two rows ahead of their use */
     auto ring_issue = [&](int rn, int slot) {                                   /* ix0 and W are even: both pixels are inside or outside together, and contiguous */
         const bool rok = rn >= 0 && rn < a.H && rn <= r_last;
+        if constexpr (YPRE) {
+            if (!(slot & 1)) {                                                  /* even slots hold the odd input rows 2oy - 1: they close output row oy - 1 */
+                const int oyp = (rn - 1) >> 1; const bool yok = writes && oyp >= oy0 && oyp < oy1;
+                const float *yp = yf + ((long)min(max(oyp, 0), a.OH - 1) * a.OW + min(max(ox, 0), a.OW - 1)) * COUT;
+#pragma unroll
+                for (int v = 0; v < COUT / 4; v++) rb_cp16(yring + (slot >> 1) * YSLOT + v * 512, yp + 4 * v, yok);
+            }
+        }
         rb_ring_issue<CIN>(ring + slot * SLOT, xf + ((long)min(max(rn, 0), a.H - 1) * a.W + max(ix0, 0)) * CIN, rok && in0);
     };
     if constexpr (RING) {
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(REG_WARPS * 32, 3) k_block_reg_s2(const __grid
             odd_chunk(std::integral_constant<int, 0>(), rin, cur, nxt);
             if constexpr (CEXP > 8)  odd_chunk(std::integral_constant<int, 8>(), rin, cur, nxt);
             if constexpr (CEXP > 16) odd_chunk(std::integral_constant<int, 16>(), rin, cur, nxt);
-            if (writes && oy - 1 >= oy0 && oy - 1 < oy1) rb_finish<false, PART>(w, a, cur, dummy, yf + ((long)(oy - 1) * a.OW + ox) * COUT);
+            if (writes && oy - 1 >= oy0 && oy - 1 < oy1) rb_finish<false, PART>(w, a, cur, dummy, yf + ((long)(oy - 1) * a.OW + ox) * COUT, YPRE ? yring + (slot >> 1) * YSLOT : 0u);
         }
         {
             const int r = 2 * oy; const bool rin = r < a.H && oy < oy1;
