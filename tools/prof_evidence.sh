@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 150 --csv --
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches_bench.log 2>&1
 python tools/ncu_summary.py gpurun_out/${TAG}_launches.csv "ncu launch list of: python bench.py --steps 4 --warmup 3 --no-cpu-baseline (launches 400-549)" > gpurun_out/${TAG}_launches_summary.txt
 for spec in "k_block_mma:6:blockmma_L38" "k_block_mma:0:blockmma_L12" "k_block_mma:11:blockmma_L61" "k_block_reg_s2:0:blockreg_L9" "k_block_reg_s1:0:blockreg_L1" \
-            "k_stem_block:0:stemblock_L0" "k_dw5s1_tma:2:dw5_L125" "k_pw_tc:8:pwtc_L129" "k_upsample:0:upsample_L123"; do
+            "k_stem_block:0:stemblock_L0" "k_dw5s1_tma:2:dw5_L125" "k_pw_tc:6:pwtc_L129" "k_upsample:0:upsample_L123"; do
   k=${spec%%:*}; rest=${spec#*:}; s=${rest%%:*}; name=${rest#*:}
   bash tools/ncu_any.sh $k $s ${TAG}_ncu_$name > /dev/null 2>&1
   (python tools/ncu_raw.py gpurun_out/${TAG}_ncu_$name.ncu-rep; python tools/ncu_hot.py gpurun_out/${TAG}_ncu_$name.ncu-rep 12) > gpurun_out/${TAG}_ncu_$name.txt 2>&1
