@@ -470,7 +470,7 @@ def main():
         dist.all_reduce(t_eq, op=dist.ReduceOp.MAX)
         equal_e2e = {"value": world * B * KE / (float(t_eq[0]) * 1e-3), "unit": "frames/s", "ms_per_step": float(t_eq[0]) / KE,
                      "ms_per_step_rank0": ms_e2e / KE}
-        run_e2e(max(2, W // 2), n_e2e)                          # graph + staging for the new batch size
+        run_e2e(max(4, W // 2), n_e2e)                          # graph + staging for the new batch size (at least one pass over every pipeline slot)
         # one refinement: the rates move when the shares do (a rank that copies less leaves bandwidth to its neighbours)
         ms_c, _, _ = timed_e2e(max(5, KE // 3), n_e2e)
         rate = torch.tensor([n_e2e * max(5, KE // 3) / ms_c], dtype=torch.float64, device="cuda")
@@ -478,7 +478,7 @@ def main():
         shards = shard.weighted_shards(B * world, [float(r[0]) for r in rates], quantum=8, max_per_rank=BE)
         if shards[rank][1] - shards[rank][0] != n_e2e:
             n_e2e = shards[rank][1] - shards[rank][0]
-        run_e2e(max(2, W // 2), n_e2e)                          # every rank takes the same path whether or not its own share moved
+        run_e2e(max(4, W // 2), n_e2e)                          # every rank takes the same path whether or not its own share moved
         ms_e2e, wall_e2e, d2h = timed_e2e(KE, n_e2e)
     nboxes = sum(len(net.boxes(f)) for f in range(n_e2e))
     clocks = sampler.summary() if rank == 0 else None

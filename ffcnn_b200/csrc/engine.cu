@@ -1361,9 +1361,12 @@ int ffb_submit_u8(NET *net, const unsigned char *frames_host, int n, int w, int 
     const int slot = (int)(e->submitted % FFB_SLOTS);
     const size_t bytes = (size_t)n * h * pitch;
     if (bytes > e->slot_cap[slot]) {
+        /* sized for the largest batch the engine is planned for, so a caller that changes its batch size from one submit to the
+           next (rate-proportional shards) never comes back here: the reallocation synchronises both streams */
+        const size_t cap = std::max(bytes, (size_t)std::max(n, e->max_batch) * h * pitch);
         CK(cudaStreamSynchronize(e->stream)); CK(cudaStreamSynchronize(e->copy_stream));
         cudaFree(e->d_slot[slot]); e->d_slot[slot] = nullptr; e->slot_cap[slot] = 0;
-        CK(cudaMalloc(&e->d_slot[slot], bytes)); e->slot_cap[slot] = bytes;
+        CK(cudaMalloc(&e->d_slot[slot], cap)); e->slot_cap[slot] = cap;
     }
     if (e->submitted >= FFB_SLOTS) CK(cudaStreamWaitEvent(e->copy_stream, e->ev_free[slot], 0));     /* the batch that used this slot has consumed it */
     if (e->h2d_chunks > 1) {
