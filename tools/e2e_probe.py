@@ -53,3 +53,23 @@ def both(k):
 ms = timed(both, K); net.detect_finish()
 print("H2D under forward   %.4f ms/copy  %.1f GB/s ; forward+copy loop %.4f ms/step" % (both.copy_ms, dst.numel() / both.copy_ms / 1e6, ms))
 net.close()
+
+# ---- the same two loops on picture-derived frames (every frame yields candidates: the host decode + NMS has work) ----
+if os.environ.get("PICTURE", "1") == "1":
+    net = fb.Net(cfg, wts, W, H, device=0, max_batch=B)
+    raw = np.fromfile(os.path.join(fb.ASSETS, "test.bmp"), np.uint8)
+    bw, bh = int(raw[18:22].view("<u4")[0]), int(raw[22:26].view("<u4")[0]); bp = (bw * 3 + 3) & ~3
+    img = np.ascontiguousarray(raw[54:54 + bp * bh].reshape(bh, bp)[::-1])
+    pic = synth.shifted_frames_from(img, bw, bh, B, W, H).reshape(B, H, PITCH)
+    for b in range(NB): hv[b] = pic if b % 2 == 0 else pic[::-1]
+    dev = host.cuda()
+    resident(5); net.detect_finish()
+    print("picture: resident (filter enqueued, never read back)   %.4f ms/step" % timed(resident, K)); net.detect_finish()
+    def resident_read(k):
+        for i in range(k):
+            net.input_u8(dev[i % NB].data_ptr(), B, W, H, PITCH, on_device=True); net.forward(); net.detect_enqueue(); net.detect_finish()
+    print("picture: resident + blocking detect_finish each step  %.4f ms/step (boxes %d)" % (timed(resident_read, K), sum(len(net.boxes(f)) for f in range(B))))
+    e2e(5)
+    print("picture: e2e                                           %.4f ms/step" % timed(e2e, K))
+    t0 = time.time(); net.detect_finish(); print("picture: detect_finish alone (host decode + NMS, D2H)   %.4f ms" % (1e3 * (time.time() - t0)))
+    net.close()
