@@ -688,7 +688,8 @@ struct Candidate { int frame, key, cls; float bs, cs, tx, ty, tw, th; };
  * of their size).  (2) The survivors of the 32 cells of a warp are taken one by one by the WHOLE warp: coalesced read of
  * the class logits, shuffle arg-max, exact-form float confidence test by lane 0, append. */
 __global__ void k_yolo_filter(const float *__restrict__ head, int n, int cells, int ld, int classes, int head_index,
-                              int key_base, float thresh, Candidate *__restrict__ list, int *__restrict__ counter, int cap)
+                              int key_base, float thresh, Candidate *__restrict__ list, int *__restrict__ counter, int cap,
+                              int *host_count = nullptr)
 {
     pdl_trigger(); pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -738,6 +739,20 @@ __global__ void k_yolo_filter(const float *__restrict__ head, int n, int cells, 
         }
     }
     (void)head_index;
+    /* The launch for the LAST head also delivers the candidate count to the host: its last block to finish (ticket in counter[1])
+       writes it into pinned host memory.  A separate 4-byte device-to-host copy in the stream put a copy-engine hand-over (and its
+       semaphore round trip) between every two batches. */
+    if (host_count) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) {
+                __threadfence();
+                *reinterpret_cast<volatile int *>(host_count) = *reinterpret_cast<volatile int *>(counter);
+                __threadfence_system();
+            }
+        }
+    }
 }
 
 __global__ void k_fill(float *p, long n, float v)
