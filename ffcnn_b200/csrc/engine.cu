@@ -873,7 +873,8 @@ static int engine_attach_body(ffb_engine *e, NET *net)
     CK(cudaMemcpyAsync(e->d_packed, net->weight_buf, (size_t)net->weight_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     if (engine_prepare_weights(e) != 0) return -1;
     for (ffb_engine::DetSet &d : e->det) {
-        CK(cudaMalloc(&d.d_count, 2 * sizeof(int)));              /* [candidates, finished blocks of the last filter launch] */
+        CK(cudaMalloc(&d.d_count, 2 * sizeof(int)));              /* [candidates, finished blocks of the last filter launch]: zero between uses (the last block resets them) */
+        CK(cudaMemset(d.d_count, 0, 2 * sizeof(int)));
         CK(cudaMallocHost(&d.h_count, sizeof(int)));
         CK(cudaHostGetDevicePointer((void **)&d.h_count_dev, d.h_count, 0));      /* the last filter launch writes the count here */
         CK(cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming));
@@ -1247,12 +1248,14 @@ int ffb_detect_enqueue(NET *net)
         d.cap = cap;
     }
     d.n = n; d.s1 = e->s1; d.s2 = e->s2;
-    CK(cudaMemsetAsync(d.d_count, 0, 2 * sizeof(int), e->stream));
     if (heads.empty()) *d.h_count = 0;                         /* no yolo layer: nothing will write the count */
     size_t hk = 0;
     for (const Head &h : heads) {
         const LAYER *yl = net->layer_list + h.layer; const Tens &t = e->outs[h.layer - 1];
-        if (t.c != 3 * (5 + yl->class_num)) { ffb_set_error("yolo layer %d: %d channels, expected %d", h.layer, t.c, 3 * (5 + yl->class_num)); return -1; }
+        if (t.c != 3 * (5 + yl->class_num)) {
+            cudaMemsetAsync(d.d_count, 0, 2 * sizeof(int), e->stream);       /* an earlier head may have counted: leave the set clean */
+            ffb_set_error("yolo layer %d: %d channels, expected %d", h.layer, t.c, 3 * (5 + yl->class_num)); return -1;
+        }
         const long threads = (long)n * h.cells;                 /* one thread per grid cell */
         CK(launch_pdl(k_yolo_filter, dim3((int)((threads + 255) / 256)), dim3(256), 0, e->stream, (const float *)t.p, n, h.cells, t.ld, yl->class_num, 0, h.key_base,
                       yl->ignore_thres, d.d_cand, d.d_count, d.cap, ++hk == heads.size() ? d.h_count_dev : (int *)nullptr));

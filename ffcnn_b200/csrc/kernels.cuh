@@ -750,6 +750,7 @@ __global__ void k_yolo_filter(const float *__restrict__ head, int n, int cells, 
                 __threadfence();
                 *reinterpret_cast<volatile int *>(host_count) = *reinterpret_cast<volatile int *>(counter);
                 __threadfence_system();
+                counter[0] = 0; counter[1] = 0;            /* ready for the next batch that uses this detection set: no memset in the stream either */
             }
         }
     }
