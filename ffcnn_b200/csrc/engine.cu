@@ -877,6 +877,7 @@ static int engine_attach_body(ffb_engine *e, NET *net)
         CK(cudaMemset(d.d_count, 0, 2 * sizeof(int)));
         CK(cudaMallocHost(&d.h_count, sizeof(int)));
         CK(cudaHostGetDevicePointer((void **)&d.h_count_dev, d.h_count, 0));      /* the last filter launch writes the count here */
+        *d.h_count = 0;
         CK(cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming));
     }
     CK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
