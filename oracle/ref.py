@@ -30,6 +30,15 @@ _libs: dict = {}
 def lib(variant: str = "v6"):
     if variant not in _libs:
         orc.build()
+        # The reference reads memory it never wrote: im2row fills fs*fs*c lanes of each ALIGN(fs*fs*c, 4)-float scratch row and the dot
+        # product runs over all of them (conv-v6.c:9-42; the stem has 27 taps in rows of 28), relying on the filter's pad lane being 0.
+        # The scratch comes from malloc: in a fresh process it is zero, inside a long-lived Python process it can hold a NaN, and
+        # NaN * 0 poisons column 0 of layer 0 (seen as a test that failed one run in ten).  glibc's M_PERTURB = 255 makes every
+        # allocation start as zero bytes -- the state the reference's own binary sees -- without touching its sources or build.
+        try:
+            C.CDLL(None).mallopt(C.c_int(-6), C.c_int(255))
+        except Exception:
+            pass
         L = C.CDLL(os.path.join(REFDIR, f"libffcnn_ref_{variant}.so"), mode=os.RTLD_LOCAL)
         fp = C.POINTER(C.c_float)
         L.net_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
