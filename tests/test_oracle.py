@@ -146,6 +146,28 @@ def test_live_reference_bit_exact(assets):
     assert raw.tobytes() == rraw.tobytes() and fin.tobytes() == rfin.tobytes()
 
 
+@pytest.mark.skipif(not ref.available("v6_O2"), reason="oracle/_ref not built (needs /root/reference)")
+def test_live_reference_is_immune_to_heap_garbage(assets):
+    """The reference's im2row leaves the pad lane of its scratch rows unwritten (conv-v6.c:9-42: 27 taps in rows of 28 for the stem) and
+    multiplies it by the filter's zero pad -- NaN * 0 = NaN when malloc hands back memory that held NaNs.  oracle/ref.py makes
+    allocations start as zero bytes (glibc M_PERTURB), the state the reference's own fresh process sees: with the heap deliberately
+    salted with NaNs the stem output must still be finite and bit-equal to the restatement."""
+    cfg, wts, _ = assets
+    ref.lib("v6_O2")                                                  # M_PERTURB is set when the library is first loaded
+    for _ in range(8):                                               # leave freed chunks full of NaNs in several size classes
+        junk = [np.full(n, np.nan, np.float32) for n in (28 * 160, 28 * 320, 4096, 65536, 3 * 322 * 322)]
+        del junk
+    fr = synth.frames_u8(1, seed0=0x5EED)[0]
+    rn = ref.RefNet(cfg, wts, 0, 0, "v6_O2")
+    rn.input_bgr(fr, 320, 320)
+    routs, _, _ = rn.forward_dump(want={0})
+    assert np.isfinite(routs[0]).all()
+    layers = orc.load_net(cfg, wts, 0, 0)
+    xo, s1, s2 = orc.net_input(fr, 320, 320, 320, 320)
+    outs, _, _ = orc.forward(layers, xo, s1, s2, True)
+    assert np.array_equal(bits(outs[0]), bits(routs[0]))
+
+
 @pytest.mark.skipif(not ref.available("v0"), reason="oracle/_ref not built (needs /root/reference)")
 def test_live_reference_random_shapes_bit_exact():
     """160 seeded random operator shapes (ragged maps from 4x4 up, 1x1 / 3x3 s1,s2 / 5x5, dense, grouped, depthwise, all three
