@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -1293,22 +1294,44 @@ int ffb_detect_finish(NET *net)
     std::sort(h_cand, h_cand + cnt, [](const Candidate &a, const Candidate &b) { return a.frame != b.frame ? a.frame < b.frame : a.key < b.key; });
     e->boxes.assign(n, std::vector<BBOX>()); e->raw.assign(n, std::vector<BBOX>());
     const int netw = net->layer_list[0].w, neth = net->layer_list[0].h;
-    for (int k = 0; k < cnt; k++) {
-        const Candidate &c = h_cand[k];
-        if (c.frame < 0 || c.frame >= n) continue;
-        const Head *hd = nullptr;
-        for (const Head &h : heads) if (c.key >= h.key_base && c.key < h.key_base + h.cells * 3) hd = &h;
-        if (!hd) continue;
-        ffb_candidate hc; hc.frame = c.frame; hc.key = c.key; hc.cls = c.cls; hc.bs = c.bs; hc.cs = c.cs; hc.tx = c.tx; hc.ty = c.ty; hc.tw = c.tw; hc.th = c.th;
-        BBOX b; const int rel = c.key - hd->key_base;
-        if ((int)e->raw[c.frame].size() < net->bbox_max &&
-            ffb_decode_candidate(net->layer_list + hd->layer, netw, neth, hd->gw, hd->gh, rel / 3, rel % 3, &hc, &b)) e->raw[c.frame].push_back(b);
+    /* exact decode (the reference's double-precision exp arithmetic, host_decode.c) + NMS of the frames [f0, f1), whose candidates are
+       h_cand[k0, k1): frames are independent, every frame's vectors are touched by one caller only */
+    auto decode_range = [&](int k0, int k1, int f0, int f1) {
+        for (int k = k0; k < k1; k++) {
+            const Candidate &c = h_cand[k];
+            if (c.frame < 0 || c.frame >= n) continue;
+            const Head *hd = nullptr;
+            for (const Head &h : heads) if (c.key >= h.key_base && c.key < h.key_base + h.cells * 3) hd = &h;
+            if (!hd) continue;
+            ffb_candidate hc; hc.frame = c.frame; hc.key = c.key; hc.cls = c.cls; hc.bs = c.bs; hc.cs = c.cs; hc.tx = c.tx; hc.ty = c.ty; hc.tw = c.tw; hc.th = c.th;
+            BBOX b; const int rel = c.key - hd->key_base;
+            if ((int)e->raw[c.frame].size() < net->bbox_max &&
+                ffb_decode_candidate(net->layer_list + hd->layer, netw, neth, hd->gw, hd->gh, rel / 3, rel % 3, &hc, &b)) e->raw[c.frame].push_back(b);
+        }
+        for (int f = f0; f < f1; f++) {
+            e->boxes[f] = e->raw[f];
+            const int m = ffb_nms(e->boxes[f].data(), (int)e->boxes[f].size(), 0.5f, 1, d.s1, d.s2);
+            e->boxes[f].resize(m);
+        }
+    };
+    /* A batch of picture frames brings thousands of candidates, six libm exp() each: 0.76 ms per 256 frames on one core
+       (tools/e2e_probe.py).  Large batches are split at frame boundaries over a few short-lived threads; the result is the same
+       vectors in the same order.  Small candidate sets (and FFCNN_DECODE_THREADS=1) stay on the calling thread. */
+    static const int max_threads = [] { const char *v = getenv("FFCNN_DECODE_THREADS"); const int t = v ? atoi(v) : 4; return t < 1 ? 1 : t > 16 ? 16 : t; }();
+    const int T = (cnt >= 2048 && n >= 8) ? std::min(max_threads, n / 4) : 1;
+    if (T <= 1) { decode_range(0, cnt, 0, n); return 0; }
+    std::vector<int> ks(T + 1), fs(T + 1);
+    ks[0] = 0; fs[0] = 0; ks[T] = cnt; fs[T] = n;
+    for (int t = 1; t < T; t++) {
+        int k = std::max(ks[t - 1], (int)((long)cnt * t / T));
+        while (k > 0 && k < cnt && h_cand[k].frame == h_cand[k - 1].frame) k++;          /* to the next frame boundary */
+        ks[t] = k;
+        fs[t] = k < cnt ? std::min(std::max(h_cand[k].frame, fs[t - 1]), n) : n;       /* candidates are sorted by frame */
     }
-    for (int f = 0; f < n; f++) {
-        e->boxes[f] = e->raw[f];
-        const int m = ffb_nms(e->boxes[f].data(), (int)e->boxes[f].size(), 0.5f, 1, d.s1, d.s2);
-        e->boxes[f].resize(m);
-    }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back(decode_range, ks[t], ks[t + 1], fs[t], fs[t + 1]);
+    decode_range(ks[0], ks[1], fs[0], fs[1]);
+    for (std::thread &th : pool) th.join();
     return 0;
 }
 

@@ -383,6 +383,44 @@ print("DIGEST", h.hexdigest())
     assert digests[0] == digests[1]
 
 
+def test_threaded_host_decode_returns_the_same_boxes(assets):
+    """ffb_detect_finish splits the exact decode + NMS of a large candidate set (thousands of candidates: picture-derived frames) at
+    frame boundaries over a few host threads.  The boxes, raw boxes and their order must be those of the single-threaded decode
+    (FFCNN_DECODE_THREADS=1), on a batch that is not a multiple of the thread count and through the pipelined calls too."""
+    import subprocess
+    code = r"""
+import sys, hashlib
+sys.path.insert(0, %r)
+import numpy as np
+import ffcnn_b200 as fb
+from ffcnn_b200 import synth
+from oracle import ref
+cfg, wts = fb.default_model()
+img, w, h = ref.load_bmp(fb.ASSETS + "/test.bmp")
+N = 203
+fr = np.ascontiguousarray(synth.shifted_frames_from(img, w, h, N))
+hsh = hashlib.sha256(); total = 0
+net = fb.Net(cfg, wts, 0, 0, device=0, max_batch=N)
+net.detect_batch_u8(fr, N, 320, 320, 960)
+total = (net.last_d2h_bytes() - 4) // 36                     # candidates the GPU filter passed to the host
+for f in range(N):
+    hsh.update(net.boxes(f).tobytes()); hsh.update(net.boxes(f, raw=True).tobytes())
+net.submit_u8(fr, N, 320, 320, 960); net.submit_u8(fr[::-1].copy(), N, 320, 320, 960)
+for _ in range(2):
+    net.collect()
+    for f in range(N): hsh.update(net.boxes(f).tobytes())
+net.close()
+print("DIGEST", hsh.hexdigest(), total)
+""" % REPO
+    out = []
+    for t in ("1", "4", "3"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, FFCNN_DECODE_THREADS=t), timeout=280)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        out.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert out[0] == out[1] == out[2]
+    assert int(out[0].split()[2]) >= 2048                    # enough candidates for the threaded path to have run
+
+
 def test_dw5_exact_mode_matches_conv_v0(assets, oracle_layers):
     cfg, wts, bmp = assets
     img, w, h = ref.load_bmp(bmp)
