@@ -1329,7 +1329,10 @@ int ffb_detect_finish(NET *net)
         fs[t] = k < cnt ? std::min(std::max(h_cand[k].frame, fs[t - 1]), n) : n;       /* candidates are sorted by frame */
     }
     std::vector<std::thread> pool;
-    for (int t = 1; t < T; t++) pool.emplace_back(decode_range, ks[t], ks[t + 1], fs[t], fs[t + 1]);
+    for (int t = 1; t < T; t++) {
+        try { pool.emplace_back(decode_range, ks[t], ks[t + 1], fs[t], fs[t + 1]); }
+        catch (...) { decode_range(ks[t], ks[t + 1], fs[t], fs[t + 1]); }          /* no thread to be had: this range on the calling thread (nothing may unwind through the C ABI) */
+    }
     decode_range(ks[0], ks[1], fs[0], fs[1]);
     for (std::thread &th : pool) th.join();
     return 0;
